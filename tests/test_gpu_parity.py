@@ -1,0 +1,252 @@
+"""GPU parity tests: the CUDA path (through the C ABI, libzpixcuda.so) against the CPU oracle on the
+same bytes.  Bit-exact: integer/byte work, no tolerance anywhere."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402
+from tools import synth_jpeg as S  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def jpeg():
+    from zpix_b200 import jpeg as J  # fails loudly if libzpixcuda.so is missing
+
+    return J
+
+
+@pytest.fixture(scope="module")
+def ctx(jpeg):
+    c = jpeg.Context()
+    yield c
+    c.close()
+
+
+def _read(d, name):
+    with open(os.path.join(d, name), "rb") as f:
+        return f.read()
+
+
+def _oracle_rgba(data):
+    try:
+        return O.decode(data).rgbaPixels(), "ok"
+    except O.OracleError as e:
+        return None, e.name
+
+
+def _gpu_batch(jpeg, ctx, datas):
+    with jpeg.Batch(ctx, datas) as b:
+        b.upload()
+        b.decode()
+        outs, st = b.fetch_rgba()
+        t = b.timing(0)
+    return outs, st, t
+
+
+def _assert_same(jpeg, ctx, datas, names=None):
+    outs, st, _ = _gpu_batch(jpeg, ctx, datas)
+    for i, d in enumerate(datas):
+        want, err = _oracle_rgba(d)
+        tag = names[i] if names else i
+        if want is None:
+            assert st[i] != 0, f"{tag}: oracle fails with {err}, GPU path succeeded"
+            assert jpeg.lib.zpx_error_name(st[i]).decode() == err, f"{tag}: {err} vs {st[i]}"
+        else:
+            assert st[i] == 0, f"{tag}: status {st[i]} {jpeg.lib.zpx_error_name(st[i]).decode()}"
+            assert outs[i].shape == want.shape, tag
+            if not np.array_equal(outs[i], want):
+                bad = np.argwhere(outs[i] != want)
+                raise AssertionError(f"{tag}: {len(bad)} bytes differ, first at {bad[0]}: gpu {outs[i][tuple(bad[0])]} want {want[tuple(bad[0])]}")
+
+
+BASELINE_FIXTURES = [
+    "video-001.jpeg", "video-001.q50.410.jpeg", "video-001.q50.411.jpeg", "video-001.q50.420.jpeg",
+    "video-001.q50.422.jpeg", "video-001.q50.440.jpeg", "video-001.q50.444.jpeg", "video-005.gray.jpeg",
+    "video-005.gray.q50.jpeg", "video-005.gray.q50.2x2.jpeg", "video-001.221212.jpeg", "video-001.restart2.jpeg",
+    "video-001.rgb.jpeg", "video-001.cmyk.jpeg",
+]
+
+
+def test_reference_fixtures_one_batch(jpeg, ctx, fixtures_dir, golden_dir):
+    """Every baseline fixture of the reference, in one mixed batch; RGBA == oracle == committed sha256."""
+    datas = [_read(fixtures_dir, n) for n in BASELINE_FIXTURES]
+    _assert_same(jpeg, ctx, datas, BASELINE_FIXTURES)
+    outs, st, _ = _gpu_batch(jpeg, ctx, datas)
+    gold = json.load(open(os.path.join(golden_dir, "rgba_sha256.json")))
+    for n, o in zip(BASELINE_FIXTURES, outs):
+        assert hashlib.sha256(o.tobytes()).hexdigest() == gold[n], n
+
+
+def test_iceberg_cfg1(jpeg, ctx, fixtures_dir, golden_dir):
+    """BASELINE.json configs[0]: iceberg.jpg, 2048x2048 4:4:4, no DRI, optimised Huffman tables."""
+    data = _read(fixtures_dir, "iceberg.jpg")
+    outs, st, _ = _gpu_batch(jpeg, ctx, [data])
+    assert st == [0]
+    gold = json.load(open(os.path.join(golden_dir, "rgba_sha256.json")))
+    assert hashlib.sha256(outs[0].tobytes()).hexdigest() == gold["iceberg.jpg"]
+
+
+def test_padded_rst_and_error_kinds(jpeg, ctx, fixtures_dir, golden_dir):
+    """decoder.zig:2029-2279 through the GPU path: padded RST decodes; junk before RST1 is skipped
+    (7 PASS splices) or raises BadRSTMarker (3 FAIL splices); truncations raise UnexpectedEof."""
+    datas = [_read(golden_dir, "padded_rst_issue28717.jpg"), _read(golden_dir, "fuzz_issue10413.bin")]
+    base = _read(fixtures_dir, "video-001.restart2.jpeg")
+    for infix in [b"", b"\x00", b"\x61", b"\x61\x62\x63\xff\x00\x64", b"\xff", b"\xff\x00",
+                  b"\xff\xff\xff\x00\xff\x00\x00\xff\xff\xff", b"\xff\x03", b"\xff\xd5", b"\xff\xff\xd5"]:
+        datas.append(base[:2816] + infix + base[2816:])
+    g = _read(fixtures_dir, "video-005.gray.q50.jpeg")
+    i = g.index(b"\xff\xda") + 2
+    datas += [g[:k] for k in range(i, i + 10)]
+    datas.append(_read(fixtures_dir, "video-001.jpeg")[:24])
+    # truncation in the middle of the entropy-coded data, and a file without EOI
+    full = _read(fixtures_dir, "video-001.q50.420.jpeg")
+    datas += [full[: len(full) // 2], full[:-2], full[:-1], b"", b"\xff", b"\x89PNG"]
+    _assert_same(jpeg, ctx, datas)
+
+
+def test_corrupt_image_inside_good_batch(jpeg, ctx, fixtures_dir):
+    good = _read(fixtures_dir, "video-001.q50.420.jpeg")
+    bad = bytearray(good)
+    k = bad.index(b"\xff\xda") + 40
+    bad[k:k + 8] = b"\xff\xd9\x00\x00\x00\x00\x00\x00"  # marker in the middle of the scan
+    datas = [good, bytes(bad), good]
+    _assert_same(jpeg, ctx, datas)
+
+
+def test_coefficients_match_oracle_tap(jpeg, ctx, fixtures_dir):
+    """K1 alone: int16 coefficient blocks == the oracle's pre-dequantisation blocks, scan order."""
+    for name in ["video-001.q50.420.jpeg", "video-001.restart2.jpeg", "video-005.gray.jpeg", "video-001.jpeg"]:
+        data = _read(fixtures_dir, name)
+        _, recs = O.decode(data, tap=True)
+        with jpeg.Batch(ctx, [data]) as b:
+            b.upload()
+            b.decode()
+            co = b.coefficients(0)
+        assert co.shape[0] == recs.shape[0], name
+        assert np.array_equal(co.astype(np.int32), recs[:, 3:]), name
+
+
+SYNTH_CASES = [
+    # (w, h, kwargs)
+    (1, 1, dict(subsampling="4:2:0")),
+    (7, 9, dict(subsampling="4:4:4")),
+    (17, 33, dict(subsampling="4:2:2")),
+    (33, 17, dict(subsampling="4:2:0", restart_blocks=1)),
+    (250, 131, dict(subsampling="4:2:0", restart_blocks=7)),
+    (250, 131, dict(subsampling="4:2:0", restart_rows=1)),
+    (250, 131, dict(subsampling="4:2:0", restart_blocks=5000)),
+    (640, 480, dict(subsampling="4:2:0", restart_rows=1)),
+    (640, 480, dict(subsampling="4:2:2", restart_rows=1)),
+    (640, 480, dict(subsampling="4:4:4", restart_rows=2)),
+    (641, 479, dict(subsampling="4:4:4")),
+    (642, 478, dict(subsampling="4:2:0")),
+    (643, 477, dict(subsampling="4:2:2")),
+    (512, 512, dict(mode="L")),
+    (513, 511, dict(mode="L", restart_rows=1)),
+    (1920, 1080, dict(subsampling="4:2:0", restart_rows=1)),
+    (3840, 2160, dict(subsampling="4:2:2", restart_rows=1)),
+    (300, 200, dict(mode="CMYK")),
+    (300, 200, dict(mode="CMYK", ycck=True)),
+    (300, 200, dict(mode="CMYK", restart_rows=1)),
+    (320, 240, dict(subsampling="4:2:0", quality=100)),
+    (320, 240, dict(subsampling="4:4:4", quality=5)),
+]
+
+
+def test_synthetic_shapes(jpeg, ctx):
+    """Odd sizes, every sampling Pillow emits, DRI in {1 block, 7, one row, > MCU count}, both table kinds."""
+    datas, names = [], []
+    for k, (w, h, kw) in enumerate(SYNTH_CASES):
+        for seed in (k * 2, k * 2 + 1):  # even: Annex-K tables, odd: optimised tables
+            datas.append(S.encode(90000 + seed, w, h, **kw))
+            names.append(f"{w}x{h} {kw} seed{seed}")
+    _assert_same(jpeg, ctx, datas, names)
+
+
+def test_cfg2_sample(jpeg, ctx):
+    """BASELINE.json configs[1] at reduced count: 1920x1080 4:2:0, DRI = one MCU row."""
+    datas = S.make_batch(2, 16, 1920, 1080, subsampling="4:2:0", restart_rows=1)
+    _assert_same(jpeg, ctx, datas)
+
+
+def test_cfg3_sample(jpeg, ctx):
+    """configs[2] at reduced count: 512x512 gray + 4:4:4, no DRI."""
+    datas = S.make_batch(3, 8, 512, 512, mode="L") + S.make_batch(3, 8, 512, 512, first=8, subsampling="4:4:4")
+    _assert_same(jpeg, ctx, datas)
+
+
+def test_cfg4_sample(jpeg, ctx):
+    """configs[3] at reduced count: 3840x2160 4:2:2, with and without DRI."""
+    datas = S.make_batch(4, 2, 3840, 2160, subsampling="4:2:2", restart_rows=1)
+    datas += S.make_batch(4, 1, 3840, 2160, first=2, subsampling="4:2:2")
+    _assert_same(jpeg, ctx, datas)
+
+
+def test_fused_equals_generic(jpeg, fixtures_dir):
+    """The fused kernel and the unfused IDCT->planes->colour path give identical bytes."""
+    datas = [_read(fixtures_dir, n) for n in BASELINE_FIXTURES] + S.make_batch(2, 2, 1920, 1080, subsampling="4:2:0", restart_rows=1)
+    c1, c2 = jpeg.Context(), jpeg.Context()
+    c2.set_option(2, 1)
+    a, sa, _ = _gpu_batch(jpeg, c1, datas)
+    b, sb, _ = _gpu_batch(jpeg, c2, datas)
+    assert sa == sb
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    c1.close()
+    c2.close()
+
+
+def test_native_variant_matches_reference_planes(jpeg, fixtures_dir):
+    """jpeg.load mirror (N2): .YCbCr / .Gray planes with makeImg's exact strides, on every block whose
+    origin is inside bounds (the reference's own `check`, decoder.zig:1803-1836)."""
+    for name in ["video-001.q50.420.jpeg", "video-001.q50.422.jpeg", "video-001.jpeg", "video-005.gray.jpeg",
+                 "video-001.221212.jpeg", "video-001.q50.411.jpeg"]:
+        data = _read(fixtures_dir, name)
+        ref = O.decode(data)
+        img = jpeg.loadFromBuffer(data)
+        assert img.tag == ref.variant_name
+        r = img.bounds()
+        assert (r.dX(), r.dY()) == (ref.width, ref.height)
+        if img.tag == "Gray":
+            got = img.Gray.pixels.reshape(-1, img.Gray.stride)
+            assert img.Gray.stride == ref.stride
+            assert np.array_equal(got[: ref.height, : ref.width], ref.pix[: ref.height, : ref.width])
+        else:
+            m = img.YCbCr
+            assert (m.y_stride, m.c_stride) == (ref.y_stride, ref.c_stride)
+            assert m.subsample_ratio.name == ref.subsample_ratio
+            assert np.array_equal(m.y.reshape(-1, m.y_stride), ref.y)
+            assert np.array_equal(m.cb.reshape(-1, m.c_stride), ref.cb)
+            assert np.array_equal(m.cr.reshape(-1, m.c_stride), ref.cr)
+        assert np.array_equal(img.rgbaPixels().reshape(ref.height, ref.width, 4), ref.rgbaPixels())
+
+
+def test_empty_batch_and_api_contract(jpeg, ctx):
+    outs, st, _ = _gpu_batch(jpeg, ctx, [])
+    assert outs == [] and st == []
+    res = jpeg.decodeBatch([b"not a jpeg", b""], ctx)
+    assert all(isinstance(r, jpeg.JpegError) for r in res)
+    assert res[0].name == "InvalidSOIMarker" and res[1].name == "UnexpectedEof"
+
+
+def test_idct_and_colour_exhaustive_blocks(jpeg, ctx):
+    """Property test of K2 through real files: random coefficient content at the extremes of the 8-bit
+    range (quality 100 and quality 1 images of pure noise) still matches the oracle bit for bit."""
+    rng = np.random.default_rng(5)
+    from PIL import Image
+    import io
+
+    datas = []
+    for q in (1, 30, 100):
+        for sub in ("4:4:4", "4:2:0"):
+            px = rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)
+            px[::2] = 255 - px[::2] // 8  # harsh edges -> large coefficients, saturating IDCT outputs
+            buf = io.BytesIO()
+            Image.fromarray(px, "RGB").save(buf, "JPEG", quality=q, subsampling=sub)
+            datas.append(buf.getvalue())
+    _assert_same(jpeg, ctx, datas)

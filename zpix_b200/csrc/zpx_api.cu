@@ -1,0 +1,1004 @@
+// zpx_api.cu -- the extern "C" boundary (include/zpix_cuda.h): context, host scheduler,
+// descriptor building, uploads, kernel launches, result hand-over.  No decode arithmetic lives
+// here and there is no CPU decode path: without a CUDA device every decode entry point fails.
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "zpx_internal.h"
+#include "zpx_kernels.h"
+
+using namespace zpx;
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+namespace {
+
+template <typename F>
+void parallel_for(size_t n, size_t min_chunk, F fn) {
+    size_t hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    if (hw > 64) hw = 64;
+    size_t nt = std::min(hw, (n + min_chunk - 1) / std::max<size_t>(min_chunk, 1));
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([&] {
+            for (;;) {
+                size_t i0 = next.fetch_add(min_chunk);
+                if (i0 >= n) break;
+                size_t i1 = std::min(n, i0 + min_chunk);
+                for (size_t i = i0; i < i1; i++) fn(i);
+            }
+        });
+    for (auto& t : th) t.join();
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostBuf {  // pinned
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct DeviceCtx {
+    int dev = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {nullptr};
+    DevBuf blob, coef, out, planes, desc, status;
+    HostBuf stage, hdesc, hstatus;
+};
+
+// images of one format that take the fused kernel in one launch
+struct FusedGroup {
+    int h, v, nc;
+    int tmax = 0;
+    std::vector<ZpxTileDev> tiles;
+    size_t tiles_off = 0;  // byte offset of the tile table inside the descriptor buffer
+    uint64_t bytes = 0;    // algorithmic bytes: 128 B + 4 P over the group's images
+};
+
+struct DevicePlan {
+    std::vector<int> images;  // batch indices scheduled here, in order
+    std::vector<ZpxImageDev> imgs;
+    std::vector<ZpxScanDev> scans;
+    std::vector<ZpxIntervalDev> ivs;
+    std::vector<ZpxHuffDev> huff;
+    std::vector<ZpxQuantDev> quant;
+    std::vector<FusedGroup> groups;
+    std::vector<uint32_t> generic;  // device image indices on the unfused path
+    int generic_max_blocks = 0;
+    size_t generic_max_pixels = 0;
+    // blob assembly: (batch image, src offset, length, dst offset)
+    struct Copy { int img; size_t src, len, dst; };
+    std::vector<Copy> copies;
+    size_t blob_bytes = 0, coef_blocks = 0, out_bytes = 0, plane_bytes = 0;
+    // descriptor buffer layout (byte offsets)
+    size_t off_imgs = 0, off_scans = 0, off_ivs = 0, off_huff = 0, off_quant = 0, off_generic = 0, desc_bytes = 0;
+    std::vector<uint64_t> out_off, plane_off0;  // per device image
+    zpx_timing timing;
+    bool uploaded = false, decoded = false;
+};
+
+}  // namespace
+
+struct zpx_ctx {
+    std::vector<DeviceCtx> devs;
+    int last_cuda = 0;
+    std::string last_cuda_str;
+    std::atomic<uint64_t> launches{0};
+    int64_t opt_entropy_mode = 0, opt_force_generic = 0, opt_subseq = 0;
+    bool busy = false;
+};
+
+struct zpx_batch {
+    zpx_ctx* ctx = nullptr;
+    int n = 0;
+    std::vector<const uint8_t*> bufs;
+    std::vector<size_t> lens;
+    std::vector<ZpxParsed> parsed;
+    std::vector<int> dev_of;      // device index per image (-1: not decoded)
+    std::vector<int> slot_of;     // index inside the device's image list
+    std::vector<int32_t> status;  // final status per image
+    std::vector<DevicePlan> plans;
+    bool status_ready = false;
+};
+
+namespace {
+
+int cuda_fail(zpx_ctx* c, cudaError_t e) {
+    c->last_cuda = (int)e;
+    c->last_cuda_str = cudaGetErrorString(e);
+    return ZPX_E_CUDA;
+}
+#define CU(ctx, call)                                \
+    do {                                             \
+        cudaError_t e__ = (call);                    \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__); \
+    } while (0)
+
+const char* const kErrNames[] = {
+    "ok", "UnexpectedEof", "InvalidSOIMarker", "ShortSegmentLength", "UnknownMarker", "UnsupportedMarker",
+    "MissingSosMarker", "MultipleSofMarkers", "NumberComponents", "Precision", "SofWrongLength",
+    "RepeatedComponentIdentifier", "BadTqValue", "LumaChromaSubSamplingRatio", "DriWrongLength", "BadPqValue",
+    "DqtWrongLength", "MissingFF00", "UnsupportedColorModel", "UninitializedHuffmanTable", "BadHuffmanCode",
+    "DhtWrongLength", "BadTcValue", "BadThValue", "HuffZeroLength", "HuffTooLong", "SosWrongLength",
+    "UnknownComponentSelector", "BadTdValue", "BadTaValue", "SamplingFactorsTooLarge", "BadSpectralSelection",
+    "ProgressiveACCoefficientsForMoreThanOneComponent", "BadSuccessiveApproximation", "ExcessiveDCComponent",
+    "UnexpectedHuffmanCode", "TooManyCoefficients", "BadRSTMarker", "CreateImageFailed", "UnsupportedComponent",
+    "InvalidImageType", "ConfigOnly", "OutOfMemory",
+};
+
+// can this image be decoded on the GPU by this build?
+int unsupported_reason(const ZpxParsed& p) {
+    if (p.progressive) return ZPX_E_UNSUPPORTED_STREAM;
+    return 0;
+}
+
+bool fused_eligible(const ZpxParsed& p) {
+    if (p.progressive || p.scans.size() != 1) return false;
+    const ZpxScanHost& s = p.scans[0];
+    if (p.ncomp == 1) return p.mode == ZPX_MODE_GRAY && s.ncomp == 1;
+    if (p.ncomp != 3 || p.mode != ZPX_MODE_YCBCR || s.ncomp != 3) return false;
+    for (int i = 0; i < 3; i++)
+        if (s.comp[i] != i) return false;
+    if (p.h[1] != 1 || p.v[1] != 1 || p.h[2] != 1 || p.v[2] != 1) return false;
+    const int hv = p.h[0] << 4 | p.v[0];
+    return hv == 0x11 || hv == 0x21 || hv == 0x22 || hv == 0x12 || hv == 0x41 || hv == 0x42;
+}
+
+struct TableDedup {
+    std::map<std::string, int> huff_ix, quant_ix;
+    int add_huff(const ZpxHuffHost& h, std::vector<ZpxHuffDev>& out) {
+        std::string key((const char*)h.counts, 16);
+        key.append((const char*)h.vals, 256);
+        key.push_back(h.defined ? 1 : 0);
+        auto it = huff_ix.find(key);
+        if (it != huff_ix.end()) return it->second;
+        ZpxHuffDev d;
+        int malformed = 0;
+        zpx_build_huff_dev(h, &d, &malformed);
+        out.push_back(d);
+        int ix = (int)out.size() - 1;
+        huff_ix.emplace(std::move(key), ix);
+        return ix;
+    }
+    int add_quant(const int32_t* zz, std::vector<ZpxQuantDev>& out) {
+        std::string key((const char*)zz, 64 * sizeof(int32_t));
+        auto it = quant_ix.find(key);
+        if (it != quant_ix.end()) return it->second;
+        ZpxQuantDev d;
+        for (int z = 0; z < 64; z++) d.q[zpx_unzig[z]] = zz[z];
+        out.push_back(d);
+        int ix = (int)out.size() - 1;
+        quant_ix.emplace(std::move(key), ix);
+        return ix;
+    }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Build everything one device needs for its share of the batch.
+void build_plan(zpx_batch* b, int di) {
+    DevicePlan& pl = b->plans[di];
+    TableDedup dd;
+    const bool force_generic = b->ctx->opt_force_generic != 0;
+    std::map<int, int> group_ix;  // (h<<8|v<<4|nc) -> index
+    for (size_t k = 0; k < pl.images.size(); k++) {
+        const int bi = pl.images[k];
+        const ZpxParsed& p = b->parsed[bi];
+        ZpxImageDev im;
+        memset(&im, 0, sizeof(im));
+        im.width = p.width;
+        im.height = p.height;
+        im.mxx = p.mxx;
+        im.myy = p.myy;
+        im.ncomp = p.ncomp;
+        im.mode = p.mode;
+        im.progressive = p.progressive ? 1 : 0;
+        im.hmax = p.h[0];
+        im.vmax = p.v[0];
+        im.status_slot = (uint32_t)k;
+        int bpm = 0;
+        for (int c = 0; c < p.ncomp; c++) {
+            im.h[c] = (uint8_t)p.h[c];
+            im.v[c] = (uint8_t)p.v[c];
+            im.blk_off[c] = (uint32_t)bpm;
+            bpm += p.h[c] * p.v[c];
+            im.comp_bw[c] = p.mxx * p.h[c];
+            im.comp_bh[c] = p.myy * p.v[c];
+        }
+        // one interleaved scan holding every component in frame order -> interleaved layout
+        bool single = !p.progressive && p.scans.size() == 1 && p.scans[0].ncomp == p.ncomp;
+        if (single)
+            for (int i = 0; i < p.ncomp; i++) single = single && p.scans[0].comp[i] == i;
+        im.layout = single ? ZPX_LAYOUT_INTERLEAVED : ZPX_LAYOUT_PLANAR;
+        im.bpm = bpm;
+        im.fused = (!force_generic && fused_eligible(p)) ? 1 : 0;
+        // coefficient storage
+        const uint64_t nblocks = (uint64_t)p.mxx * p.myy * bpm;
+        im.coef_base = pl.coef_blocks;
+        uint64_t cb = pl.coef_blocks;
+        for (int c = 0; c < p.ncomp; c++) {
+            im.comp_base[c] = cb;
+            cb += (uint64_t)im.comp_bw[c] * im.comp_bh[c];
+        }
+        pl.coef_blocks += nblocks;
+        // quantisers: sequential frames use the tables in force at the component's SOS,
+        // progressive frames those at EOI
+        for (int c = 0; c < p.ncomp; c++) {
+            const int32_t* zz = p.final_quant[p.tq[c]];
+            if (!p.progressive)
+                for (const ZpxScanHost& s : p.scans)
+                    for (int i = 0; i < s.ncomp; i++)
+                        if (s.comp[i] == c) zz = s.quant[i];
+            im.qidx[c] = dd.add_quant(zz, pl.quant);
+        }
+        // output
+        im.out_off = pl.out_bytes;
+        pl.out_off.push_back(pl.out_bytes);
+        pl.out_bytes += align_up((size_t)4 * p.width * p.height, 256);
+        // native planes (generic path): exact makeImg layout: Y, Cb, Cr contiguous, then black
+        pl.plane_off0.push_back(pl.plane_bytes);
+        if (!im.fused) {
+            zpx_image_info info;
+            zpx_fill_info(p, &info);
+            size_t base = pl.plane_bytes;
+            if (p.ncomp == 1) {
+                im.plane_off[0] = base;
+                im.plane_stride[0] = 8 * p.mxx;
+                im.plane_rows[0] = 8 * p.myy;
+                base += (size_t)im.plane_stride[0] * im.plane_rows[0];
+            } else {
+                const size_t w = (size_t)8 * p.h[0] * p.mxx, hh = (size_t)8 * p.v[0] * p.myy;
+                const size_t cw = (size_t)info.c_stride, ch = (size_t)8 * p.v[1] * p.myy;
+                im.plane_off[0] = base;
+                im.plane_stride[0] = (int)w;
+                im.plane_rows[0] = (int)hh;
+                im.plane_off[1] = base + w * hh;
+                im.plane_off[2] = base + w * hh + cw * ch;
+                im.plane_stride[1] = im.plane_stride[2] = (int)cw;
+                im.plane_rows[1] = im.plane_rows[2] = (int)ch;
+                base += w * hh + 2 * cw * ch;
+                if (p.ncomp == 4) {
+                    im.plane_off[3] = base;
+                    im.plane_stride[3] = 8 * p.h[3] * p.mxx;
+                    im.plane_rows[3] = 8 * p.v[3] * p.myy;
+                    base += (size_t)im.plane_stride[3] * im.plane_rows[3];
+                }
+            }
+            pl.plane_bytes = align_up(base, 256);
+            pl.generic.push_back((uint32_t)k);
+            pl.generic_max_blocks = std::max<int>(pl.generic_max_blocks, (int)nblocks);
+            pl.generic_max_pixels = std::max<size_t>(pl.generic_max_pixels, (size_t)p.width * p.height);
+        } else {
+            // tiles of the fused kernel: runs of MCUs inside one MCU row, sized so that one tile is
+            // (close to) one block per thread of a 256-thread CTA
+            const int nc = p.ncomp == 1 ? 1 : 3;
+            const int key = p.h[0] << 8 | p.v[0] << 4 | nc;
+            auto it = group_ix.find(key);
+            if (it == group_ix.end()) {
+                FusedGroup g;
+                g.h = p.h[0];
+                g.v = p.v[0];
+                g.nc = nc;
+                pl.groups.push_back(g);
+                it = group_ix.emplace(key, (int)pl.groups.size() - 1).first;
+            }
+            FusedGroup& g = pl.groups[it->second];
+            const int tcap = std::max(1, 256 / bpm);
+            const int per_row = (p.mxx + tcap - 1) / tcap;
+            const int tn = (p.mxx + per_row - 1) / per_row;
+            g.tmax = std::max(g.tmax, tn);
+            for (int my = 0; my < p.myy; my++)
+                for (int mx0 = 0; mx0 < p.mxx; mx0 += tn) {
+                    ZpxTileDev t;
+                    t.img = (uint32_t)k;
+                    t.my = (uint16_t)my;
+                    t.n = (uint16_t)std::min(tn, p.mxx - mx0);
+                    t.mx0 = (uint32_t)mx0;
+                    t.pad = 0;
+                    g.tiles.push_back(t);
+                }
+            g.bytes += nblocks * 128 + (uint64_t)4 * p.width * p.height;
+        }
+        // scans and intervals
+        int scan_index = 0;
+        for (const ZpxScanHost& s : p.scans) {
+            ZpxScanDev sd;
+            memset(&sd, 0, sizeof(sd));
+            sd.img = (uint32_t)k;
+            sd.ncomp = s.ncomp;
+            sd.interleaved = s.ncomp > 1 ? 1 : 0;
+            sd.ss = s.ss;
+            sd.se = s.se;
+            sd.ah = s.ah;
+            sd.al = s.al;
+            sd.total_mcu = p.mxx * p.myy;
+            sd.restart_interval = s.restart_interval;
+            sd.scan_index = scan_index++;
+            int nb = 0;
+            for (int i = 0; i < s.ncomp; i++) {
+                const int c = s.comp[i];
+                const int dci = dd.add_huff(s.dc[i], pl.huff), aci = dd.add_huff(s.ac[i], pl.huff);
+                for (int j = 0; j < p.h[c] * p.v[c]; j++) {
+                    sd.blk_comp[nb] = (uint8_t)c;
+                    sd.blk_hx[nb] = (uint8_t)(j % p.h[c]);
+                    sd.blk_vy[nb] = (uint8_t)(j / p.h[c]);
+                    sd.blk_slot[nb] = (uint8_t)(im.blk_off[c] + j);
+                    sd.blk_dc[nb] = (uint16_t)dci;
+                    sd.blk_ac[nb] = (uint16_t)aci;
+                    nb++;
+                }
+            }
+            sd.nblk = nb;
+            if (s.ncomp == 1) {
+                const int c = s.comp[0];
+                sd.cw = std::min(im.comp_bw[c], (p.width + 7) / 8);
+                sd.ch = std::min(im.comp_bh[c], (p.height + 7) / 8);
+            }
+            const uint32_t scan_ix = (uint32_t)pl.scans.size();
+            pl.scans.push_back(sd);
+            if (s.intervals.empty()) continue;
+            // one contiguous copy per scan: [first interval start, last interval limit)
+            const size_t src0 = s.intervals.front().start, src1 = s.intervals.back().limit;
+            const size_t dst0 = pl.blob_bytes;
+            pl.copies.push_back({bi, src0, src1 - src0, dst0});
+            pl.blob_bytes = align_up(dst0 + (src1 - src0) + 8, 16);
+            uint32_t ord = 0;
+            for (const ZpxIntervalHost& iv : s.intervals) {
+                ZpxIntervalDev d;
+                d.start = dst0 + (iv.start - src0);
+                d.len = (uint32_t)(iv.limit - iv.start);
+                d.scan = scan_ix;
+                d.first_mcu = iv.first_mcu;
+                d.n_mcu = iv.n_mcu;
+                d.ordinal = ord++;
+                d.flags = iv.eof_limit ? 1u : 0u;
+                pl.ivs.push_back(d);
+            }
+        }
+        pl.imgs.push_back(im);
+    }
+    // descriptor buffer layout
+    size_t off = 0;
+    auto place = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    pl.off_imgs = place(pl.imgs.size() * sizeof(ZpxImageDev));
+    pl.off_scans = place(pl.scans.size() * sizeof(ZpxScanDev));
+    pl.off_ivs = place(pl.ivs.size() * sizeof(ZpxIntervalDev));
+    pl.off_huff = place(pl.huff.size() * sizeof(ZpxHuffDev));
+    pl.off_quant = place(pl.quant.size() * sizeof(ZpxQuantDev));
+    pl.off_generic = place(pl.generic.size() * sizeof(uint32_t));
+    for (FusedGroup& g : pl.groups) g.tiles_off = place(g.tiles.size() * sizeof(ZpxTileDev));
+    pl.desc_bytes = off;
+    memset(&pl.timing, 0, sizeof(pl.timing));
+    pl.timing.images = (int32_t)pl.images.size();
+    for (const ZpxImageDev& im : pl.imgs) {
+        pl.timing.pixels += (uint64_t)im.width * im.height;
+        pl.timing.rgba_bytes += (uint64_t)4 * im.width * im.height;
+    }
+    pl.timing.coef_bytes = pl.coef_blocks * 128;
+    for (const ZpxIntervalDev& d : pl.ivs) pl.timing.entropy_bytes_in += d.len;
+    for (const FusedGroup& g : pl.groups) pl.timing.idct_fused_bytes += g.bytes;
+}
+
+int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
+    zpx_ctx* ctx = b->ctx;
+    DeviceCtx& dc = ctx->devs[di];
+    DevicePlan& pl = b->plans[di];
+    if (pl.images.empty()) return ZPX_OK;
+    CU(ctx, cudaSetDevice(dc.dev));
+    cudaStream_t st = user_stream ? user_stream : dc.stream;
+    uint8_t* desc = (uint8_t*)dc.desc.p;
+
+    CU(ctx, cudaEventRecord(dc.ev[0], st));
+    CU(ctx, cudaMemsetAsync(dc.status.p, 0xff, pl.imgs.size() * sizeof(unsigned long long), st));
+    if (pl.plane_bytes) CU(ctx, cudaMemsetAsync(dc.planes.p, 0, pl.plane_bytes, st));
+
+    int k1_launches = 0, k2_launches = 0;
+    // ---- K1: entropy decode ----
+    K1Params k1;
+    k1.blob = (const uint8_t*)dc.blob.p;
+    k1.ivs = (const ZpxIntervalDev*)(desc + pl.off_ivs);
+    k1.n_iv = (int)pl.ivs.size();
+    k1.scans = (const ZpxScanDev*)(desc + pl.off_scans);
+    k1.imgs = (const ZpxImageDev*)(desc + pl.off_imgs);
+    k1.huff = (const ZpxHuffDev*)(desc + pl.off_huff);
+    k1.coef = (uint4*)dc.coef.p;
+    k1.status = (unsigned long long*)dc.status.p;
+    if (k1.n_iv > 0) {
+        CU(ctx, k1_launch_lane_per_interval(k1, st));
+        k1_launches++;
+    }
+    CU(ctx, cudaEventRecord(dc.ev[1], st));
+
+    // ---- K2: fused kernel, one launch per sampling format ----
+    for (const FusedGroup& g : pl.groups) {
+        K2Params k2;
+        k2.coef = (const int16_t*)dc.coef.p;
+        k2.out = (uint8_t*)dc.out.p;
+        k2.imgs = k1.imgs;
+        k2.tiles = (const ZpxTileDev*)(desc + g.tiles_off);
+        k2.quant = (const ZpxQuantDev*)(desc + pl.off_quant);
+        k2.ntiles = (int)g.tiles.size();
+        k2.tmax = g.tmax;
+        const int grid = std::min<int>(k2.ntiles, dc.sm_count * 2);
+        CU(ctx, k2_launch_fused(g.h, g.v, g.nc, k2, grid, st));
+        k2_launches++;
+    }
+    CU(ctx, cudaEventRecord(dc.ev[2], st));
+    // ---- K2 generic ----
+    if (!pl.generic.empty()) {
+        K2GParams kg;
+        kg.coef = (const int16_t*)dc.coef.p;
+        kg.planes = (uint8_t*)dc.planes.p;
+        kg.out = (uint8_t*)dc.out.p;
+        kg.imgs = k1.imgs;
+        kg.quant = (const ZpxQuantDev*)(desc + pl.off_quant);
+        const uint32_t* list = (const uint32_t*)(desc + pl.off_generic);
+        const int total = (int)pl.generic.size();
+        for (int i0 = 0; i0 < total; i0 += 32768) {
+            kg.list = list + i0;
+            CU(ctx, k2g_launch(kg, std::min(32768, total - i0), pl.generic_max_blocks, pl.generic_max_pixels, st));
+            k2_launches += 2;
+        }
+    }
+    CU(ctx, cudaEventRecord(dc.ev[3], st));
+    ctx->launches += (uint64_t)(k1_launches + k2_launches);
+    pl.timing.entropy_launches = k1_launches;
+    pl.timing.idct_launches = k2_launches;
+    pl.decoded = true;
+    return ZPX_OK;
+}
+
+int collect_timing(zpx_batch* b, int di) {
+    zpx_ctx* ctx = b->ctx;
+    DeviceCtx& dc = ctx->devs[di];
+    DevicePlan& pl = b->plans[di];
+    if (pl.images.empty() || !pl.decoded) return ZPX_OK;
+    CU(ctx, cudaSetDevice(dc.dev));
+    CU(ctx, cudaEventSynchronize(dc.ev[3]));
+    float a = 0, c = 0, d = 0, t = 0;
+    cudaEventElapsedTime(&a, dc.ev[0], dc.ev[1]);
+    cudaEventElapsedTime(&c, dc.ev[1], dc.ev[2]);
+    cudaEventElapsedTime(&d, dc.ev[2], dc.ev[3]);
+    cudaEventElapsedTime(&t, dc.ev[0], dc.ev[3]);
+    pl.timing.entropy_ms = a;
+    pl.timing.idct_fused_ms = c;
+    pl.timing.idct_ms = c + d;
+    pl.timing.total_ms = t;
+    return ZPX_OK;
+}
+
+// combine header status, host-side pending errors and the device error records
+int finalize_status(zpx_batch* b) {
+    if (b->status_ready) return ZPX_OK;
+    zpx_ctx* ctx = b->ctx;
+    for (size_t di = 0; di < b->plans.size(); di++) {
+        DevicePlan& pl = b->plans[di];
+        if (pl.images.empty() || !pl.decoded) continue;
+        DeviceCtx& dc = ctx->devs[di];
+        CU(ctx, cudaSetDevice(dc.dev));
+        CU(ctx, dc.hstatus.ensure(pl.imgs.size() * sizeof(unsigned long long)));
+        CU(ctx, cudaMemcpyAsync(dc.hstatus.p, dc.status.p, pl.imgs.size() * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, dc.stream));
+        CU(ctx, cudaStreamSynchronize(dc.stream));
+        const unsigned long long* hs = (const unsigned long long*)dc.hstatus.p;
+        int failed = 0;
+        for (size_t k = 0; k < pl.images.size(); k++) {
+            const int bi = pl.images[k];
+            const ZpxParsed& p = b->parsed[bi];
+            int st = 0;
+            if (hs[k] != ZPX_STATUS_NONE) st = (int)(hs[k] & 0xff);
+            if (st == 0) {
+                for (const ZpxScanHost& s : p.scans)
+                    if (s.pending_err) { st = s.pending_err; break; }
+            }
+            if (st == 0) st = p.trailing_err;
+            b->status[bi] = st;
+            if (st) failed++;
+        }
+        pl.timing.images_failed = failed;
+    }
+    b->status_ready = true;
+    return ZPX_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int32_t zpx_abi_version(void) { return ZPX_ABI_VERSION; }
+
+const char* zpx_error_name(int32_t code) {
+    if (code >= 0 && code <= ZPX_E_REF_LAST) return kErrNames[code];
+    switch (code) {
+        case ZPX_E_CUDA: return "CudaFailure";
+        case ZPX_E_NO_DEVICE: return "NoCudaDevice";
+        case ZPX_E_INVALID_ARG: return "InvalidArgument";
+        case ZPX_E_BAD_STATE: return "BadState";
+        case ZPX_E_COEF_RANGE: return "CoefficientOutOfRange";
+        case ZPX_E_UNSUPPORTED_STREAM: return "UnsupportedStream";
+        case ZPX_E_MALFORMED_TABLE: return "MalformedHuffmanTable";
+    }
+    return "?";
+}
+
+int32_t zpx_probe(const uint8_t* buf, size_t len, zpx_image_info* out) {
+    if (!out || (!buf && len)) return ZPX_E_INVALID_ARG;
+    ZpxParsed p;
+    zpx_parse_jpeg(buf, len, true, &p);
+    zpx_fill_info(p, out);
+    // decodeConfig reports 4-component frames as YCbCr too (decoder.zig:210-215); variant stays what load returns
+    return p.status;
+}
+
+int32_t zpx_parse_report_of(const uint8_t* buf, size_t len, zpx_image_info* info, zpx_parse_report* rep) {
+    if (!rep || (!buf && len)) return ZPX_E_INVALID_ARG;
+    ZpxParsed p;
+    zpx_parse_jpeg(buf, len, false, &p);
+    if (info) zpx_fill_info(p, info);
+    memset(rep, 0, sizeof(*rep));
+    rep->status = p.status;
+    rep->n_scans = (int32_t)p.scans.size();
+    rep->pending_after_interval = -1;
+    for (const ZpxScanHost& s : p.scans) {
+        rep->n_intervals += (int32_t)s.intervals.size();
+        if (s.pending_err) {
+            rep->pending_err = s.pending_err;
+            rep->pending_after_interval = s.err_after_interval;
+        }
+        if (!s.intervals.empty()) rep->entropy_bytes += s.intervals.back().limit - s.intervals.front().start;
+    }
+    rep->trailing_err = p.trailing_err;
+    rep->fused = (p.status == 0 && fused_eligible(p)) ? 1 : 0;
+    rep->mode = p.mode;
+    return ZPX_OK;
+}
+
+int32_t zpx_ctx_create(const int32_t* device_ids, int32_t n_devices, zpx_ctx** out) {
+    if (!out) return ZPX_E_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) return ZPX_E_NO_DEVICE;
+    zpx_ctx* c = new (std::nothrow) zpx_ctx();
+    if (!c) return ZPX_E_OutOfMemory;
+    std::vector<int> ids;
+    if (!device_ids || n_devices <= 0) ids.push_back(0);
+    else ids.assign(device_ids, device_ids + n_devices);
+    for (int id : ids) {
+        if (id < 0 || id >= count) {
+            zpx_ctx_destroy(c);
+            return ZPX_E_INVALID_ARG;
+        }
+        DeviceCtx d;
+        d.dev = id;
+        if ((e = cudaSetDevice(id)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            zpx_ctx_destroy(c);
+            return ZPX_E_CUDA;
+        }
+        cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, id);
+        for (auto& ev : d.ev) cudaEventCreate(&ev);
+        c->devs.push_back(d);
+    }
+    *out = c;
+    return ZPX_OK;
+}
+
+void zpx_ctx_destroy(zpx_ctx* c) {
+    if (!c) return;
+    for (DeviceCtx& d : c->devs) {
+        cudaSetDevice(d.dev);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        d.blob.release();
+        d.coef.release();
+        d.out.release();
+        d.planes.release();
+        d.desc.release();
+        d.status.release();
+        d.stage.release();
+        d.hdesc.release();
+        d.hstatus.release();
+        for (auto& ev : d.ev)
+            if (ev) cudaEventDestroy(ev);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete c;
+}
+
+int32_t zpx_ctx_num_devices(const zpx_ctx* c) { return c ? (int32_t)c->devs.size() : 0; }
+int32_t zpx_last_cuda_error(const zpx_ctx* c) { return c ? c->last_cuda : 0; }
+const char* zpx_last_cuda_error_string(const zpx_ctx* c) { return c ? c->last_cuda_str.c_str() : ""; }
+uint64_t zpx_ctx_kernel_launches(const zpx_ctx* c) { return c ? c->launches.load() : 0; }
+
+int32_t zpx_ctx_set_option(zpx_ctx* c, int32_t option, int64_t value) {
+    if (!c) return ZPX_E_INVALID_ARG;
+    switch (option) {
+        case ZPX_OPT_ENTROPY_MODE: c->opt_entropy_mode = value; return ZPX_OK;
+        case ZPX_OPT_FORCE_GENERIC: c->opt_force_generic = value; return ZPX_OK;
+        case ZPX_OPT_SUBSEQ_BYTES: c->opt_subseq = value; return ZPX_OK;
+    }
+    return ZPX_E_INVALID_ARG;
+}
+
+void* zpx_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void zpx_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int32_t zpx_batch_open(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* lens, int32_t n, zpx_batch** out) {
+    if (!ctx || !out || n < 0 || (n > 0 && (!bufs || !lens))) return ZPX_E_INVALID_ARG;
+    *out = nullptr;
+    zpx_batch* b = new (std::nothrow) zpx_batch();
+    if (!b) return ZPX_E_OutOfMemory;
+    b->ctx = ctx;
+    b->n = n;
+    b->bufs.assign(bufs, bufs + n);
+    b->lens.assign(lens, lens + n);
+    b->parsed.resize(n);
+    b->dev_of.assign(n, -1);
+    b->slot_of.assign(n, -1);
+    b->status.assign(n, 0);
+    // header parse, parallel over host cores (decodeInner's marker loop; no entropy decode)
+    parallel_for((size_t)n, 4, [&](size_t i) {
+        if (!b->bufs[i] && b->lens[i]) {
+            b->parsed[i].status = ZPX_E_INVALID_ARG;
+            return;
+        }
+        zpx_parse_jpeg(b->bufs[i], b->lens[i], false, &b->parsed[i]);
+        if (b->parsed[i].status == 0) {
+            int u = unsupported_reason(b->parsed[i]);
+            if (u) b->parsed[i].status = u;
+        }
+    });
+    // schedule: contiguous index ranges balanced by entropy-coded bytes (images are independent,
+    // nothing is exchanged between devices)
+    const int nd = (int)ctx->devs.size();
+    b->plans.resize(nd);
+    std::vector<uint64_t> w(n, 0);
+    uint64_t total = 0;
+    for (int i = 0; i < n; i++) {
+        b->status[i] = b->parsed[i].status;
+        if (b->parsed[i].status != 0) continue;
+        for (const ZpxScanHost& s : b->parsed[i].scans)
+            if (!s.intervals.empty()) w[i] += s.intervals.back().limit - s.intervals.front().start;
+        w[i] += 1024;
+        total += w[i];
+    }
+    uint64_t acc = 0;
+    for (int i = 0; i < n; i++) {
+        if (b->parsed[i].status != 0) continue;
+        int d = total ? (int)std::min<uint64_t>(nd - 1, (acc + w[i] / 2) * nd / total) : 0;
+        acc += w[i];
+        b->dev_of[i] = d;
+        b->slot_of[i] = (int)b->plans[d].images.size();
+        b->plans[d].images.push_back(i);
+    }
+    for (int d = 0; d < nd; d++) build_plan(b, d);
+    *out = b;
+    return ZPX_OK;
+}
+
+int32_t zpx_batch_size(const zpx_batch* b) { return b ? b->n : 0; }
+
+int32_t zpx_batch_info(const zpx_batch* b, int32_t i, zpx_image_info* out) {
+    if (!b || !out || i < 0 || i >= b->n) return ZPX_E_INVALID_ARG;
+    zpx_fill_info(b->parsed[i], out);
+    out->device = b->dev_of[i];
+    return ZPX_OK;
+}
+
+int32_t zpx_batch_upload(zpx_batch* b) {
+    if (!b) return ZPX_E_INVALID_ARG;
+    zpx_ctx* ctx = b->ctx;
+    const int nd = (int)ctx->devs.size();
+    // allocate and stage
+    for (int di = 0; di < nd; di++) {
+        DevicePlan& pl = b->plans[di];
+        if (pl.images.empty()) continue;
+        DeviceCtx& dc = ctx->devs[di];
+        CU(ctx, cudaSetDevice(dc.dev));
+        CU(ctx, dc.blob.ensure(pl.blob_bytes + 64));
+        CU(ctx, dc.coef.ensure(pl.coef_blocks * 128 + 256));
+        CU(ctx, dc.out.ensure(pl.out_bytes + 256));
+        if (pl.plane_bytes) CU(ctx, dc.planes.ensure(pl.plane_bytes + 256));
+        CU(ctx, dc.desc.ensure(pl.desc_bytes + 256));
+        CU(ctx, dc.status.ensure(pl.imgs.size() * sizeof(unsigned long long) + 256));
+        CU(ctx, dc.stage.ensure(pl.blob_bytes + 64));
+        CU(ctx, dc.hdesc.ensure(pl.desc_bytes + 256));
+        // descriptors
+        uint8_t* hd = (uint8_t*)dc.hdesc.p;
+        memcpy(hd + pl.off_imgs, pl.imgs.data(), pl.imgs.size() * sizeof(ZpxImageDev));
+        memcpy(hd + pl.off_scans, pl.scans.data(), pl.scans.size() * sizeof(ZpxScanDev));
+        memcpy(hd + pl.off_ivs, pl.ivs.data(), pl.ivs.size() * sizeof(ZpxIntervalDev));
+        memcpy(hd + pl.off_huff, pl.huff.data(), pl.huff.size() * sizeof(ZpxHuffDev));
+        memcpy(hd + pl.off_quant, pl.quant.data(), pl.quant.size() * sizeof(ZpxQuantDev));
+        memcpy(hd + pl.off_generic, pl.generic.data(), pl.generic.size() * sizeof(uint32_t));
+        for (const FusedGroup& g : pl.groups) memcpy(hd + g.tiles_off, g.tiles.data(), g.tiles.size() * sizeof(ZpxTileDev));
+        // entropy-coded segments into pinned staging, parallel over host cores
+        uint8_t* stg = (uint8_t*)dc.stage.p;
+        parallel_for(pl.copies.size(), 8, [&](size_t k) {
+            const DevicePlan::Copy& c = pl.copies[k];
+            memcpy(stg + c.dst, b->bufs[c.img] + c.src, c.len);
+            memset(stg + c.dst + c.len, 0, 8);
+        });
+        CU(ctx, cudaEventRecord(dc.ev[4], dc.stream));
+        CU(ctx, cudaMemcpyAsync(dc.desc.p, dc.hdesc.p, pl.desc_bytes, cudaMemcpyHostToDevice, dc.stream));
+        if (pl.blob_bytes) CU(ctx, cudaMemcpyAsync(dc.blob.p, dc.stage.p, pl.blob_bytes, cudaMemcpyHostToDevice, dc.stream));
+        CU(ctx, cudaEventRecord(dc.ev[5], dc.stream));
+    }
+    for (int di = 0; di < nd; di++) {
+        DevicePlan& pl = b->plans[di];
+        if (pl.images.empty()) continue;
+        DeviceCtx& dc = ctx->devs[di];
+        CU(ctx, cudaSetDevice(dc.dev));
+        CU(ctx, cudaStreamSynchronize(dc.stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, dc.ev[4], dc.ev[5]);
+        pl.timing.h2d_ms = ms;
+        pl.uploaded = true;
+    }
+    return ZPX_OK;
+}
+
+int32_t zpx_batch_decode(zpx_batch* b, void* stream) {
+    if (!b) return ZPX_E_INVALID_ARG;
+    zpx_ctx* ctx = b->ctx;
+    const int nd = (int)ctx->devs.size();
+    if (stream && nd != 1) return ZPX_E_INVALID_ARG;
+    for (int di = 0; di < nd; di++)
+        if (!b->plans[di].images.empty() && !b->plans[di].uploaded) return ZPX_E_BAD_STATE;
+    b->status_ready = false;
+    for (int di = 0; di < nd; di++) {
+        int e = decode_on_device(b, di, (cudaStream_t)stream);
+        if (e) return e;
+    }
+    if (stream) return ZPX_OK;  // caller synchronises its own stream
+    for (int di = 0; di < nd; di++) {
+        int e = collect_timing(b, di);
+        if (e) return e;
+    }
+    return ZPX_OK;
+}
+
+int32_t zpx_batch_status(zpx_batch* b, int32_t* status) {
+    if (!b) return ZPX_E_INVALID_ARG;
+    int e = finalize_status(b);
+    if (e) return e;
+    if (status) memcpy(status, b->status.data(), sizeof(int32_t) * b->n);
+    return ZPX_OK;
+}
+
+int32_t zpx_batch_timing(const zpx_batch* b, int32_t di, zpx_timing* out) {
+    if (!b || !out || di < 0 || di >= (int)b->plans.size()) return ZPX_E_INVALID_ARG;
+    // timing of a user-stream decode is collected lazily
+    if (b->plans[di].decoded) collect_timing(const_cast<zpx_batch*>(b), di);
+    *out = b->plans[di].timing;
+    return ZPX_OK;
+}
+
+const void* zpx_batch_device_rgba(const zpx_batch* b, int32_t i) {
+    if (!b || i < 0 || i >= b->n || b->dev_of[i] < 0) return nullptr;
+    const DevicePlan& pl = b->plans[b->dev_of[i]];
+    if (!pl.decoded) return nullptr;
+    return (const uint8_t*)b->ctx->devs[b->dev_of[i]].out.p + pl.out_off[b->slot_of[i]];
+}
+
+int32_t zpx_batch_fetch_rgba(zpx_batch* b, uint8_t* const* out, const size_t* out_stride, int32_t* status) {
+    if (!b || (b->n > 0 && !out)) return ZPX_E_INVALID_ARG;
+    zpx_ctx* ctx = b->ctx;
+    const int nd = (int)ctx->devs.size();
+    for (int di = 0; di < nd; di++)
+        if (!b->plans[di].images.empty() && !b->plans[di].decoded) return ZPX_E_BAD_STATE;
+    int e = finalize_status(b);
+    if (e) return e;
+    for (int di = 0; di < nd; di++) {
+        DevicePlan& pl = b->plans[di];
+        if (pl.images.empty()) continue;
+        DeviceCtx& dc = ctx->devs[di];
+        CU(ctx, cudaSetDevice(dc.dev));
+        CU(ctx, cudaEventRecord(dc.ev[6], dc.stream));
+        size_t k = 0;
+        while (k < pl.images.size()) {
+            const int bi = pl.images[k];
+            const ZpxParsed& p = b->parsed[bi];
+            const size_t row = (size_t)4 * p.width;
+            const size_t len = row * p.height;
+            if (!out[bi] || b->status[bi] != 0) { k++; continue; }
+            const uint8_t* src = (const uint8_t*)dc.out.p + pl.out_off[k];
+            if (out_stride && out_stride[bi] != 0 && out_stride[bi] != row) {
+                CU(ctx, cudaMemcpy2DAsync(out[bi], out_stride[bi], src, row, row, p.height, cudaMemcpyDeviceToHost, dc.stream));
+                k++;
+                continue;
+            }
+            // merge runs that are contiguous on both sides into one copy
+            size_t run = len, k2 = k + 1;
+            while (k2 < pl.images.size()) {
+                const int bj = pl.images[k2];
+                const ZpxParsed& pj = b->parsed[bj];
+                if (!out[bj] || b->status[bj] != 0) break;
+                if (out_stride && out_stride[bj] != 0 && out_stride[bj] != (size_t)4 * pj.width) break;
+                if (pl.out_off[k2] != pl.out_off[k] + run || out[bj] != out[bi] + run) break;
+                run += (size_t)4 * pj.width * pj.height;
+                k2++;
+            }
+            CU(ctx, cudaMemcpyAsync(out[bi], src, run, cudaMemcpyDeviceToHost, dc.stream));
+            k = k2;
+        }
+        CU(ctx, cudaEventRecord(dc.ev[7], dc.stream));
+    }
+    for (int di = 0; di < nd; di++) {
+        DevicePlan& pl = b->plans[di];
+        if (pl.images.empty()) continue;
+        DeviceCtx& dc = ctx->devs[di];
+        CU(ctx, cudaSetDevice(dc.dev));
+        CU(ctx, cudaStreamSynchronize(dc.stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, dc.ev[6], dc.ev[7]);
+        pl.timing.d2h_ms = ms;
+    }
+    if (status) memcpy(status, b->status.data(), sizeof(int32_t) * b->n);
+    return ZPX_OK;
+}
+
+int32_t zpx_batch_fetch_native(zpx_batch* b, uint8_t* const* out, int32_t* status) {
+    if (!b || (b->n > 0 && !out)) return ZPX_E_INVALID_ARG;
+    zpx_ctx* ctx = b->ctx;
+    int e = finalize_status(b);
+    if (e) return e;
+    for (int i = 0; i < b->n; i++) {
+        if (!out[i] || b->status[i] != 0 || b->dev_of[i] < 0) continue;
+        const int di = b->dev_of[i];
+        DevicePlan& pl = b->plans[di];
+        if (!pl.decoded) return ZPX_E_BAD_STATE;
+        DeviceCtx& dc = ctx->devs[di];
+        const ZpxImageDev& im = pl.imgs[b->slot_of[i]];
+        const ZpxParsed& p = b->parsed[i];
+        CU(ctx, cudaSetDevice(dc.dev));
+        zpx_image_info info;
+        zpx_fill_info(p, &info);
+        if (p.variant == ZPX_VARIANT_RGBA) {
+            CU(ctx, cudaMemcpyAsync(out[i], (const uint8_t*)dc.out.p + im.out_off, info.native_len, cudaMemcpyDeviceToHost, dc.stream));
+        } else if (im.fused || p.variant == ZPX_VARIANT_CMYK) {
+            // planes only exist on the unfused path; CMYK's native interleave is not materialised
+            b->status[i] = ZPX_E_UNSUPPORTED_STREAM;
+        } else {
+            CU(ctx, cudaMemcpyAsync(out[i], (const uint8_t*)dc.planes.p + im.plane_off[0], info.native_len, cudaMemcpyDeviceToHost, dc.stream));
+        }
+    }
+    for (DeviceCtx& dc : ctx->devs) {
+        CU(ctx, cudaSetDevice(dc.dev));
+        CU(ctx, cudaStreamSynchronize(dc.stream));
+    }
+    if (status) memcpy(status, b->status.data(), sizeof(int32_t) * b->n);
+    return ZPX_OK;
+}
+
+int32_t zpx_batch_fetch_coefficients(zpx_batch* b, int32_t i, int16_t* out, size_t cap_blocks, size_t* n_blocks) {
+    if (!b || i < 0 || i >= b->n || b->dev_of[i] < 0) return ZPX_E_INVALID_ARG;
+    zpx_ctx* ctx = b->ctx;
+    const int di = b->dev_of[i];
+    DevicePlan& pl = b->plans[di];
+    if (!pl.decoded) return ZPX_E_BAD_STATE;
+    DeviceCtx& dc = ctx->devs[di];
+    const ZpxImageDev& im = pl.imgs[b->slot_of[i]];
+    const ZpxParsed& p = b->parsed[i];
+    const size_t nb = (size_t)p.mxx * p.myy * im.bpm;
+    if (n_blocks) *n_blocks = nb;
+    if (!out) return ZPX_OK;
+    if (cap_blocks < nb) return ZPX_E_INVALID_ARG;
+    CU(ctx, cudaSetDevice(dc.dev));
+    CU(ctx, cudaStreamSynchronize(dc.stream));
+    CU(ctx, cudaMemcpy(out, (const uint8_t*)dc.coef.p + im.coef_base * 128, nb * 128, cudaMemcpyDeviceToHost));
+    // undo the row swizzle: block with component-x index bx stores row r at slot r ^ (bx & 7)
+    std::vector<int16_t> tmp(64);
+    for (size_t k = 0; k < nb; k++) {
+        int bx;
+        if (im.layout == ZPX_LAYOUT_INTERLEAVED) {
+            const size_t mcu = k / im.bpm;
+            const int slot = (int)(k % im.bpm);
+            int c = 0;
+            for (int cc = 0; cc < im.ncomp; cc++)
+                if ((int)im.blk_off[cc] <= slot) c = cc;
+            const int j = slot - (int)im.blk_off[c];
+            bx = im.h[c] * (int)(mcu % p.mxx) + j % im.h[c];
+        } else {
+            size_t kk = k;
+            int c = 0;
+            for (; c < im.ncomp; c++) {
+                const size_t cnt = (size_t)im.comp_bw[c] * im.comp_bh[c];
+                if (kk < cnt) break;
+                kk -= cnt;
+            }
+            bx = (int)(kk % im.comp_bw[c]);
+        }
+        int16_t* blk = out + k * 64;
+        memcpy(tmp.data(), blk, 128);
+        for (int r = 0; r < 8; r++) memcpy(blk + r * 8, tmp.data() + ((r ^ (bx & 7)) * 8), 16);
+    }
+    return ZPX_OK;
+}
+
+void zpx_batch_close(zpx_batch* b) {
+    if (!b) return;
+    for (DeviceCtx& dc : b->ctx->devs) {
+        cudaSetDevice(dc.dev);
+        cudaStreamSynchronize(dc.stream);
+    }
+    delete b;
+}
+
+int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* lens, int32_t n,
+                              uint8_t* const* out, const size_t* out_stride, int32_t* status) {
+    zpx_batch* b = nullptr;
+    int e = zpx_batch_open(ctx, bufs, lens, n, &b);
+    if (e) return e;
+    e = zpx_batch_upload(b);
+    if (!e) e = zpx_batch_decode(b, nullptr);
+    if (!e) e = zpx_batch_fetch_rgba(b, out, out_stride, status);
+    zpx_batch_close(b);
+    return e;
+}
+
+}  // extern "C"

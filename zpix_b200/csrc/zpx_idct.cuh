@@ -1,0 +1,167 @@
+// zpx_idct.cuh -- exact fixed-point 8x8 IDCT of the reference (src/jpeg/idct.zig:77-201),
+// one thread per block, everything in registers.  Every shift of the reference is a rounding point
+// and stays where it is; only value-neutral rewrites are used:
+//   * the row pass' "all AC zero" shortcut (idct.zig:84-97) is dropped: the general formulas give the
+//     same values (((s0<<11)+128)>>8 == s0<<3) -- SURVEY B3;
+//   * dequantisation (decoder.zig:1564-1567) is fused into the row-pass loads; the <<11 prescale of
+//     columns 0 and 4 is folded into the quantiser ((c*q)<<11 == c*(q<<11) in wrapping 32-bit);
+//   * level shift + clamp (decoder.zig:1622-1628: v<-128 -> 0, v>127 -> 255, else v+128) is a
+//     saturating pack to s8 followed by ^0x80 on the packed bytes.
+// All arithmetic is wrapping 32-bit int, like the oracle.
+#pragma once
+#include <stdint.h>
+
+namespace zpx {
+
+constexpr int W1 = 2841, W2 = 2676, W3 = 2408, W5 = 1609, W6 = 1108, W7 = 565;
+constexpr int W1PW7 = W1 + W7, W1MW7 = W1 - W7, W2PW6 = W2 + W6, W2MW6 = W2 - W6, W3PW5 = W3 + W5, W3MW5 = W3 - W5;
+constexpr int R2 = 181;
+
+// signed halves of a packed pair of int16
+__device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t w) { return ((int)w) >> 16; }
+
+// Row pass on one row.  In: 8 dequantised values, x0/x1 already prescaled (x0 without the +128).
+// Out: o[0..7].
+__device__ __forceinline__ void idct_row(int x0, int x4, int x3, int x7, int x1, int x6, int x2, int x5, int* o) {
+    // names follow idct.zig:100-107: x0=s0<<11+128, x1=s4<<11, x2=s6, x3=s2, x4=s1, x5=s7, x6=s5, x7=s3
+    x0 += 128;
+    int x8 = W7 * (x4 + x5);
+    x4 = x8 + W1MW7 * x4;
+    x5 = x8 - W1PW7 * x5;
+    x8 = W3 * (x6 + x7);
+    x6 = x8 - W3MW5 * x6;
+    x7 = x8 - W3PW5 * x7;
+
+    x8 = x0 + x1;
+    x0 -= x1;
+    x1 = W6 * (x3 + x2);
+    x2 = x1 - W2PW6 * x2;
+    x3 = x1 + W2MW6 * x3;
+    x1 = x4 + x6;
+    x4 -= x6;
+    x6 = x5 + x7;
+    x5 -= x7;
+
+    x7 = x8 + x3;
+    x8 -= x3;
+    x3 = x0 + x2;
+    x0 -= x2;
+    x2 = (R2 * (x4 + x5) + 128) >> 8;
+    x4 = (R2 * (x4 - x5) + 128) >> 8;
+
+    o[0] = (x7 + x1) >> 8;
+    o[1] = (x3 + x2) >> 8;
+    o[2] = (x0 + x4) >> 8;
+    o[3] = (x8 + x6) >> 8;
+    o[4] = (x8 - x6) >> 8;
+    o[5] = (x0 - x4) >> 8;
+    o[6] = (x3 - x2) >> 8;
+    o[7] = (x7 - x1) >> 8;
+}
+
+// Column pass on one column (stride 8 inside b), in place.  idct.zig:149-199.
+__device__ __forceinline__ void idct_col(int* b) {
+    int y0 = (b[8 * 0] << 8) + 8192;
+    int y1 = b[8 * 4] << 8;
+    int y2 = b[8 * 6], y3 = b[8 * 2], y4 = b[8 * 1], y5 = b[8 * 7], y6 = b[8 * 5], y7 = b[8 * 3];
+
+    int y8 = W7 * (y4 + y5) + 4;
+    y4 = (y8 + W1MW7 * y4) >> 3;
+    y5 = (y8 - W1PW7 * y5) >> 3;
+    y8 = W3 * (y6 + y7) + 4;
+    y6 = (y8 - W3MW5 * y6) >> 3;
+    y7 = (y8 - W3PW5 * y7) >> 3;
+
+    y8 = y0 + y1;
+    y0 -= y1;
+    y1 = W6 * (y3 + y2) + 4;
+    y2 = (y1 - W2PW6 * y2) >> 3;
+    y3 = (y1 + W2MW6 * y3) >> 3;
+    y1 = y4 + y6;
+    y4 -= y6;
+    y6 = y5 + y7;
+    y5 -= y7;
+
+    y7 = y8 + y3;
+    y8 -= y3;
+    y3 = y0 + y2;
+    y0 -= y2;
+    y2 = (R2 * (y4 + y5) + 128) >> 8;
+    y4 = (R2 * (y4 - y5) + 128) >> 8;
+
+    b[8 * 0] = (y7 + y1) >> 14;
+    b[8 * 1] = (y3 + y2) >> 14;
+    b[8 * 2] = (y0 + y4) >> 14;
+    b[8 * 3] = (y8 + y6) >> 14;
+    b[8 * 4] = (y8 - y6) >> 14;
+    b[8 * 5] = (y0 - y4) >> 14;
+    b[8 * 6] = (y3 - y2) >> 14;
+    b[8 * 7] = (y7 - y1) >> 14;
+}
+
+// pack four int32 to bytes with signed saturation to [-128,127], then +128 (== ^0x80 on each byte)
+__device__ __forceinline__ uint32_t pack4_level_shift(int v0, int v1, int v2, int v3) {
+    uint32_t t, d;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(t));
+    return d ^ 0x80808080u;
+}
+
+// pack four int32 to bytes with unsigned saturation to [0,255]
+__device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3) {
+    uint32_t t, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(t));
+    return d;
+}
+
+// Dequantise + IDCT one block.  `ld(r)` returns row r of the block as a uint4 of 8 int16 (natural
+// order); `q` points at the block's quantiser in natural order with columns 0 and 4 pre-multiplied
+// by 2048 (int32[64], warp-uniform address).  Result: 8 rows x 2 words of level-shifted pixels.
+template <typename LoadRow>
+__device__ __forceinline__ void dequant_idct_block(LoadRow ld, const int* __restrict__ q, uint32_t (&px)[16]) {
+    int b[64];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint4 c = ld(r);
+        const int4 qa = *reinterpret_cast<const int4*>(q + r * 8);
+        const int4 qb = *reinterpret_cast<const int4*>(q + r * 8 + 4);
+        const int s0 = lo16(c.x) * qa.x, s1 = hi16(c.x) * qa.y, s2 = lo16(c.y) * qa.z, s3 = hi16(c.y) * qa.w;
+        const int s4 = lo16(c.z) * qb.x, s5 = hi16(c.z) * qb.y, s6 = lo16(c.w) * qb.z, s7 = hi16(c.w) * qb.w;
+        // idct_row(x0=s0', x4=s1, x3=s2, x7=s3, x1=s4', x6=s5, x2=s6, x5=s7)
+        idct_row(s0, s1, s2, s3, s4, s5, s6, s7, &b[r * 8]);
+    }
+#pragma unroll
+    for (int x = 0; x < 8; x++) idct_col(&b[x]);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        px[2 * r + 0] = pack4_level_shift(b[r * 8 + 0], b[r * 8 + 1], b[r * 8 + 2], b[r * 8 + 3]);
+        px[2 * r + 1] = pack4_level_shift(b[r * 8 + 4], b[r * 8 + 5], b[r * 8 + 6], b[r * 8 + 7]);
+    }
+}
+
+// ---- colour (src/color/color.zig:90-126 followed by the >>8 of image.zig:122-125) ----
+// YCbCr -> RGBA8: channel = sat_u8(v >> 16) reproduces the reference's branch exactly for every
+// int32 v: (v & 0xff000000)==0 -> v>>16 ; v<0 -> 0 ; else 255.
+__device__ __forceinline__ uint32_t ycc_pixel(int y, int rr, int gg, int bb) {
+    const int r = y * 0x10101 + rr, g = y * 0x10101 + gg, b = y * 0x10101 + bb;
+    return pack4_sat_u8(r >> 16, g >> 16, b >> 16, 255);
+}
+// per-chroma-sample terms, shared by every luma pixel that replicates the sample
+__device__ __forceinline__ void chroma_terms(int cb, int cr, int& rr, int& gg, int& bb) {
+    const int cb1 = cb - 128, cr1 = cr - 128;
+    rr = 91881 * cr1;
+    gg = -22554 * cb1 - 46802 * cr1;
+    bb = 116130 * cb1;
+}
+// CMYK -> RGBA8 (color.zig:115-121, then >>8).  c,m,y,k are the stored (already inverted) bytes.
+__device__ __forceinline__ uint32_t cmyk_pixel(uint32_t c, uint32_t m, uint32_t y, uint32_t k) {
+    const uint32_t w = 0xffffu - k * 0x101u;
+    const uint32_t r = ((0xffffu - c * 0x101u) * w / 0xffffu) >> 8;
+    const uint32_t g = ((0xffffu - m * 0x101u) * w / 0xffffu) >> 8;
+    const uint32_t b = ((0xffffu - y * 0x101u) * w / 0xffffu) >> 8;
+    return r | (g << 8) | (b << 16) | 0xff000000u;
+}
+
+}  // namespace zpx

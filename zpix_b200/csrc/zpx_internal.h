@@ -1,0 +1,174 @@
+// zpx_internal.h -- structures shared by the host parser, the scheduler and the kernels.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/zpix_cuda.h"
+
+#define ZPX_MAX_COMP 4
+#define ZPX_MAX_BLK_PER_MCU 16   // interleaved scans are limited to 10 (decoder.zig:1216); non-interleaved use h*v <= 16
+#define ZPX_LUT_BITS 10
+#define ZPX_LUT_SIZE (1 << ZPX_LUT_BITS)
+
+// ---------------------------------------------------------------------------
+// device-visible descriptors (POD, identical layout on host and device)
+// ---------------------------------------------------------------------------
+
+// One Huffman table in device form.  Built on the host from the DHT payload
+// (decoder.zig:1026-1111).  lut: first ZPX_LUT_BITS bits -> (symbol << 8) | code length, 0 = longer
+// code or invalid.  Longer codes: smallest l with v16 < limit[l] (v16 = next 16 bits, left aligned),
+// symbol = vals[valoff[l] + (v16 >> (16 - l))]  -- the canonical decode the reference does bit by
+// bit at decoder.zig:946-969; identical results for every code of the table.
+struct ZpxHuffDev {
+    uint16_t lut[ZPX_LUT_SIZE];
+    uint32_t limit[17];  // index 1..16
+    int32_t valoff[17];  // index 1..16
+    uint8_t vals[256];
+    uint32_t defined;    // num_codes != 0
+    uint32_t pad[3];
+};
+
+// Quantisation table, natural (row-major) order, as int32 so the kernels multiply directly.
+// decoder.zig:629-666 stores zig-zag order; de-zigzagging is a pure permutation.
+struct ZpxQuantDev {
+    int32_t q[64];
+};
+
+// colour exit of an image (decoder.zig:361-370, 699-709, 792-902)
+enum { ZPX_MODE_GRAY = 0, ZPX_MODE_YCBCR = 1, ZPX_MODE_RGB = 2, ZPX_MODE_CMYK = 3, ZPX_MODE_YCCK = 4 };
+// coefficient layout of an image in HBM
+enum { ZPX_LAYOUT_INTERLEAVED = 0, ZPX_LAYOUT_PLANAR = 1 };
+
+struct ZpxImageDev {
+    int32_t width, height;
+    int32_t mxx, myy;
+    int32_t ncomp;
+    int32_t mode;      // ZPX_MODE_*
+    int32_t layout;    // ZPX_LAYOUT_*
+    int32_t bpm;       // blocks per MCU in the interleaved layout
+    int32_t progressive;
+    int32_t fused;     // 1: eligible for the fused kernel
+    int32_t hmax, vmax;  // = h[0], v[0]
+    uint8_t h[4], v[4];
+    int32_t qidx[4];          // index into the quant table array, per component
+    uint32_t blk_off[4];      // interleaved: index of the component's first block inside an MCU
+    uint64_t coef_base;       // first block of the image in the coefficient buffer (block units)
+    uint64_t comp_base[4];    // planar: first block of each component's grid (block units, absolute)
+    int32_t comp_bw[4];       // planar: grid width in blocks = mxx*h
+    int32_t comp_bh[4];       //         grid height in blocks = myy*v
+    uint64_t out_off;         // RGBA output, byte offset in the device output buffer
+    uint64_t plane_off[4];    // native planes (generic path / native output): byte offsets in plane buffer
+    int32_t plane_stride[4];
+    int32_t plane_rows[4];
+    uint32_t status_slot;     // index into the device status array
+    uint32_t pad0;
+};
+
+// One scan (SOS) of an image, device form.
+struct ZpxScanDev {
+    uint32_t img;        // image index on this device
+    int32_t ncomp;       // components in scan
+    int32_t nblk;        // coded blocks per MCU iteration (interleaved) ; h*v iterations for non-interleaved
+    int32_t interleaved; // ncomp > 1
+    int32_t ss, se, ah, al;
+    int32_t total_mcu;   // mxx*myy
+    int32_t restart_interval;
+    int32_t scan_index;  // ordinal of the scan inside the image (error ordering)
+    int32_t cw, ch;      // non-interleaved: coded blocks per row / rows = blocks intersecting the image
+    // per block inside one MCU of this scan
+    uint8_t blk_comp[ZPX_MAX_BLK_PER_MCU]; // frame component index
+    uint8_t blk_hx[ZPX_MAX_BLK_PER_MCU];
+    uint8_t blk_vy[ZPX_MAX_BLK_PER_MCU];
+    uint8_t blk_slot[ZPX_MAX_BLK_PER_MCU]; // block's index inside the image's interleaved MCU (layout)
+    uint16_t blk_dc[ZPX_MAX_BLK_PER_MCU];  // Huffman table indices (into the device table array)
+    uint16_t blk_ac[ZPX_MAX_BLK_PER_MCU];
+};
+
+// One restart interval (or the whole scan when DRI == 0): the unit the
+// entropy kernels parallelise over.
+struct ZpxIntervalDev {
+    uint64_t start;      // byte offset of the first entropy-coded byte in the device blob
+    uint32_t len;        // bytes up to the limit (next marker or end of file)
+    uint32_t scan;       // index into the scan array
+    uint32_t first_mcu;  // MCU iteration index (my*mxx+mx) of the interval's first MCU
+    uint32_t n_mcu;      // MCU iterations in this interval
+    uint32_t ordinal;    // interval index inside the scan (error ordering)
+    uint32_t flags;      // bit0: limit is the end of the file (UnexpectedEof instead of MissingFF00)
+};
+
+// K2 tile: a run of MCUs inside one MCU row of one image.
+struct ZpxTileDev {
+    uint32_t img;
+    uint16_t my;
+    uint16_t n;      // MCUs in tile
+    uint32_t mx0;
+    uint32_t pad;
+};
+
+// device error record: smaller key = earlier in the reference's decode order
+// key = scan_index << 48 | block ordinal << 8 | code
+#define ZPX_STATUS_NONE 0xFFFFFFFFFFFFFFFFull
+
+// ---------------------------------------------------------------------------
+// host-side parse results
+// ---------------------------------------------------------------------------
+struct ZpxHuffHost {
+    bool defined = false;
+    uint8_t counts[16] = {0};
+    uint8_t vals[256] = {0};
+    int num_codes = 0;
+};
+
+struct ZpxIntervalHost {
+    size_t start;   // offset in the source file
+    size_t limit;   // offset of the limit (first 0xFF followed by a byte != 0x00, or file end)
+    uint32_t first_mcu, n_mcu;
+    bool eof_limit;
+};
+
+struct ZpxScanHost {
+    int ncomp = 0;
+    int comp[ZPX_MAX_COMP] = {0};  // frame component index per scan component
+    int td[ZPX_MAX_COMP] = {0}, ta[ZPX_MAX_COMP] = {0};
+    int ss = 0, se = 63, ah = 0, al = 0;
+    int restart_interval = 0;
+    ZpxHuffHost dc[ZPX_MAX_COMP], ac[ZPX_MAX_COMP];  // snapshot of the tables this scan uses
+    int32_t quant[ZPX_MAX_COMP][64];                 // snapshot of quant[tq] (zig-zag order) per scan component
+    std::vector<ZpxIntervalHost> intervals;
+    // error the reference raises after `err_after_interval` intervals decoded fine (findRst / EOF)
+    int pending_err = 0;
+    int err_after_interval = -1;
+};
+
+struct ZpxParsed {
+    int status = 0;          // header-level error (image is not decoded at all)
+    int width = 0, height = 0;
+    int ncomp = 0;
+    int h[ZPX_MAX_COMP] = {0}, v[ZPX_MAX_COMP] = {0}, tq[ZPX_MAX_COMP] = {0};
+    uint8_t cid[ZPX_MAX_COMP] = {0};
+    bool baseline = false, progressive = false;
+    bool jfif = false, adobe_valid = false;
+    int adobe_transform = 0;
+    int mxx = 0, myy = 0;
+    std::vector<ZpxScanHost> scans;
+    int32_t final_quant[4][64];  // quant tables as they stand at EOI (progressive reconstruct)
+    bool saw_sos = false;
+    // error raised by the marker loop AFTER some scans were accepted (e.g. missing EOI):
+    // decoding on the device still happens for earlier errors, this one wins otherwise.
+    int trailing_err = 0;
+    // derived
+    int mode = 0;      // ZPX_MODE_*
+    int variant = 0;   // ZPX_VARIANT_*
+    int ratio = 0;     // ZPX_RATIO_*
+};
+
+// parse one JPEG byte buffer the way decodeInner walks it (decoder.zig:220-373), without
+// decoding any entropy-coded data.  config_only mirrors decodeConfig.
+void zpx_parse_jpeg(const uint8_t* data, size_t len, bool config_only, ZpxParsed* out);
+void zpx_build_huff_dev(const ZpxHuffHost& h, ZpxHuffDev* out, int* malformed);
+void zpx_fill_info(const ZpxParsed& p, zpx_image_info* info);
+
+extern const uint8_t zpx_unzig[64];

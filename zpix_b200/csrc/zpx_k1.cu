@@ -1,0 +1,324 @@
+// zpx_k1.cu -- Huffman / run-length coefficient decode on the GPU.
+//
+// Replaces the MCU loop of processSos (src/jpeg/decoder.zig:1294-1452) together with
+// decodeHuffman (:909-970), ensureNBits (:975-991), readByteStuffedByte (:712-749),
+// receiveExtend (:1115-1134) and decodeBits (:1009-1022) for sequential (SOF0/SOF1) scans.
+// Output: int16 coefficient blocks, natural (de-zigzagged) order, absolute DC, in the HBM layout
+// k2 consumes (zpx_k2.cu header).
+//
+// Semantics kept from the reference, bit for bit on every conforming stream:
+//   * MSB-first bit reader over the byte-stuffed stream (FF 00 -> FF); a 0xFF followed by anything
+//     else is never consumed.  The host hands each restart interval its byte range [start, limit):
+//     limit = first such 0xFF (zpx_parse.cpp).  Bits past the limit read as zero here and any
+//     symbol that needs them is the reference's MissingFF00 (or UnexpectedEof at end of file).
+//   * Huffman codes up to 16 bits, canonical; RECEIVE/EXTEND; DC prediction per component, reset at
+//     each restart interval; AC run-length placement b[unzig[zig]].
+//   * the End-Of-Band-run quirk of sequential scans inside one interval.
+// Error kinds are reported per image through an atomicMin on (scan, block ordinal, code) so the
+// first error in the reference's decode order wins.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "zpx_internal.h"
+#include "zpx_kernels.h"
+
+namespace zpx {
+
+__constant__ uint8_t c_unzig[64] = {
+    0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63,
+};
+
+// ---------------------------------------------------------------------------
+// bit reader over [start, start+len) of the stuffed stream
+// ---------------------------------------------------------------------------
+struct BitReader {
+    const uint32_t* words;  // 4-byte aligned base covering the range
+    uint32_t widx;          // next word to load
+    uint32_t first;         // byte offset (relative to words) of the first valid byte
+    uint32_t end;           // byte offset (relative to words) one past the last valid byte
+    uint64_t buf;           // unread bits, left aligned
+    int cnt;                // number of bits in buf (real + zero padding)
+    uint32_t fed;           // real data bits fed into buf so far
+    uint32_t pad;           // zero padding bits fed after the data ran out
+    uint32_t skip;          // the next byte is the 0x00 of an FF 00 pair
+
+    __device__ __forceinline__ void init(const uint8_t* blob, uint64_t start, uint32_t len) {
+        const uint64_t a = start & ~(uint64_t)3;
+        words = reinterpret_cast<const uint32_t*>(blob + a);
+        first = (uint32_t)(start - a);
+        end = first + len;
+        widx = 0;
+        buf = 0;
+        cnt = 0;
+        fed = 0;
+        pad = 0;
+        skip = 0;
+        fill();
+    }
+
+    // bits consumed so far
+    __device__ __forceinline__ uint32_t used() const { return fed + pad - (uint32_t)cnt; }
+    // true if a symbol needed bits the stream does not have
+    __device__ __forceinline__ bool overrun() const { return used() > fed; }
+
+    // append up to one word; precondition cnt <= 32
+    __device__ __forceinline__ void fill_once() {
+        const uint32_t off = widx * 4;
+        if (off >= end) {  // past the limit: zeros
+            cnt += 32;
+            pad += 32;
+            return;
+        }
+        const uint32_t raw = __ldg(words + widx);
+        widx++;
+        const uint32_t be = __byte_perm(raw, 0, 0x0123);
+        const uint32_t nff = ~raw;
+        const bool has_ff = ((nff - 0x01010101u) & ~nff & 0x80808080u) != 0;
+        if (!has_ff && !skip && off >= first && off + 4 <= end) {
+            buf |= ((uint64_t)be << 32) >> cnt;
+            cnt += 32;
+            fed += 32;
+            return;
+        }
+        // slow path: byte by byte (range edges, FF 00 pairs)
+        uint32_t acc = 0;
+        int nb = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t o = off + j;
+            const uint32_t b = (be >> (24 - 8 * j)) & 0xffu;
+            if (o < first || o >= end) continue;
+            if (skip) {  // the stuffed 0x00
+                skip = 0;
+                continue;
+            }
+            acc = (acc << 8) | b;
+            nb++;
+            if (b == 0xffu) skip = 1;
+        }
+        if (nb) {
+            const uint32_t w = acc << (32 - 8 * nb);
+            buf |= ((uint64_t)w << 32) >> cnt;
+            cnt += 8 * nb;
+            fed += 8 * nb;
+        }
+    }
+    __device__ __forceinline__ void fill() {
+        while (cnt <= 32) fill_once();
+    }
+    __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(buf >> 32); }
+    __device__ __forceinline__ void consume(int n) {
+        buf <<= n;
+        cnt -= n;
+    }
+};
+
+struct HuffSym {
+    uint32_t sym;
+    int len;  // code length; 0 = no code matches (BadHuffmanCode after 16 bits)
+};
+
+// decodeHuffman (decoder.zig:909-970) with a ZPX_LUT_BITS-bit first level
+__device__ __forceinline__ HuffSym huff_decode(const ZpxHuffDev* __restrict__ t, uint32_t hi) {
+    HuffSym r;
+    const uint32_t e = __ldg(&t->lut[hi >> (32 - ZPX_LUT_BITS)]);
+    r.len = (int)(e & 0xffu);
+    r.sym = e >> 8;
+    if (r.len == 0) {
+        const uint32_t v16 = hi >> 16;
+#pragma unroll 1
+        for (int l = ZPX_LUT_BITS + 1; l <= 16; l++) {
+            if (v16 < __ldg(&t->limit[l])) {
+                r.sym = __ldg(&t->vals[(__ldg(&t->valoff[l]) + (int)(v16 >> (16 - l))) & 0xff]);
+                r.len = l;
+                break;
+            }
+        }
+    }
+    return r;
+}
+
+// RECEIVE + EXTEND (decoder.zig:1115-1134) on the `size` bits that follow a `len`-bit code
+__device__ __forceinline__ int receive_extend(uint64_t buf, int len, int size) {
+    const uint32_t t = (uint32_t)((buf << len) >> 32);   // value bits, left aligned
+    const int v = (int)((t >> 1) >> (31 - size));        // size == 0 -> 0
+    const int neg = (size != 0) && !(t >> 31);           // first bit 0 -> negative
+    return neg ? v + ((-1) << size) + 1 : v;
+}
+
+__device__ __forceinline__ void report(unsigned long long* status, uint32_t img_slot, int scan_index, uint64_t ordinal,
+                                       int code) {
+    const unsigned long long key =
+        ((unsigned long long)(uint32_t)scan_index << 48) | ((ordinal & 0xffffffffffull) << 8) | (unsigned)code;
+    atomicMin(&status[img_slot], key);
+}
+
+// ---------------------------------------------------------------------------
+// per-lane block buffer in shared memory: [8 rows][NT lanes] x 16 bytes, so a warp's
+// row loads/stores are contiguous and the scattered int16 stores spread over banks
+// ---------------------------------------------------------------------------
+template <int NT>
+struct LaneBlock {
+    uint4* base;  // this lane's row 0
+    __device__ __forceinline__ void put(int nat, int v) {
+        // natural index -> row (nat>>3), element (nat&7)
+        short* p = reinterpret_cast<short*>(base + (nat >> 3) * NT) + (nat & 7);
+        *p = (short)v;
+    }
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int r = 0; r < 8; r++) base[r * NT] = make_uint4(0, 0, 0, 0);
+    }
+    // write the block to HBM with its rows XOR-swizzled by key, and clear it
+    __device__ __forceinline__ void flush(uint4* dst, int key) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint4 v = base[r * NT];
+            dst[r ^ key] = v;
+            base[r * NT] = make_uint4(0, 0, 0, 0);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// K1a: one lane per restart interval (32 intervals per warp), serial inside the interval
+// ---------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
+    __shared__ uint4 sblk[8 * NT];
+    __shared__ uint8_t s_unzig[64];  // lane-divergent index: shared, not constant, memory
+    const int gid = blockIdx.x * NT + threadIdx.x;
+    LaneBlock<NT> lb;
+    lb.base = sblk + threadIdx.x;
+    lb.clear();
+    if (threadIdx.x < 64) s_unzig[threadIdx.x] = c_unzig[threadIdx.x];
+    __syncthreads();
+    if (gid >= P.n_iv) return;
+
+    const ZpxIntervalDev iv = P.ivs[gid];
+    const ZpxScanDev* __restrict__ sc = &P.scans[iv.scan];
+    const ZpxImageDev* __restrict__ im = &P.imgs[sc->img];
+    const int err_eof = (iv.flags & 1) ? ZPX_E_UnexpectedEof : ZPX_E_MissingFF00;
+
+    BitReader br;
+    br.init(P.blob, iv.start, iv.len);
+
+    const int nblk = sc->nblk;
+    const int mxx = im->mxx;
+    const bool interleaved = sc->interleaved != 0;
+    const bool planar = im->layout == ZPX_LAYOUT_PLANAR;
+    int dc0 = 0, dc1 = 0, dc2 = 0, dc3 = 0;
+    uint32_t eob_run = 0;
+    int err = 0;
+    uint64_t ordinal = (uint64_t)iv.first_mcu * nblk;  // block ordinal inside the scan (error ordering)
+
+    uint32_t mcu = iv.first_mcu;
+    int mx = (int)(mcu % (uint32_t)mxx), my = (int)(mcu / (uint32_t)mxx);
+    // non-interleaved scans: linear block counter over the component's MCU-padded grid
+    // (decoder.zig:1331-1336); blocks outside the image carry no data.
+    const int c0 = sc->blk_comp[0];
+    const int ni_h = im->h[c0], ni_v = im->v[c0];
+    uint32_t block_count = interleaved ? 0 : iv.first_mcu * (uint32_t)(ni_h * ni_v);
+    const int ni_bw = mxx * ni_h;
+
+    for (uint32_t m = 0; m < iv.n_mcu && !err; m++) {
+        for (int b = 0; b < nblk && !err; b++, ordinal++) {
+            const int comp = interleaved ? sc->blk_comp[b] : c0;
+            int bx, by;
+            if (interleaved) {
+                bx = im->h[comp] * mx + sc->blk_hx[b];
+                by = im->v[comp] * my + sc->blk_vy[b];
+            } else {
+                bx = (int)(block_count % (uint32_t)ni_bw);
+                by = (int)(block_count / (uint32_t)ni_bw);
+                block_count++;
+                if (bx * 8 >= im->width || by * 8 >= im->height) continue;
+            }
+            const ZpxHuffDev* __restrict__ tdc = &P.huff[sc->blk_dc[interleaved ? b : 0]];
+            const ZpxHuffDev* __restrict__ tac = &P.huff[sc->blk_ac[interleaved ? b : 0]];
+
+            // ---- DC (decoder.zig:1366-1376) ----
+            br.fill();
+            if (!tdc->defined) { err = ZPX_E_UninitializedHuffmanTable; break; }
+            HuffSym hs = huff_decode(tdc, br.peek32());
+            if (hs.len == 0) {
+                br.consume(16);
+                err = br.overrun() ? err_eof : ZPX_E_BadHuffmanCode;
+                break;
+            }
+            if (hs.sym > 16) {
+                br.consume(hs.len);
+                err = br.overrun() ? err_eof : ZPX_E_ExcessiveDCComponent;
+                break;
+            }
+            const int diff = receive_extend(br.buf, hs.len, (int)hs.sym);
+            br.consume(hs.len + (int)hs.sym);
+            int dc = comp == 0 ? dc0 : comp == 1 ? dc1 : comp == 2 ? dc2 : dc3;
+            dc += diff;
+            if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
+            if (dc < -32768 || dc > 32767) { err = br.overrun() ? err_eof : ZPX_E_COEF_RANGE; break; }
+            lb.put(0, dc);
+
+            // ---- AC (decoder.zig:1378-1411) ----
+            if (eob_run > 0) {
+                eob_run--;
+            } else {
+                if (!tac->defined) { err = ZPX_E_UninitializedHuffmanTable; break; }
+                int k = 1;
+                while (k <= 63) {
+                    br.fill();
+                    hs = huff_decode(tac, br.peek32());
+                    if (hs.len == 0) {
+                        br.consume(16);
+                        err = br.overrun() ? err_eof : ZPX_E_BadHuffmanCode;
+                        break;
+                    }
+                    const int r = (int)(hs.sym >> 4), s = (int)(hs.sym & 15);
+                    if (s != 0) {
+                        k += r;
+                        if (k > 63) {
+                            br.consume(hs.len);
+                            break;
+                        }
+                        const int ac = receive_extend(br.buf, hs.len, s);
+                        br.consume(hs.len + s);
+                        lb.put(s_unzig[k], ac);
+                        k++;
+                    } else if (r != 15) {
+                        // EOB, or the EOB-run form that the reference also honours in sequential scans
+                        eob_run = 1u << r;
+                        if (r != 0) eob_run |= (uint32_t)((br.buf << hs.len) >> (64 - r));
+                        eob_run = (eob_run - 1) & 0xffffu;
+                        br.consume(hs.len + r);
+                        break;
+                    } else {
+                        br.consume(hs.len);
+                        k += 16;
+                    }
+                }
+                if (err) break;
+            }
+            if (br.overrun()) { err = err_eof; break; }
+
+            // ---- hand the block to HBM ----
+            uint64_t blk;
+            if (planar) blk = im->comp_base[comp] + (uint64_t)by * im->comp_bw[comp] + bx;
+            else blk = im->coef_base + (uint64_t)mcu * im->bpm + sc->blk_slot[b];
+            lb.flush(P.coef + blk * 8, bx & 7);
+        }
+        mcu++;
+        if (++mx == mxx) { mx = 0; my++; }
+    }
+    if (err) report(P.status, im->status_slot, sc->scan_index, ordinal, err);
+}
+
+cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s) {
+    if (P.n_iv <= 0) return cudaSuccess;
+    constexpr int NT = 128;
+    k1_lane_per_interval<NT><<<(P.n_iv + NT - 1) / NT, NT, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace zpx

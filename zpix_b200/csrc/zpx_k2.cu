@@ -1,0 +1,408 @@
+// zpx_k2.cu -- block reconstruction and colour: the part of the reference after entropy decode.
+//
+//   k2_fused<H,V,NC>   dequantise + integer IDCT + chroma replication + YCbCr->RGBA + clamp + store,
+//                      one pass over HBM (coefficients in, RGBA out).  Replaces, per image,
+//                      reconstructBlock (decoder.zig:1553-1634), idct.transform (idct.zig:77-201),
+//                      the YCbCr planes of makeImg (:1708-1783), Image.rgbaPixels (image.zig:103-130),
+//                      YCbCrImage.cOffset (image.zig:594-605) and Color.toRGBA (color.zig:90-126).
+//   k2g_idct_planes /  the same work unfused (IDCT -> native planes -> colour), for every stream shape
+//   k2g_colour         the fused kernel does not take (CMYK/YCCK, RGB-tagged, Y 2x2 + C 1x2, multi-scan
+//                      and progressive frames) and for the native-variant output (jpeg.load's planes).
+//
+// Data layout in HBM: coefficients are int16, natural order, 128 B per block,
+// blocks in MCU-interleaved scan order; the eight 16-byte rows of a block are stored XOR-swizzled by
+// (bx & 7), bx = the block's x index inside its component, so that the linear bulk copy of a tile
+// lands in shared memory bank-conflict-free for one-thread-per-block row loads.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "zpx_idct.cuh"
+#include "zpx_internal.h"
+#include "zpx_kernels.h"
+
+namespace zpx {
+
+// ---------------------------------------------------------------------------
+// mbarrier / bulk-copy (TMA unit, non-tensor form) helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fused kernel
+// ---------------------------------------------------------------------------
+// Shared memory (dynamic):
+//   [0,16)     two mbarriers
+//   [16,32)    reserved
+//   QS         3 x 64 int32 quantisers (columns 0/4 prescaled by 2048)
+//   PL         Y plane 8V rows x PY bytes, then Cb, Cr: 8 rows x PC bytes each
+//   ST0, ST1   coefficient stages, tmax * BPM * 128 bytes each
+template <int H, int V, int NC>
+struct K2Cfg {
+    static constexpr int BPM = NC == 1 ? 1 : H * V + 2;
+    static constexpr int YROWS = 8 * V;
+    static constexpr int MCU_W = 8 * H;
+    __host__ __device__ static int pitch_y(int tmax) { return tmax * MCU_W + 16; }
+    __host__ __device__ static int pitch_c(int tmax) { return tmax * 8 + 16; }
+    __host__ __device__ static size_t smem_bytes(int tmax) {
+        size_t s = 32 + 3 * 64 * 4;
+        s += (size_t)YROWS * pitch_y(tmax);
+        if (NC == 3) s += (size_t)2 * 8 * pitch_c(tmax);
+        s = (s + 127) & ~(size_t)127;
+        s += (size_t)2 * tmax * BPM * 128;
+        return s;
+    }
+};
+
+template <int H, int V, int NC>
+__global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
+    using Cfg = K2Cfg<H, V, NC>;
+    constexpr int BPM = Cfg::BPM;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    int* qs = reinterpret_cast<int*>(smem + 32);
+    const int PY = Cfg::pitch_y(P.tmax), PC = Cfg::pitch_c(P.tmax);
+    uint8_t* planeY = smem + 32 + 3 * 64 * 4;
+    uint8_t* planeCb = planeY + Cfg::YROWS * PY;
+    uint8_t* planeCr = planeCb + 8 * PC;
+    size_t st_off = 32 + 3 * 64 * 4 + (size_t)Cfg::YROWS * PY + (NC == 3 ? (size_t)2 * 8 * PC : 0);
+    st_off = (st_off + 127) & ~(size_t)127;
+    uint8_t* stage0 = smem + st_off;
+    const uint32_t stage_bytes = (uint32_t)P.tmax * BPM * 128;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint4* __restrict__ coef = reinterpret_cast<const uint4*>(P.coef);
+    int tile = blockIdx.x;
+    if (tile >= P.ntiles) return;
+
+    // prologue: fetch the first tile
+    if (tid == 0) {
+        const ZpxTileDev t = P.tiles[tile];
+        const ZpxImageDev* im = &P.imgs[t.img];
+        const uint64_t blk0 = im->coef_base + ((uint64_t)t.my * im->mxx + t.mx0) * BPM;
+        const uint32_t bytes = (uint32_t)t.n * BPM * 128;
+        mbar_arrive_expect_tx(&bars[0], bytes);
+        bulk_g2s(stage0, coef + blk0 * 8, bytes, &bars[0]);
+    }
+
+    uint32_t phase0 = 0, phase1 = 0;
+    int stage = 0;
+    int cur_img = -1;
+    for (; tile < P.ntiles; tile += gridDim.x) {
+        const ZpxTileDev t = P.tiles[tile];
+        const ZpxImageDev* __restrict__ im = &P.imgs[t.img];
+        const int n = t.n;
+
+        // prefetch the next tile into the other stage (free since the barrier after last phase 1)
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < P.ntiles) {
+            const ZpxTileDev tn = P.tiles[next];
+            const ZpxImageDev* imn = &P.imgs[tn.img];
+            const uint64_t blk0 = imn->coef_base + ((uint64_t)tn.my * imn->mxx + tn.mx0) * BPM;
+            const uint32_t bytes = (uint32_t)tn.n * BPM * 128;
+            mbar_arrive_expect_tx(&bars[stage ^ 1], bytes);
+            bulk_g2s(stage0 + (size_t)(stage ^ 1) * stage_bytes, coef + blk0 * 8, bytes, &bars[stage ^ 1]);
+        }
+
+        // quantisers of this image (uniform branch)
+        if ((int)t.img != cur_img) {
+            cur_img = (int)t.img;
+            if (tid < 64 * NC) {
+                const int c = tid >> 6, k = tid & 63;
+                int q = P.quant[im->qidx[c]].q[k];
+                if ((k & 7) == 0 || (k & 7) == 4) q <<= 11;  // prescale of idct.zig:100-101 folded in
+                qs[tid] = q;
+            }
+            __syncthreads();
+        }
+
+        mbar_wait(&bars[stage], stage ? phase1 : phase0);
+        if (stage) phase1 ^= 1; else phase0 ^= 1;
+
+        // ---------------- phase 1: one thread per 8x8 block ----------------
+        const uint4* st = reinterpret_cast<const uint4*>(stage0 + (size_t)stage * stage_bytes);
+        const int nY = (NC == 1) ? n : n * H * V;
+        const int nblk = n * BPM;
+        for (int i = tid; i < nblk; i += 256) {
+            int slot, bxa;        // block index inside the stage; absolute component-x of the block
+            uint8_t* dst;
+            int pitch;
+            const int* q;
+            if (i < nY) {
+                const int nH = n * H;
+                const int vy = (V == 2 && i >= nH) ? 1 : 0;
+                const int bx = i - vy * nH;
+                const int m = bx / H, hx = bx % H;
+                slot = m * BPM + vy * H + hx;
+                bxa = (int)t.mx0 * H + bx;
+                dst = planeY + (vy * 8) * PY + bx * 8;
+                pitch = PY;
+                q = qs;
+            } else {
+                const int j = i - nY;
+                const int c = j >= n ? 1 : 0;
+                const int m = j - c * n;
+                slot = m * BPM + H * V + c;
+                bxa = (int)t.mx0 + m;
+                dst = (c ? planeCr : planeCb) + m * 8;
+                pitch = PC;
+                q = qs + 64 * (1 + c);
+            }
+            const uint4* blk = st + slot * 8;
+            const int key = bxa & 7;
+            uint32_t px[16];
+            dequant_idct_block([&](int r) { return blk[r ^ key]; }, q, px);
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                *reinterpret_cast<uint2*>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+        }
+        __syncthreads();
+
+        // ---------------- phase 2: colour + coalesced RGBA stores ----------------
+        {
+            const int W = im->width, Hh = im->height;
+            const int x0 = (int)t.mx0 * Cfg::MCU_W, y0 = (int)t.my * Cfg::YROWS;
+            const int ipr = n * (Cfg::MCU_W / 4);  // 4-pixel items per row
+            const int items = ipr * Cfg::YROWS;
+            const uint32_t magic = 0xffffffffu / (uint32_t)ipr + 1u;  // exact it/ipr for it, ipr < 2^16
+            uint8_t* __restrict__ outp = P.out + im->out_off;
+            const bool vec_ok = (W & 3) == 0;
+            for (int it = tid; it < items; it += 256) {
+                const int row = (int)__umulhi((uint32_t)it, magic);
+                const int xg = it - row * ipr;
+                const int y = y0 + row, x = x0 + 4 * xg;
+                if (y >= Hh || x >= W) continue;
+                const uint32_t yw = *reinterpret_cast<const uint32_t*>(planeY + row * PY + 4 * xg);
+                uint32_t p0, p1, p2, p3;
+                if (NC == 1) {
+                    // .gray: (Y,Y,Y,255)   color.zig:122-126
+                    p0 = (yw & 0xffu) * 0x010101u | 0xff000000u;
+                    p1 = ((yw >> 8) & 0xffu) * 0x010101u | 0xff000000u;
+                    p2 = ((yw >> 16) & 0xffu) * 0x010101u | 0xff000000u;
+                    p3 = (yw >> 24) * 0x010101u | 0xff000000u;
+                } else {
+                    const int crow = (V == 2) ? (row >> 1) : row;
+                    int rr, gg, bb;
+                    if (H == 1) {
+                        const uint32_t cbw = *reinterpret_cast<const uint32_t*>(planeCb + crow * PC + 4 * xg);
+                        const uint32_t crw = *reinterpret_cast<const uint32_t*>(planeCr + crow * PC + 4 * xg);
+                        chroma_terms(cbw & 0xff, crw & 0xff, rr, gg, bb);
+                        p0 = ycc_pixel(yw & 0xff, rr, gg, bb);
+                        chroma_terms((cbw >> 8) & 0xff, (crw >> 8) & 0xff, rr, gg, bb);
+                        p1 = ycc_pixel((yw >> 8) & 0xff, rr, gg, bb);
+                        chroma_terms((cbw >> 16) & 0xff, (crw >> 16) & 0xff, rr, gg, bb);
+                        p2 = ycc_pixel((yw >> 16) & 0xff, rr, gg, bb);
+                        chroma_terms(cbw >> 24, crw >> 24, rr, gg, bb);
+                        p3 = ycc_pixel(yw >> 24, rr, gg, bb);
+                    } else if (H == 2) {
+                        const uint32_t cbw = *reinterpret_cast<const uint16_t*>(planeCb + crow * PC + 2 * xg);
+                        const uint32_t crw = *reinterpret_cast<const uint16_t*>(planeCr + crow * PC + 2 * xg);
+                        chroma_terms(cbw & 0xff, crw & 0xff, rr, gg, bb);
+                        p0 = ycc_pixel(yw & 0xff, rr, gg, bb);
+                        p1 = ycc_pixel((yw >> 8) & 0xff, rr, gg, bb);
+                        chroma_terms(cbw >> 8, crw >> 8, rr, gg, bb);
+                        p2 = ycc_pixel((yw >> 16) & 0xff, rr, gg, bb);
+                        p3 = ycc_pixel(yw >> 24, rr, gg, bb);
+                    } else {  // H == 4
+                        const uint32_t cbv = planeCb[crow * PC + xg];
+                        const uint32_t crv = planeCr[crow * PC + xg];
+                        chroma_terms(cbv, crv, rr, gg, bb);
+                        p0 = ycc_pixel(yw & 0xff, rr, gg, bb);
+                        p1 = ycc_pixel((yw >> 8) & 0xff, rr, gg, bb);
+                        p2 = ycc_pixel((yw >> 16) & 0xff, rr, gg, bb);
+                        p3 = ycc_pixel(yw >> 24, rr, gg, bb);
+                    }
+                }
+                uint8_t* o = outp + ((size_t)y * W + x) * 4;
+                if (vec_ok) {
+                    __stcs(reinterpret_cast<uint4*>(o), make_uint4(p0, p1, p2, p3));
+                } else {
+                    uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
+                    __stcs(o32, p0);
+                    if (x + 1 < W) __stcs(o32 + 1, p1);
+                    if (x + 2 < W) __stcs(o32 + 2, p2);
+                    if (x + 3 < W) __stcs(o32 + 3, p3);
+                }
+            }
+        }
+        __syncthreads();
+        stage ^= 1;
+    }
+}
+
+template <int H, int V, int NC>
+static cudaError_t launch_fused_t(const K2Params& P, int grid, cudaStream_t s) {
+    using Cfg = K2Cfg<H, V, NC>;
+    const size_t smem = Cfg::smem_bytes(P.tmax);
+    cudaError_t e = cudaFuncSetAttribute(k2_fused<H, V, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k2_fused<H, V, NC><<<grid, 256, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
+int k2_fused_bpm(int h, int v, int nc) { return nc == 1 ? 1 : h * v + 2; }
+
+size_t k2_fused_smem(int h, int v, int nc, int tmax) {
+    size_t s = 32 + 3 * 64 * 4;
+    s += (size_t)(8 * v) * (tmax * 8 * h + 16);
+    if (nc == 3) s += (size_t)2 * 8 * (tmax * 8 + 16);
+    s = (s + 127) & ~(size_t)127;
+    s += (size_t)2 * tmax * k2_fused_bpm(h, v, nc) * 128;
+    return s;
+}
+
+cudaError_t k2_launch_fused(int h, int v, int nc, const K2Params& P, int grid, cudaStream_t s) {
+    if (nc == 1) return launch_fused_t<1, 1, 1>(P, grid, s);
+    switch (h << 4 | v) {
+        case 0x11: return launch_fused_t<1, 1, 3>(P, grid, s);
+        case 0x21: return launch_fused_t<2, 1, 3>(P, grid, s);
+        case 0x22: return launch_fused_t<2, 2, 3>(P, grid, s);
+        case 0x12: return launch_fused_t<1, 2, 3>(P, grid, s);
+        case 0x41: return launch_fused_t<4, 1, 3>(P, grid, s);
+        case 0x42: return launch_fused_t<4, 2, 3>(P, grid, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------
+// generic (unfused) path
+// ---------------------------------------------------------------------------
+// One thread per block of one image; blockIdx.y = index into the image list.
+// Writes 8x8 pixels into the component's native plane, exactly where reconstructBlock does.
+__global__ void __launch_bounds__(128) k2g_idct_planes(const K2GParams P) {
+    const ZpxImageDev* __restrict__ im = &P.imgs[P.list[blockIdx.y]];
+    // quantisers of all components with columns 0/4 prescaled (idct.zig:100-101 folded in)
+    __shared__ __align__(16) int qsm[4][64];
+    for (int k = threadIdx.x; k < 64 * im->ncomp; k += blockDim.x) {
+        const int cc = k >> 6, kk = k & 63;
+        int q = P.quant[im->qidx[cc]].q[kk];
+        if ((kk & 7) == 0 || (kk & 7) == 4) q <<= 11;
+        qsm[cc][kk] = q;
+    }
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = 0;
+    for (; c < im->ncomp; c++) {
+        const int cnt = im->comp_bw[c] * im->comp_bh[c];
+        if (i < cnt) break;
+        i -= cnt;
+    }
+    if (c >= im->ncomp) return;
+    const int bw = im->comp_bw[c];
+    const int by = i / bw, bx = i - by * bw;
+    const int h = im->h[c], v = im->v[c];
+    if (im->progressive) {
+        // reconstructProgressiveImage (decoder.zig:1636-1661) only visits blocks that intersect the image
+        const int sx = 8 * (im->hmax / h), sy = 8 * (im->vmax / v);
+        if (bx * sx >= im->width || by * sy >= im->height) return;
+    }
+    uint64_t blk;
+    if (im->layout == ZPX_LAYOUT_INTERLEAVED) {
+        const int mx = bx / h, my = by / v;
+        blk = im->coef_base + ((uint64_t)my * im->mxx + mx) * im->bpm + im->blk_off[c] + (by % v) * h + (bx % h);
+    } else {
+        blk = im->comp_base[c] + (uint64_t)by * bw + bx;
+    }
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(P.coef) + blk * 8;
+    const int key = bx & 7;
+    uint32_t px[16];
+    dequant_idct_block([&](int r) { return __ldg(src + (r ^ key)); }, qsm[c], px);
+    uint8_t* dst = P.planes + im->plane_off[c] + ((size_t)by * 8) * im->plane_stride[c] + (size_t)bx * 8;
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+        *reinterpret_cast<uint2*>(dst + (size_t)r * im->plane_stride[c]) = make_uint2(px[2 * r], px[2 * r + 1]);
+}
+
+// One thread per pixel; blockIdx.y = index into the image list.  Image.rgbaPixels semantics per
+// variant: image.zig:103-130 + color.zig toRGBA, decoder.zig:751-783 convertToRGB,
+// :852-901 applyBlack (CMYK), :811-846 applyBlack (YCbCrK, intent = Go image/jpeg).
+__global__ void __launch_bounds__(256) k2g_colour(const K2GParams P) {
+    const ZpxImageDev* __restrict__ im = &P.imgs[P.list[blockIdx.y]];
+    const int W = im->width, Hh = im->height;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)W * Hh) return;
+    const int y = (int)(idx / W), x = (int)(idx - (size_t)y * W);
+    const uint8_t* __restrict__ pl = P.planes;
+    uint32_t px;
+    const uint8_t Y = pl[im->plane_off[0] + (size_t)y * im->plane_stride[0] + x];
+    if (im->mode == ZPX_MODE_GRAY) {
+        px = (uint32_t)Y * 0x010101u | 0xff000000u;
+    } else {
+        const int hr = im->h[0] / im->h[1], vr = im->v[0] / im->v[1];
+        if (im->mode == ZPX_MODE_CMYK) {
+            // each plane t sub-sampled by >>1 iff its (h,v) differs from component 0's
+            uint32_t v4[4];
+            for (int t = 0; t < 4; t++) {
+                const bool sub = im->h[t] != im->h[0] || im->v[t] != im->v[0];
+                const int sx = sub ? x >> 1 : x, sy = sub ? y >> 1 : y;
+                v4[t] = 255u - pl[im->plane_off[t] + (size_t)sy * im->plane_stride[t] + sx];
+            }
+            px = cmyk_pixel(v4[0], v4[1], v4[2], v4[3]);
+        } else {
+            const int cx = x / hr, cy = y / vr;
+            const uint8_t Cb = pl[im->plane_off[1] + (size_t)cy * im->plane_stride[1] + cx];
+            const uint8_t Cr = pl[im->plane_off[2] + (size_t)cy * im->plane_stride[2] + cx];
+            if (im->mode == ZPX_MODE_RGB) {
+                px = (uint32_t)Y | ((uint32_t)Cb << 8) | ((uint32_t)Cr << 16) | 0xff000000u;
+            } else {
+                int rr, gg, bb;
+                chroma_terms(Cb, Cr, rr, gg, bb);
+                px = ycc_pixel(Y, rr, gg, bb);
+                if (im->mode == ZPX_MODE_YCCK) {
+                    const uint32_t K = 255u - pl[im->plane_off[3] + (size_t)y * im->plane_stride[3] + x];
+                    px = cmyk_pixel(px & 0xff, (px >> 8) & 0xff, (px >> 16) & 0xff, K);
+                }
+            }
+        }
+    }
+    reinterpret_cast<uint32_t*>(P.out + im->out_off)[idx] = px;
+}
+
+cudaError_t k2g_launch(const K2GParams& P, int n_list, int max_blocks, size_t max_pixels, cudaStream_t s) {
+    if (n_list <= 0) return cudaSuccess;
+    dim3 g1((max_blocks + 127) / 128, n_list);
+    k2g_idct_planes<<<g1, 128, 0, s>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dim3 g2((unsigned)((max_pixels + 255) / 256), n_list);
+    k2g_colour<<<g2, 256, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace zpx

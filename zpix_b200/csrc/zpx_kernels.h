@@ -1,0 +1,48 @@
+// zpx_kernels.h -- kernel parameter blocks and host-callable launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "zpx_internal.h"
+
+namespace zpx {
+
+// ---- K1: entropy decode -----------------------------------------------------
+struct K1Params {
+    const uint8_t* blob;          // entropy-coded bytes of the whole device batch, still byte-stuffed
+    const ZpxIntervalDev* ivs;
+    int n_iv;
+    const ZpxScanDev* scans;
+    const ZpxImageDev* imgs;
+    const ZpxHuffDev* huff;
+    uint4* coef;                  // 8 x uint4 per block
+    unsigned long long* status;   // per image: smallest error key, ZPX_STATUS_NONE if none
+};
+cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s);
+
+// ---- K2: fused dequant + IDCT + upsample + colour ------------------------------
+struct K2Params {
+    const int16_t* coef;
+    uint8_t* out;
+    const ZpxImageDev* imgs;
+    const ZpxTileDev* tiles;
+    const ZpxQuantDev* quant;
+    int ntiles;
+    int tmax;  // largest tile (MCUs): fixes the shared-memory layout
+};
+int k2_fused_bpm(int h, int v, int nc);
+size_t k2_fused_smem(int h, int v, int nc, int tmax);
+cudaError_t k2_launch_fused(int h, int v, int nc, const K2Params& P, int grid, cudaStream_t s);
+
+// ---- generic unfused path -------------------------------------------------------
+struct K2GParams {
+    const int16_t* coef;
+    uint8_t* planes;
+    uint8_t* out;
+    const ZpxImageDev* imgs;
+    const ZpxQuantDev* quant;
+    const uint32_t* list;  // image indices taking this path
+};
+cudaError_t k2g_launch(const K2GParams& P, int n_list, int max_blocks, size_t max_pixels, cudaStream_t s);
+
+}  // namespace zpx
