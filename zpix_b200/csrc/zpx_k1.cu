@@ -19,168 +19,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "zpx_entropy.cuh"
 #include "zpx_internal.h"
 #include "zpx_kernels.h"
 
 namespace zpx {
-
-__constant__ uint8_t c_unzig[64] = {
-    0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
-    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
-    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63,
-};
-
-// ---------------------------------------------------------------------------
-// bit reader over [start, start+len) of the stuffed stream
-// ---------------------------------------------------------------------------
-struct BitReader {
-    const uint32_t* words;  // 4-byte aligned base covering the range
-    uint32_t widx;          // next word to load
-    uint32_t first;         // byte offset (relative to words) of the first valid byte
-    uint32_t end;           // byte offset (relative to words) one past the last valid byte
-    uint64_t buf;           // unread bits, left aligned
-    int cnt;                // number of bits in buf (real + zero padding)
-    uint32_t fed;           // real data bits fed into buf so far
-    uint32_t pad;           // zero padding bits fed after the data ran out
-    uint32_t skip;          // the next byte is the 0x00 of an FF 00 pair
-
-    __device__ __forceinline__ void init(const uint8_t* blob, uint64_t start, uint32_t len) {
-        const uint64_t a = start & ~(uint64_t)3;
-        words = reinterpret_cast<const uint32_t*>(blob + a);
-        first = (uint32_t)(start - a);
-        end = first + len;
-        widx = 0;
-        buf = 0;
-        cnt = 0;
-        fed = 0;
-        pad = 0;
-        skip = 0;
-        fill();
-    }
-
-    // bits consumed so far
-    __device__ __forceinline__ uint32_t used() const { return fed + pad - (uint32_t)cnt; }
-    // true if a symbol needed bits the stream does not have
-    __device__ __forceinline__ bool overrun() const { return used() > fed; }
-
-    // append up to one word; precondition cnt <= 32
-    __device__ __forceinline__ void fill_once() {
-        const uint32_t off = widx * 4;
-        if (off >= end) {  // past the limit: zeros
-            cnt += 32;
-            pad += 32;
-            return;
-        }
-        const uint32_t raw = __ldg(words + widx);
-        widx++;
-        const uint32_t be = __byte_perm(raw, 0, 0x0123);
-        const uint32_t nff = ~raw;
-        const bool has_ff = ((nff - 0x01010101u) & ~nff & 0x80808080u) != 0;
-        if (!has_ff && !skip && off >= first && off + 4 <= end) {
-            buf |= ((uint64_t)be << 32) >> cnt;
-            cnt += 32;
-            fed += 32;
-            return;
-        }
-        // slow path: byte by byte (range edges, FF 00 pairs)
-        uint32_t acc = 0;
-        int nb = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t o = off + j;
-            const uint32_t b = (be >> (24 - 8 * j)) & 0xffu;
-            if (o < first || o >= end) continue;
-            if (skip) {  // the stuffed 0x00
-                skip = 0;
-                continue;
-            }
-            acc = (acc << 8) | b;
-            nb++;
-            if (b == 0xffu) skip = 1;
-        }
-        if (nb) {
-            const uint32_t w = acc << (32 - 8 * nb);
-            buf |= ((uint64_t)w << 32) >> cnt;
-            cnt += 8 * nb;
-            fed += 8 * nb;
-        }
-    }
-    __device__ __forceinline__ void fill() {
-        while (cnt <= 32) fill_once();
-    }
-    __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(buf >> 32); }
-    __device__ __forceinline__ void consume(int n) {
-        buf <<= n;
-        cnt -= n;
-    }
-};
-
-struct HuffSym {
-    uint32_t sym;
-    int len;  // code length; 0 = no code matches (BadHuffmanCode after 16 bits)
-};
-
-// decodeHuffman (decoder.zig:909-970) with a ZPX_LUT_BITS-bit first level
-__device__ __forceinline__ HuffSym huff_decode(const ZpxHuffDev* __restrict__ t, uint32_t hi) {
-    HuffSym r;
-    const uint32_t e = __ldg(&t->lut[hi >> (32 - ZPX_LUT_BITS)]);
-    r.len = (int)(e & 0xffu);
-    r.sym = e >> 8;
-    if (r.len == 0) {
-        const uint32_t v16 = hi >> 16;
-#pragma unroll 1
-        for (int l = ZPX_LUT_BITS + 1; l <= 16; l++) {
-            if (v16 < __ldg(&t->limit[l])) {
-                r.sym = __ldg(&t->vals[(__ldg(&t->valoff[l]) + (int)(v16 >> (16 - l))) & 0xff]);
-                r.len = l;
-                break;
-            }
-        }
-    }
-    return r;
-}
-
-// RECEIVE + EXTEND (decoder.zig:1115-1134) on the `size` bits that follow a `len`-bit code
-__device__ __forceinline__ int receive_extend(uint64_t buf, int len, int size) {
-    const uint32_t t = (uint32_t)((buf << len) >> 32);   // value bits, left aligned
-    const int v = (int)((t >> 1) >> (31 - size));        // size == 0 -> 0
-    const int neg = (size != 0) && !(t >> 31);           // first bit 0 -> negative
-    return neg ? v + ((-1) << size) + 1 : v;
-}
-
-__device__ __forceinline__ void report(unsigned long long* status, uint32_t img_slot, int scan_index, uint64_t ordinal,
-                                       int code) {
-    const unsigned long long key =
-        ((unsigned long long)(uint32_t)scan_index << 48) | ((ordinal & 0xffffffffffull) << 8) | (unsigned)code;
-    atomicMin(&status[img_slot], key);
-}
-
-// ---------------------------------------------------------------------------
-// per-lane block buffer in shared memory: [8 rows][NT lanes] x 16 bytes, so a warp's
-// row loads/stores are contiguous and the scattered int16 stores spread over banks
-// ---------------------------------------------------------------------------
-template <int NT>
-struct LaneBlock {
-    uint4* base;  // this lane's row 0
-    __device__ __forceinline__ void put(int nat, int v) {
-        // natural index -> row (nat>>3), element (nat&7)
-        short* p = reinterpret_cast<short*>(base + (nat >> 3) * NT) + (nat & 7);
-        *p = (short)v;
-    }
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int r = 0; r < 8; r++) base[r * NT] = make_uint4(0, 0, 0, 0);
-    }
-    // write the block to HBM with its rows XOR-swizzled by key, and clear it
-    __device__ __forceinline__ void flush(uint4* dst, int key) {
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const uint4 v = base[r * NT];
-            dst[r ^ key] = v;
-            base[r * NT] = make_uint4(0, 0, 0, 0);
-        }
-    }
-};
 
 // ---------------------------------------------------------------------------
 // K1a: one lane per restart interval (32 intervals per warp), serial inside the interval
