@@ -20,9 +20,20 @@ def jpeg():
     return J
 
 
-@pytest.fixture(scope="module")
-def ctx(jpeg):
+# entropy-decoder variants every parity test runs under:
+#   auto   lane-per-interval when the batch has many restart intervals, else self-synchronising
+#   lane   one lane per restart interval (serial inside the interval)
+#   sub    self-synchronising sub-sequence decoder, default sub-sequence size
+#   sub32  the same with 32-byte sub-sequences: many warps per segment, stresses cross-warp sweeps
+ENTROPY_MODES = {"auto": (0, 0), "lane": (1, 0), "sub": (2, 0), "sub32": (2, 32)}
+
+
+@pytest.fixture(scope="module", params=list(ENTROPY_MODES))
+def ctx(jpeg, request):
     c = jpeg.Context()
+    mode, sub = ENTROPY_MODES[request.param]
+    c.set_option(1, mode)
+    c.set_option(3, sub)
     yield c
     c.close()
 

@@ -20,6 +20,8 @@ ap.add_argument("--mode", default="YCbCr")
 ap.add_argument("--dri", type=int, default=1)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--generic", type=int, default=0)
+ap.add_argument("--emode", type=int, default=0)
+ap.add_argument("--subb", type=int, default=0)
 a = ap.parse_args()
 
 print("cpus", os.cpu_count())
@@ -35,6 +37,8 @@ print(f"synth {a.distinct} images in {time.time()-t:.1f}s, avg {sum(map(len, bas
 ctx = jpeg.Context([0])
 if a.generic:
     ctx.set_option(2, 1)
+ctx.set_option(1, a.emode)
+ctx.set_option(3, a.subb)
 t = time.time()
 b = jpeg.Batch(ctx, datas)
 t1 = time.time()

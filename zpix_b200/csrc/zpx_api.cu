@@ -94,8 +94,8 @@ struct DeviceCtx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr};
-    DevBuf blob, coef, out, planes, desc, status;
-    HostBuf stage, hdesc, hstatus;
+    DevBuf blob, coef, out, planes, desc, status, subs;
+    HostBuf stage, hdesc, hstatus, hflag;
 };
 
 // images of one format that take the fused kernel in one launch
@@ -115,6 +115,10 @@ struct DevicePlan {
     std::vector<ZpxHuffDev> huff;
     std::vector<ZpxQuantDev> quant;
     std::vector<FusedGroup> groups;
+    std::vector<ZpxWarpDev> warps;  // self-synchronising mode: one entry per warp
+    size_t n_subs = 0;
+    bool sub_mode = false;
+    size_t off_warps = 0;
     std::vector<uint32_t> generic;  // device image indices on the unfused path
     int generic_max_blocks = 0;
     size_t generic_max_pixels = 0;
@@ -377,6 +381,12 @@ void build_plan(zpx_batch* b, int di) {
                     sd.blk_slot[nb] = (uint8_t)(im.blk_off[c] + j);
                     sd.blk_dc[nb] = (uint16_t)dci;
                     sd.blk_ac[nb] = (uint16_t)aci;
+                    sd.blk_pack[nb][0] = (uint32_t)dci;
+                    sd.blk_pack[nb][1] = (uint32_t)aci;
+                    sd.blk_pack[nb][2] = (uint32_t)c | (uint32_t)(j % p.h[c]) << 8 | (uint32_t)(j / p.h[c]) << 16 |
+                                         (uint32_t)(im.blk_off[c] + j) << 24;
+                    sd.blk_pack[nb][3] = (uint32_t)p.h[c] | (uint32_t)p.v[c] << 8 | (s.dc[i].defined ? 0u : 1u << 16) |
+                                         (s.ac[i].defined ? 0u : 1u << 17);
                     nb++;
                 }
             }
@@ -404,10 +414,45 @@ void build_plan(zpx_batch* b, int di) {
                 d.n_mcu = iv.n_mcu;
                 d.ordinal = ord++;
                 d.flags = iv.eof_limit ? 1u : 0u;
+                if (s.ncomp > 1) {
+                    d.first_block = iv.first_mcu * (uint32_t)nb;
+                    d.n_blocks = iv.n_mcu * (uint32_t)nb;
+                } else {
+                    // non-interleaved: h*v linearised blocks per MCU iteration over the padded grid, only
+                    // those intersecting the image carry data (decoder.zig:1331-1336)
+                    const int c = s.comp[0];
+                    const uint64_t hv = (uint64_t)p.h[c] * p.v[c], bw = (uint64_t)im.comp_bw[c];
+                    auto coded_before = [&](uint64_t x) {
+                        const uint64_t by = x / bw, rem = x % bw;
+                        return std::min<uint64_t>(by, (uint64_t)sd.ch) * sd.cw + (by < (uint64_t)sd.ch ? std::min<uint64_t>(rem, (uint64_t)sd.cw) : 0);
+                    };
+                    const uint64_t x0 = iv.first_mcu * hv, x1 = ((uint64_t)iv.first_mcu + iv.n_mcu) * hv;
+                    d.first_block = (uint32_t)coded_before(x0);
+                    d.n_blocks = (uint32_t)(coded_before(x1) - coded_before(x0));
+                }
+                d.sub_first = d.nsub = d.sub_bytes = d.pad0 = 0;
                 pl.ivs.push_back(d);
             }
         }
         pl.imgs.push_back(im);
+    }
+    // entropy mode: with enough restart intervals to fill the GPU, one lane per interval decodes each
+    // once, serially; otherwise the self-synchronising decoder parallelises inside the intervals
+    const int64_t mode = b->ctx->opt_entropy_mode;
+    pl.sub_mode = mode == 2 || (mode == 0 && pl.ivs.size() < 16384);
+    if (pl.sub_mode) {
+        const uint32_t submax = b->ctx->opt_subseq > 0 ? (uint32_t)align_up((size_t)b->ctx->opt_subseq, 4) : 256u;
+        for (size_t k = 0; k < pl.ivs.size(); k++) {
+            ZpxIntervalDev& d = pl.ivs[k];
+            const uint32_t span = (uint32_t)(d.start & 3) + d.len;
+            uint32_t sub = (uint32_t)align_up((span + 31) / 32, 4);
+            sub = std::max(32u, std::min(submax, sub));
+            d.sub_bytes = sub;
+            d.nsub = std::max(1u, (span + sub - 1) / sub);
+            d.sub_first = (uint32_t)pl.n_subs;
+            pl.n_subs += d.nsub;
+            for (uint32_t f = 0; f < d.nsub; f += 32) pl.warps.push_back({(uint32_t)k, f});
+        }
     }
     // descriptor buffer layout
     size_t off = 0;
@@ -422,6 +467,7 @@ void build_plan(zpx_batch* b, int di) {
     pl.off_huff = place(pl.huff.size() * sizeof(ZpxHuffDev));
     pl.off_quant = place(pl.quant.size() * sizeof(ZpxQuantDev));
     pl.off_generic = place(pl.generic.size() * sizeof(uint32_t));
+    pl.off_warps = place(pl.warps.size() * sizeof(ZpxWarpDev));
     for (FusedGroup& g : pl.groups) g.tiles_off = place(g.tiles.size() * sizeof(ZpxTileDev));
     pl.desc_bytes = off;
     memset(&pl.timing, 0, sizeof(pl.timing));
@@ -459,9 +505,40 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
     k1.huff = (const ZpxHuffDev*)(desc + pl.off_huff);
     k1.coef = (uint4*)dc.coef.p;
     k1.status = (unsigned long long*)dc.status.p;
-    if (k1.n_iv > 0) {
+    if (k1.n_iv > 0 && !pl.sub_mode) {
         CU(ctx, k1_launch_lane_per_interval(k1, st));
         k1_launches++;
+    } else if (k1.n_iv > 0) {
+        K1SParams ks;
+        ks.k1 = k1;
+        ks.warps = (const ZpxWarpDev*)(desc + pl.off_warps);
+        ks.n_warps = (int)pl.warps.size();
+        ks.n_iv = k1.n_iv;
+        uint8_t* sb = (uint8_t*)dc.subs.p;
+        const size_t S = align_up(pl.n_subs, 64);
+        ks.s_dc = (int4*)sb;
+        ks.s_in = (unsigned long long*)(sb + S * 16);
+        ks.s_out = (unsigned long long*)(sb + S * 24);
+        ks.s_n = (int*)(sb + S * 32);
+        ks.changed = (int*)(sb + S * 36);
+        int* hflag = (int*)dc.hflag.p;
+        // sweep 0 decodes every sub-sequence from its guess and settles each warp; later sweeps carry
+        // end states across warp boundaries until nothing changes (exact fixed point)
+        CU(ctx, k1s_launch_sync(ks, 0, st));
+        k1_launches++;
+        bool multi = false;
+        for (const ZpxIntervalDev& d : pl.ivs) multi = multi || d.nsub > 32;
+        for (int sweep = 1; multi; sweep++) {
+            CU(ctx, cudaMemsetAsync(ks.changed, 0, sizeof(int), st));
+            CU(ctx, k1s_launch_sync(ks, sweep, st));
+            k1_launches++;
+            CU(ctx, cudaMemcpyAsync(hflag, ks.changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(ctx, cudaStreamSynchronize(st));
+            if (*hflag == 0) break;
+        }
+        CU(ctx, k1s_launch_scan(ks, st));
+        CU(ctx, k1s_launch_write(ks, st));
+        k1_launches += 2;
     }
     CU(ctx, cudaEventRecord(dc.ev[1], st));
 
@@ -653,6 +730,8 @@ void zpx_ctx_destroy(zpx_ctx* c) {
         d.planes.release();
         d.desc.release();
         d.status.release();
+        d.subs.release();
+        d.hflag.release();
         d.stage.release();
         d.hdesc.release();
         d.hstatus.release();
@@ -775,6 +854,11 @@ int32_t zpx_batch_upload(zpx_batch* b) {
         memcpy(hd + pl.off_huff, pl.huff.data(), pl.huff.size() * sizeof(ZpxHuffDev));
         memcpy(hd + pl.off_quant, pl.quant.data(), pl.quant.size() * sizeof(ZpxQuantDev));
         memcpy(hd + pl.off_generic, pl.generic.data(), pl.generic.size() * sizeof(uint32_t));
+        memcpy(hd + pl.off_warps, pl.warps.data(), pl.warps.size() * sizeof(ZpxWarpDev));
+        if (pl.sub_mode) {
+            CU(ctx, dc.subs.ensure(align_up(pl.n_subs, 64) * 36 + 256));
+            CU(ctx, dc.hflag.ensure(64));
+        }
         for (const FusedGroup& g : pl.groups) memcpy(hd + g.tiles_off, g.tiles.data(), g.tiles.size() * sizeof(ZpxTileDev));
         // entropy-coded segments into pinned staging, parallel over host cores
         uint8_t* stg = (uint8_t*)dc.stage.p;

@@ -21,7 +21,8 @@ __constant__ uint8_t c_unzig[64] = {
 // ---------------------------------------------------------------------------
 struct BitReader {
     const uint32_t* words;  // 4-byte aligned base covering the range
-    uint32_t widx;          // next word to load
+    uint32_t widx;          // next word to feed
+    uint32_t nextw;         // words[widx], loaded one refill ahead so its latency overlaps decoding
     uint32_t first;         // byte offset (relative to words) of the first valid byte
     uint32_t end;           // byte offset (relative to words) one past the last valid byte
     uint64_t buf;           // unread bits, left aligned
@@ -29,6 +30,11 @@ struct BitReader {
     uint32_t fed;           // real data bits fed into buf so far
     uint32_t pad;           // zero padding bits fed after the data ran out
     uint32_t skip;          // the next byte is the 0x00 of an FF 00 pair
+    // sub-sequence boundary tracking (self-synchronising decoder): B = data bits fed before the
+    // feed position reached byte offset bnd (a multiple of 4)
+    uint32_t bnd;
+    uint32_t B;
+    uint32_t bpassed;
 
     __device__ __forceinline__ void init(const uint8_t* blob, uint64_t start, uint32_t len) {
         const uint64_t a = start & ~(uint64_t)3;
@@ -41,7 +47,52 @@ struct BitReader {
         fed = 0;
         pad = 0;
         skip = 0;
+        bnd = 0xffffffffu;
+        B = 0;
+        bpassed = 0;
+        nextw = __ldg(words);
         fill();
+    }
+
+    // start at raw bit position `bitpos` (relative to `w`), which must lie in a data byte;
+    // bytes before it are ignored.  end_off: byte offset of the limit.  boundary: see bnd.
+    __device__ __forceinline__ void init_at(const uint32_t* w, uint32_t bitpos, uint32_t end_off, uint32_t boundary) {
+        words = w;
+        first = bitpos >> 3;
+        end = end_off;
+        widx = first >> 2;
+        buf = 0;
+        cnt = 0;
+        fed = 0;
+        pad = 0;
+        skip = 0;
+        bnd = boundary;
+        B = 0;
+        bpassed = 0;
+        nextw = __ldg(words + widx);
+        fill();
+        consume((int)(bitpos & 7));
+    }
+
+    // raw bit position (relative to words) of the next unread bit.  Walks back over the buffered
+    // data bytes; an FF 00 pair counts as one data byte.  Deterministic for any input; exact
+    // whenever the reader started on a data byte of a well-formed stream.
+    __device__ __forceinline__ uint32_t rawpos() const {
+        const uint8_t* raw = reinterpret_cast<const uint8_t*>(words);
+        uint32_t e = widx * 4;
+        if (e > end) e = end;
+        const uint32_t u = used();
+        if (u > fed) return end * 8 + (u - fed);          // overran the data: past-the-end marker
+        const uint32_t real = fed - u;                    // data bits fed but not yet consumed
+        if (real == 0) return (e + skip) * 8;
+        const uint32_t nbytes = (real + 7) >> 3;
+        const uint32_t headbits = real - 8 * (nbytes - 1);  // unread bits of the head byte, 1..8
+        uint32_t r = e;
+        for (uint32_t k = 0; k < nbytes; k++) {
+            r -= 1;
+            if (r > first && raw[r] == 0x00 && raw[r - 1] == 0xff) r -= 1;
+        }
+        return r * 8 + (8 - headbits);
     }
 
     // bits consumed so far
@@ -52,13 +103,18 @@ struct BitReader {
     // append up to one word; precondition cnt <= 32
     __device__ __forceinline__ void fill_once() {
         const uint32_t off = widx * 4;
+        if (off >= bnd && !bpassed) {
+            bpassed = 1;
+            B = fed;
+        }
         if (off >= end) {  // past the limit: zeros
             cnt += 32;
             pad += 32;
             return;
         }
-        const uint32_t raw = __ldg(words + widx);
+        const uint32_t raw = nextw;
         widx++;
+        nextw = __ldg(words + widx);  // at most one word past the limit: the blob is padded
         const uint32_t be = __byte_perm(raw, 0, 0x0123);
         const uint32_t nff = ~raw;
         const bool has_ff = ((nff - 0x01010101u) & ~nff & 0x80808080u) != 0;
@@ -142,6 +198,108 @@ __device__ __forceinline__ void report(unsigned long long* status, uint32_t img_
 }
 
 // ---------------------------------------------------------------------------
+// One Huffman symbol of a sequential scan, DC or AC alike (decoder.zig:1363-1411): the table, the
+// run/size split and the destination index are selects, so lanes that sit at different symbols of
+// different blocks share one instruction stream.
+//   k        in/out: 0 = the next symbol is the block's DC, 1..63 = next AC zig-zag index
+//   kk       out: zig-zag index the value goes to (valid when store)
+//   SPEC     speculative decode (self-synchronising passes): an invalid code advances one bit and
+//            nothing is an error; DC sums accumulate in dc0..dc3 exactly like the predictors
+// Returns an error code (0 = none); the caller checks br.overrun() to tell MissingFF00 apart.
+// ---------------------------------------------------------------------------
+struct SymOut {
+    int kk, v;
+    bool store, done;
+};
+
+template <bool SPEC>
+__device__ __forceinline__ int symbol_step(BitReader& br, const ZpxHuffDev* __restrict__ tdc,
+                                           const ZpxHuffDev* __restrict__ tac, uint32_t flags, int comp, int& k,
+                                           uint32_t& eob_run, int& dc0, int& dc1, int& dc2, int& dc3, SymOut& o) {
+    int err = 0;
+    br.fill();
+    const uint32_t hi = br.peek32();
+    const bool isdc = k == 0;
+    const ZpxHuffDev* __restrict__ tab = isdc ? tdc : tac;
+    const uint32_t e = __ldg(&tab->lut[hi >> (32 - ZPX_LUT_BITS)]);
+    int len = (int)(e & 0xffu);
+    uint32_t sym = e >> 8;
+    if (len == 0) {  // code longer than the first-level table (about 1 % of the symbols)
+        const uint32_t v16 = hi >> 16;
+#pragma unroll 1
+        for (int l = ZPX_LUT_BITS + 1; l <= 16 && len == 0; l++) {
+            if (v16 < __ldg(&tab->limit[l])) {
+                sym = __ldg(&tab->vals[(__ldg(&tab->valoff[l]) + (int)(v16 >> (16 - l))) & 0xff]);
+                len = l;
+            }
+        }
+        if (len == 0) {
+            if (SPEC) {  // stay in the same state, one bit further
+                br.consume(1);
+                o.store = false;
+                o.done = false;
+                o.kk = 0;
+                o.v = 0;
+                return 0;
+            }
+            len = 16;  // the reference reads 16 bits, then BadHuffmanCode (decoder.zig:947-969)
+            sym = 0;
+            err = ZPX_E_BadHuffmanCode;
+        }
+    }
+    if (!SPEC && (flags & (isdc ? 0x10000u : 0x20000u))) err = ZPX_E_UninitializedHuffmanTable;
+    int size = isdc ? (int)sym : (int)(sym & 15u);
+    const int run = isdc ? 0 : (int)(sym >> 4);
+    if (size > 16) {  // DC category > 16 (decoder.zig:1370)
+        size = 0;
+        if (!SPEC && !err) err = ZPX_E_ExcessiveDCComponent;
+    }
+    int v = receive_extend(br.buf, len, size);
+    int tot = len + size;
+    bool done = false, store = true;
+    int kk = k + run;
+    if (isdc) {
+        // decoder.zig:1366-1376
+        int dc = comp == 0 ? dc0 : comp == 1 ? dc1 : comp == 2 ? dc2 : dc3;
+        dc += v;
+        if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
+        v = dc;
+        kk = 0;
+        k = 1;
+        if (!SPEC && (dc < -32768 || dc > 32767) && !err) err = ZPX_E_COEF_RANGE;
+        if (!SPEC && eob_run > 0) {  // decoder.zig:1379-1380 (End-Of-Band run)
+            eob_run--;
+            done = true;
+        }
+    } else if (size == 0) {
+        store = false;
+        if (run == 15) {  // ZRL
+            k += 16;
+            done = k > 63;
+        } else {          // EOB / EOB run (decoder.zig:1399-1407)
+            eob_run = 1u << run;
+            if (run != 0) eob_run |= (uint32_t)((br.buf << len) >> (64 - run));
+            eob_run = (eob_run - 1) & 0xffffu;
+            tot = len + run;
+            done = true;
+        }
+    } else if (kk > 63) {  // decoder.zig:1393-1395: the value bits stay unread
+        tot = len;
+        store = false;
+        done = true;
+    } else {
+        k = kk + 1;
+        done = k > 63;
+    }
+    br.consume(tot);
+    o.kk = kk;
+    o.v = v;
+    o.store = store;
+    o.done = done;
+    return err;
+}
+
+// ---------------------------------------------------------------------------
 // per-lane block buffer in shared memory: [8 rows][NT lanes] x 16 bytes, so a warp's
 // row loads/stores are contiguous and the scattered int16 stores spread over banks
 // ---------------------------------------------------------------------------
@@ -160,10 +318,10 @@ struct LaneBlock {
     // write the block to HBM with its rows XOR-swizzled by key, and clear it
     __device__ __forceinline__ void flush(uint4* dst, int key) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const uint4 v = base[r * NT];
-            dst[r ^ key] = v;
-            base[r * NT] = make_uint4(0, 0, 0, 0);
+        for (int slot = 0; slot < 8; slot++) {  // slot s of the block holds row s ^ key
+            uint4* src = base + (slot ^ key) * NT;
+            dst[slot] = *src;
+            *src = make_uint4(0, 0, 0, 0);
         }
     }
 };

@@ -85,6 +85,11 @@ struct ZpxScanDev {
     uint8_t blk_slot[ZPX_MAX_BLK_PER_MCU]; // block's index inside the image's interleaved MCU (layout)
     uint16_t blk_dc[ZPX_MAX_BLK_PER_MCU];  // Huffman table indices (into the device table array)
     uint16_t blk_ac[ZPX_MAX_BLK_PER_MCU];
+    // the same, packed for one 16-byte load per block:
+    //   x = DC table index, y = AC table index,
+    //   z = comp | hx << 8 | vy << 16 | slot << 24,
+    //   w = h | v << 8 | (DC table undefined) << 16 | (AC table undefined) << 17
+    alignas(16) uint32_t blk_pack[ZPX_MAX_BLK_PER_MCU][4];
 };
 
 // One restart interval (or the whole scan when DRI == 0): the unit the
@@ -97,6 +102,20 @@ struct ZpxIntervalDev {
     uint32_t n_mcu;      // MCU iterations in this interval
     uint32_t ordinal;    // interval index inside the scan (error ordering)
     uint32_t flags;      // bit0: limit is the end of the file (UnexpectedEof instead of MissingFF00)
+    uint32_t first_block;  // ordinal (inside the scan) of the interval's first coded block
+    uint32_t n_blocks;     // coded blocks in this interval
+    // self-synchronising mode: the interval is cut into nsub sub-sequences of sub_bytes raw bytes,
+    // boundaries at multiples of sub_bytes from (start & ~3); their state lives at sub_first + i
+    uint32_t sub_first;
+    uint32_t nsub;
+    uint32_t sub_bytes;
+    uint32_t pad0;
+};
+
+// one warp of the self-synchronising decoder: 32 consecutive sub-sequences of one interval
+struct ZpxWarpDev {
+    uint32_t iv;     // interval index
+    uint32_t first;  // index (inside the interval) of lane 0's sub-sequence
 };
 
 // K2 tile: a run of MCUs inside one MCU row of one image.

@@ -26,21 +26,27 @@
 namespace zpx {
 
 // ---------------------------------------------------------------------------
-// K1a: one lane per restart interval (32 intervals per warp), serial inside the interval
+// K1a: one lane per restart interval (32 intervals per warp), serial inside the interval.
+//
+// The loop body decodes ONE Huffman symbol per lane per iteration, DC or AC alike (the table, the
+// run/size split and the destination index are selects), so the 32 lanes of a warp -- which sit at
+// different symbols of different blocks -- execute one common instruction stream.  Only the end of a
+// block (flush of the 128-byte block, next block's descriptor) and the rare paths (codes longer than
+// ZPX_LUT_BITS, FF 00 inside a refill word, errors) are divergent.
 // ---------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
     __shared__ uint4 sblk[8 * NT];
-    __shared__ uint8_t s_unzig[64];  // lane-divergent index: shared, not constant, memory
+    __shared__ uint8_t s_unzig[80];  // lane-divergent index: shared, not constant, memory (padded: k+run <= 78)
     const int gid = blockIdx.x * NT + threadIdx.x;
     LaneBlock<NT> lb;
     lb.base = sblk + threadIdx.x;
     lb.clear();
-    if (threadIdx.x < 64) s_unzig[threadIdx.x] = c_unzig[threadIdx.x];
+    if (threadIdx.x < 80) s_unzig[threadIdx.x] = threadIdx.x < 64 ? c_unzig[threadIdx.x] : 63;
     __syncthreads();
-    if (gid >= P.n_iv) return;
 
-    const ZpxIntervalDev iv = P.ivs[gid];
+    // lanes past the end of the interval list idle through the loop (the loop head is a warp vote)
+    const ZpxIntervalDev iv = P.ivs[gid < P.n_iv ? gid : P.n_iv - 1];
     const ZpxScanDev* __restrict__ sc = &P.scans[iv.scan];
     const ZpxImageDev* __restrict__ im = &P.imgs[sc->img];
     const int err_eof = (iv.flags & 1) ? ZPX_E_UnexpectedEof : ZPX_E_MissingFF00;
@@ -48,113 +54,85 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
     BitReader br;
     br.init(P.blob, iv.start, iv.len);
 
-    const int nblk = sc->nblk;
-    const int mxx = im->mxx;
     const bool interleaved = sc->interleaved != 0;
-    const bool planar = im->layout == ZPX_LAYOUT_PLANAR;
+    const int nblk = interleaved ? sc->nblk : 1;
+    const uint32_t mxx = (uint32_t)im->mxx;
+    const bool planar = im->layout == ZPX_LAYOUT_PLANAR || !interleaved;
+    const uint4* __restrict__ bpack = reinterpret_cast<const uint4*>(sc->blk_pack);
+    const uint32_t cw = (uint32_t)sc->cw;
+
+    // position of the current block
+    uint32_t mcu = iv.first_mcu, mx = 0, my = 0, bxn = 0, byn = 0;
+    if (interleaved) {
+        mx = mcu % mxx;
+        my = mcu / mxx;
+    } else {  // n-th coded block of the component, row-major over the blocks that intersect the image
+        byn = iv.first_block / cw;
+        bxn = iv.first_block - byn * cw;
+    }
+    int c = 0;
+    uint4 bi = bpack[0];
+    const ZpxHuffDev* __restrict__ tdc = &P.huff[bi.x];
+    const ZpxHuffDev* __restrict__ tac = &P.huff[bi.y];
+
     int dc0 = 0, dc1 = 0, dc2 = 0, dc3 = 0;
     uint32_t eob_run = 0;
+    int k = 0;                       // 0: the next symbol is the block's DC; 1..63: next AC index
+    uint32_t left = gid < P.n_iv ? iv.n_blocks : 0;  // blocks still to decode (including the current one)
     int err = 0;
-    uint64_t ordinal = (uint64_t)iv.first_mcu * nblk;  // block ordinal inside the scan (error ordering)
 
-    uint32_t mcu = iv.first_mcu;
-    int mx = (int)(mcu % (uint32_t)mxx), my = (int)(mcu / (uint32_t)mxx);
-    // non-interleaved scans: linear block counter over the component's MCU-padded grid
-    // (decoder.zig:1331-1336); blocks outside the image carry no data.
-    const int c0 = sc->blk_comp[0];
-    const int ni_h = im->h[c0], ni_v = im->v[c0];
-    uint32_t block_count = interleaved ? 0 : iv.first_mcu * (uint32_t)(ni_h * ni_v);
-    const int ni_bw = mxx * ni_h;
-
-    for (uint32_t m = 0; m < iv.n_mcu && !err; m++) {
-        for (int b = 0; b < nblk && !err; b++, ordinal++) {
-            const int comp = interleaved ? sc->blk_comp[b] : c0;
-            int bx, by;
-            if (interleaved) {
-                bx = im->h[comp] * mx + sc->blk_hx[b];
-                by = im->v[comp] * my + sc->blk_vy[b];
-            } else {
-                bx = (int)(block_count % (uint32_t)ni_bw);
-                by = (int)(block_count / (uint32_t)ni_bw);
-                block_count++;
-                if (bx * 8 >= im->width || by * 8 >= im->height) continue;
-            }
-            const ZpxHuffDev* __restrict__ tdc = &P.huff[sc->blk_dc[interleaved ? b : 0]];
-            const ZpxHuffDev* __restrict__ tac = &P.huff[sc->blk_ac[interleaved ? b : 0]];
-
-            // ---- DC (decoder.zig:1366-1376) ----
-            br.fill();
-            if (!tdc->defined) { err = ZPX_E_UninitializedHuffmanTable; break; }
-            HuffSym hs = huff_decode(tdc, br.peek32());
-            if (hs.len == 0) {
-                br.consume(16);
-                err = br.overrun() ? err_eof : ZPX_E_BadHuffmanCode;
-                break;
-            }
-            if (hs.sym > 16) {
-                br.consume(hs.len);
-                err = br.overrun() ? err_eof : ZPX_E_ExcessiveDCComponent;
-                break;
-            }
-            const int diff = receive_extend(br.buf, hs.len, (int)hs.sym);
-            br.consume(hs.len + (int)hs.sym);
-            int dc = comp == 0 ? dc0 : comp == 1 ? dc1 : comp == 2 ? dc2 : dc3;
-            dc += diff;
-            if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
-            if (dc < -32768 || dc > 32767) { err = br.overrun() ? err_eof : ZPX_E_COEF_RANGE; break; }
-            lb.put(0, dc);
-
-            // ---- AC (decoder.zig:1378-1411) ----
-            if (eob_run > 0) {
-                eob_run--;
-            } else {
-                if (!tac->defined) { err = ZPX_E_UninitializedHuffmanTable; break; }
-                int k = 1;
-                while (k <= 63) {
-                    br.fill();
-                    hs = huff_decode(tac, br.peek32());
-                    if (hs.len == 0) {
-                        br.consume(16);
-                        err = br.overrun() ? err_eof : ZPX_E_BadHuffmanCode;
-                        break;
-                    }
-                    const int r = (int)(hs.sym >> 4), s = (int)(hs.sym & 15);
-                    if (s != 0) {
-                        k += r;
-                        if (k > 63) {
-                            br.consume(hs.len);
-                            break;
-                        }
-                        const int ac = receive_extend(br.buf, hs.len, s);
-                        br.consume(hs.len + s);
-                        lb.put(s_unzig[k], ac);
-                        k++;
-                    } else if (r != 15) {
-                        // EOB, or the EOB-run form that the reference also honours in sequential scans
-                        eob_run = 1u << r;
-                        if (r != 0) eob_run |= (uint32_t)((br.buf << hs.len) >> (64 - r));
-                        eob_run = (eob_run - 1) & 0xffffu;
-                        br.consume(hs.len + r);
-                        break;
+    // One Huffman symbol per lane per iteration; the vote keeps the warp in lock step.
+    while (__any_sync(0xffffffffu, left != 0)) {
+        if (left != 0) {
+            SymOut so;
+            err = symbol_step<false>(br, tdc, tac, bi.w, (int)(bi.z & 0xff), k, eob_run, dc0, dc1, dc2, dc3, so);
+            const bool done = so.done;
+            if (so.store) lb.put(s_unzig[so.kk], so.v);
+            if (err) {
+                // a symbol that needed bits past the limit is the reference's MissingFF00 / UnexpectedEof,
+                // whatever the garbage decoded to
+                if (br.overrun()) err = err_eof;
+                report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + (iv.n_blocks - left), err);
+                left = 0;
+            } else if (done) {
+                if (br.overrun()) {
+                    report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + (iv.n_blocks - left), err_eof);
+                    left = 0;
+                } else {
+                    // ---- hand the block to HBM ----
+                    const int comp = (int)(bi.z & 0xff);
+                    int bx, by;
+                    if (interleaved) {
+                        bx = (int)(bi.w & 0xff) * (int)mx + (int)((bi.z >> 8) & 0xff);
+                        by = (int)((bi.w >> 8) & 0xff) * (int)my + (int)((bi.z >> 16) & 0xff);
                     } else {
-                        br.consume(hs.len);
-                        k += 16;
+                        bx = (int)bxn;
+                        by = (int)byn;
+                    }
+                    uint64_t blk;
+                    if (planar) blk = im->comp_base[comp] + (uint64_t)by * im->comp_bw[comp] + bx;
+                    else blk = im->coef_base + (uint64_t)mcu * im->bpm + (bi.z >> 24);
+                    lb.flush(P.coef + blk * 8, bx & 7);
+                    // ---- next block ----
+                    left--;
+                    k = 0;
+                    if (interleaved) {
+                        if (++c == nblk) {
+                            c = 0;
+                            mcu++;
+                            if (++mx == mxx) { mx = 0; my++; }
+                        }
+                        bi = bpack[c];
+                        tdc = &P.huff[bi.x];
+                        tac = &P.huff[bi.y];
+                    } else if (++bxn == cw) {
+                        bxn = 0;
+                        byn++;
                     }
                 }
-                if (err) break;
             }
-            if (br.overrun()) { err = err_eof; break; }
-
-            // ---- hand the block to HBM ----
-            uint64_t blk;
-            if (planar) blk = im->comp_base[comp] + (uint64_t)by * im->comp_bw[comp] + bx;
-            else blk = im->coef_base + (uint64_t)mcu * im->bpm + sc->blk_slot[b];
-            lb.flush(P.coef + blk * 8, bx & 7);
         }
-        mcu++;
-        if (++mx == mxx) { mx = 0; my++; }
     }
-    if (err) report(P.status, im->status_slot, sc->scan_index, ordinal, err);
 }
 
 cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s) {

@@ -1,0 +1,369 @@
+// zpx_k1s.cu -- self-synchronising speculative Huffman decode for entropy-coded segments that have
+// no (or too few) restart markers.  Same reference code as zpx_k1.cu (processSos MCU loop,
+// src/jpeg/decoder.zig:1294-1452, and the bit/Huffman layer :909-1134), parallelised INSIDE a segment.
+//
+// A segment ("domain": a restart interval, or the whole scan when DRI = 0) is cut into sub-sequences
+// of sub_bytes raw bytes; one lane per sub-sequence, 32 consecutive sub-sequences per warp.
+// Decoder state at a symbol boundary: (raw bit position, block index inside the MCU, zig-zag index).
+//
+//   k1s_sync   every lane decodes its sub-sequence (no output) from a start state and records the
+//              state in which the decoder crosses into the next sub-sequence, the number of blocks it
+//              started and the sum of the DC differences it decoded, per component.  Sub-sequence 0
+//              starts in the true state, the others from a guess (boundary byte, block 0, DC).  Lanes
+//              hand their end state to the next lane (shuffle inside the warp, global memory across
+//              warps, one kernel launch per sweep) and re-decode while their start state changes.
+//              Fixed point => every start state is the true one, by induction from sub-sequence 0
+//              (F_i(true start of i) = true start of i+1); Huffman streams re-synchronise after a
+//              few symbols, so this takes 2-3 rounds in practice but is exact for any input.
+//   k1s_scan   exclusive prefix sums, per domain, of the block counts and DC sums (wrapping int32
+//              adds: identical to the sequential accumulation of decoder.zig:1374).
+//   k1s_write  every lane decodes again from its true start state and writes the blocks that START
+//              inside its sub-sequence (it skips the tail of a block begun earlier and runs past
+//              its boundary to finish its last block), absolute DC included.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "zpx_entropy.cuh"
+#include "zpx_internal.h"
+#include "zpx_kernels.h"
+
+namespace zpx {
+
+constexpr int K1S_NT = 128;  // threads per CTA (4 warps)
+
+__device__ __forceinline__ unsigned long long pack_state(uint32_t pos, int c, int z) {
+    return (unsigned long long)pos | ((unsigned long long)(uint32_t)c << 32) | ((unsigned long long)(uint32_t)z << 40);
+}
+
+struct LaneCtx {
+    const ZpxIntervalDev* iv;
+    const ZpxScanDev* sc;
+    const ZpxImageDev* im;
+    const uint32_t* words;  // (blob + start) rounded down to 4 bytes
+    uint32_t first;         // byte offset of the domain's first byte inside words
+    uint32_t end;           // byte offset of the limit
+    uint32_t li;            // sub-sequence index inside the domain
+    uint32_t bnd;           // byte offset of this sub-sequence's end boundary
+};
+
+__device__ __forceinline__ void lane_setup(const K1Params& P, const ZpxWarpDev w, int lane, LaneCtx& L) {
+    L.iv = &P.ivs[w.iv];
+    L.sc = &P.scans[L.iv->scan];
+    L.im = &P.imgs[L.sc->img];
+    const uint64_t a = L.iv->start & ~(uint64_t)3;
+    L.words = reinterpret_cast<const uint32_t*>(P.blob + a);
+    L.first = (uint32_t)(L.iv->start - a);
+    L.end = L.first + L.iv->len;
+    L.li = w.first + lane;
+    L.bnd = (L.li + 1) * L.iv->sub_bytes;
+}
+
+// Decode (without output) from state `in` until the first symbol that starts at or after the
+// sub-sequence boundary, or the data runs out.  Invalid codes advance one bit (any deterministic
+// rule works: true states of a well-formed stream never meet one; errors are reported by k1s_write).
+// Called by the lanes in `mask` together; the vote at the loop head keeps them in lock step.
+__device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, const LaneCtx& L, unsigned long long in,
+                                                          unsigned mask, int& n_out, int4& dc_out) {
+    BitReader br;
+    br.init_at(L.words, (uint32_t)in, L.end, L.bnd);
+    int c = (int)((in >> 32) & 0xff), k = (int)((in >> 40) & 0xff);
+    const ZpxScanDev* __restrict__ sc = L.sc;
+    const int nblk = sc->interleaved ? sc->nblk : 1;
+    const uint4* __restrict__ bpack = reinterpret_cast<const uint4*>(sc->blk_pack);
+    int n = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+    uint32_t eob_run = 0;
+    uint4 bi = bpack[c];
+    const ZpxHuffDev* __restrict__ tdc = &P.huff[bi.x];
+    const ZpxHuffDev* __restrict__ tac = &P.huff[bi.y];
+    bool go = true;
+    while (__any_sync(mask, go)) {
+        if (go) {
+            const uint32_t u = br.used();
+            if ((br.bpassed && u >= br.B) || (br.pad && u >= br.fed)) {
+                go = false;
+            } else {
+                n += k == 0;
+                SymOut so;
+                symbol_step<true>(br, tdc, tac, bi.w, (int)(bi.z & 0xff), k, eob_run, d0, d1, d2, d3, so);
+                if (so.done) {
+                    k = 0;
+                    c = c + 1 == nblk ? 0 : c + 1;
+                    bi = bpack[c];
+                    tdc = &P.huff[bi.x];
+                    tac = &P.huff[bi.y];
+                }
+            }
+        }
+    }
+    n_out = n;
+    dc_out = make_int4(d0, d1, d2, d3);
+    return pack_state(br.rawpos(), c, k);
+}
+
+// ---------------------------------------------------------------------------
+// sweep kernel
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int sweep) {
+    const int wid = blockIdx.x * (K1S_NT / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wid >= P.n_warps) return;
+    const ZpxWarpDev w = P.warps[wid];
+    LaneCtx L;
+    lane_setup(P.k1, w, lane, L);
+    const bool active = L.li < L.iv->nsub;
+    const uint32_t t = L.iv->sub_first + L.li;
+    const bool last_active = active && (lane == 31 || L.li + 1 == L.iv->nsub);
+    const bool more_warps = w.first + 32 < L.iv->nsub;
+
+    unsigned long long in = 0, out = 0, old_out = 0;
+    int n = 0;
+    int4 dc = make_int4(0, 0, 0, 0);
+    bool dirty = false;
+    if (sweep == 0) {
+        if (active) {
+            in = L.li == 0 ? pack_state(L.first * 8, 0, 0) : pack_state(L.li * L.iv->sub_bytes * 8, 0, 0);
+            dirty = true;
+        }
+    } else {
+        if (active) {
+            in = P.s_in[t];
+            out = P.s_out[t];
+            old_out = out;
+            n = P.s_n[t];
+            dc = P.s_dc[t];
+            if (lane == 0 && w.first > 0) {
+                const unsigned long long ni = P.s_out[t - 1];
+                if (ni != in) {
+                    in = ni;
+                    dirty = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, dirty)) return;
+    }
+    bool touched = false;
+    do {
+        const unsigned dm = __ballot_sync(0xffffffffu, dirty);
+        if (dirty) {
+            out = sync_decode(P.k1, L, in, dm, n, dc);
+            touched = true;
+        }
+        const unsigned long long po = __shfl_up_sync(0xffffffffu, out, 1);
+        bool nd = false;
+        if (lane > 0 && active && po != in) {
+            in = po;
+            nd = true;
+        }
+        dirty = nd;
+    } while (__any_sync(0xffffffffu, dirty));
+    if (active && touched) {
+        P.s_in[t] = in;
+        P.s_out[t] = out;
+        P.s_n[t] = n;
+        P.s_dc[t] = dc;
+    }
+    if (last_active && more_warps && (sweep == 0 || out != old_out)) atomicExch(P.changed, 1);
+}
+
+// ---------------------------------------------------------------------------
+// per-domain exclusive scan of (blocks started, DC sums); one warp per domain
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(K1S_NT) k1s_scan(const K1SParams P) {
+    const int d = blockIdx.x * (K1S_NT / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (d >= P.n_iv) return;
+    const ZpxIntervalDev* iv = &P.k1.ivs[d];
+    const uint32_t nsub = iv->nsub, base = iv->sub_first;
+    int cn = 0;
+    int4 cd = make_int4(0, 0, 0, 0);
+    for (uint32_t i0 = 0; i0 < nsub; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        int n = 0;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (i < nsub) {
+            n = P.s_n[base + i];
+            v = P.s_dc[base + i];
+        }
+        int sn = n;
+        int4 sv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tn = __shfl_up_sync(0xffffffffu, sn, o);
+            const int tx = __shfl_up_sync(0xffffffffu, sv.x, o), ty = __shfl_up_sync(0xffffffffu, sv.y, o);
+            const int tz = __shfl_up_sync(0xffffffffu, sv.z, o), tw = __shfl_up_sync(0xffffffffu, sv.w, o);
+            if (lane >= o) {
+                sn += tn;
+                sv.x += tx;
+                sv.y += ty;
+                sv.z += tz;
+                sv.w += tw;
+            }
+        }
+        if (i < nsub) {
+            P.s_n[base + i] = cn + sn - n;
+            P.s_dc[base + i] = make_int4(cd.x + sv.x - v.x, cd.y + sv.y - v.y, cd.z + sv.z - v.z, cd.w + sv.w - v.w);
+        }
+        cn += __shfl_sync(0xffffffffu, sn, 31);
+        cd.x += __shfl_sync(0xffffffffu, sv.x, 31);
+        cd.y += __shfl_sync(0xffffffffu, sv.y, 31);
+        cd.z += __shfl_sync(0xffffffffu, sv.z, 31);
+        cd.w += __shfl_sync(0xffffffffu, sv.w, 31);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// write kernel
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(K1S_NT) k1s_write(const K1SParams P) {
+    __shared__ uint4 sblk[8 * K1S_NT];
+    __shared__ uint8_t s_unzig[80];
+    LaneBlock<K1S_NT> lb;
+    lb.base = sblk + threadIdx.x;
+    lb.clear();
+    if (threadIdx.x < 80) s_unzig[threadIdx.x] = threadIdx.x < 64 ? c_unzig[threadIdx.x] : 63;
+    __syncthreads();
+    const int wid = blockIdx.x * (K1S_NT / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wid >= P.n_warps) return;  // whole warp
+    const ZpxWarpDev w = P.warps[wid];
+    LaneCtx L;
+    lane_setup(P.k1, w, lane, L);
+    const ZpxIntervalDev* __restrict__ iv = L.iv;
+    const ZpxScanDev* __restrict__ sc = L.sc;
+    const ZpxImageDev* __restrict__ im = L.im;
+    const bool valid = L.li < iv->nsub;
+    const uint32_t t = iv->sub_first + (valid ? L.li : 0);
+    const unsigned long long in = P.s_in[t];
+    const int excl_n = P.s_n[t];
+    const int4 excl_dc = P.s_dc[t];
+    const int err_eof = (iv->flags & 1) ? ZPX_E_UnexpectedEof : ZPX_E_MissingFF00;
+
+    BitReader br;
+    br.init_at(L.words, (uint32_t)in, L.end, L.bnd);
+    int c = (int)((in >> 32) & 0xff), k = (int)((in >> 40) & 0xff);
+    const bool interleaved = sc->interleaved != 0;
+    const int nblk = interleaved ? sc->nblk : 1;
+    const bool planar = im->layout == ZPX_LAYOUT_PLANAR || !interleaved;
+    const uint4* __restrict__ bpack = reinterpret_cast<const uint4*>(sc->blk_pack);
+    uint4 bi = bpack[c];
+    const ZpxHuffDev* __restrict__ tdc = &P.k1.huff[bi.x];
+    const ZpxHuffDev* __restrict__ tac = &P.k1.huff[bi.y];
+
+    // a lane whose start state is inside a block first skips that block's tail (it belongs to the
+    // lane in whose sub-sequence the block started); `skipping` ends at the first block start
+    bool skipping = k != 0;
+    int dc0 = excl_dc.x, dc1 = excl_dc.y, dc2 = excl_dc.z, dc3 = excl_dc.w;
+    uint32_t eob_run = 0;
+    uint32_t j = (uint32_t)excl_n;  // index (inside the domain) of the next block this lane starts
+    const uint32_t mxx = (uint32_t)im->mxx;
+    const uint32_t cw = (uint32_t)sc->cw;
+    uint32_t mcu = 0, mx = 0, my = 0, bxn = 0, byn = 0;
+    // the block that follows a skipped tail has phase c+1; j % nblk says the same for true states
+    {
+        const uint32_t jj = j;
+        if (interleaved) {
+            mcu = iv->first_mcu + jj / (uint32_t)nblk;
+            mx = mcu % mxx;
+            my = mcu / mxx;
+        } else {
+            const uint32_t o = iv->first_block + jj;
+            byn = o / cw;
+            bxn = o - byn * cw;
+        }
+    }
+    bool go = valid && j < iv->n_blocks;
+    while (__any_sync(0xffffffffu, go)) {
+        if (go) {
+            // a block (or a skipped tail's successor) may only START before the boundary
+            const uint32_t u = br.used();
+            if (k == 0 && !skipping && br.bpassed && u >= br.B) {
+                go = false;
+            } else if (skipping && ((br.bpassed && u >= br.B) || (br.pad && u >= br.fed))) {
+                go = false;  // no block starts inside this sub-sequence
+            } else {
+                SymOut so;
+                int err;
+                if (skipping) {
+                    int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                    uint32_t er = 0;
+                    err = symbol_step<true>(br, tdc, tac, bi.w, 0, k, er, s0, s1, s2, s3, so);
+                    if (so.done) {
+                        skipping = false;
+                        k = 0;
+                        c = c + 1 == nblk ? 0 : c + 1;
+                        bi = bpack[c];
+                        tdc = &P.k1.huff[bi.x];
+                        tac = &P.k1.huff[bi.y];
+                    }
+                } else {
+                    err = symbol_step<false>(br, tdc, tac, bi.w, (int)(bi.z & 0xff), k, eob_run, dc0, dc1, dc2, dc3, so);
+                    if (so.store) lb.put(s_unzig[so.kk], so.v);
+                    // End-Of-Band RUN inside a sequential scan: the reference blanks the next
+                    // blocks; the speculative passes do not model that state
+                    if (!err && eob_run != 0) err = ZPX_E_UNSUPPORTED_STREAM;
+                    if (err) {
+                        if (br.overrun()) err = err_eof;
+                        report(P.k1.status, im->status_slot, sc->scan_index, (uint64_t)iv->first_block + j, err);
+                        go = false;
+                    } else if (so.done) {
+                        if (br.overrun()) {
+                            report(P.k1.status, im->status_slot, sc->scan_index, (uint64_t)iv->first_block + j, err_eof);
+                            go = false;
+                        } else {
+                            const int comp = (int)(bi.z & 0xff);
+                            int bx, by;
+                            if (interleaved) {
+                                bx = (int)(bi.w & 0xff) * (int)mx + (int)((bi.z >> 8) & 0xff);
+                                by = (int)((bi.w >> 8) & 0xff) * (int)my + (int)((bi.z >> 16) & 0xff);
+                            } else {
+                                bx = (int)bxn;
+                                by = (int)byn;
+                            }
+                            uint64_t blk;
+                            if (planar) blk = im->comp_base[comp] + (uint64_t)by * im->comp_bw[comp] + bx;
+                            else blk = im->coef_base + (uint64_t)mcu * im->bpm + (bi.z >> 24);
+                            lb.flush(P.k1.coef + blk * 8, bx & 7);
+                            k = 0;
+                            j++;
+                            if (j >= iv->n_blocks) go = false;
+                            if (interleaved) {
+                                if (++c == nblk) {
+                                    c = 0;
+                                    mcu++;
+                                    if (++mx == mxx) { mx = 0; my++; }
+                                }
+                                bi = bpack[c];
+                                tdc = &P.k1.huff[bi.x];
+                                tac = &P.k1.huff[bi.y];
+                            } else if (++bxn == cw) {
+                                bxn = 0;
+                                byn++;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+cudaError_t k1s_launch_sync(const K1SParams& P, int sweep, cudaStream_t s) {
+    if (P.n_warps <= 0) return cudaSuccess;
+    const int wpc = K1S_NT / 32;
+    k1s_sync<<<(P.n_warps + wpc - 1) / wpc, K1S_NT, 0, s>>>(P, sweep);
+    return cudaGetLastError();
+}
+cudaError_t k1s_launch_scan(const K1SParams& P, cudaStream_t s) {
+    if (P.n_iv <= 0) return cudaSuccess;
+    const int wpc = K1S_NT / 32;
+    k1s_scan<<<(P.n_iv + wpc - 1) / wpc, K1S_NT, 0, s>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t k1s_launch_write(const K1SParams& P, cudaStream_t s) {
+    if (P.n_warps <= 0) return cudaSuccess;
+    const int wpc = K1S_NT / 32;
+    k1s_write<<<(P.n_warps + wpc - 1) / wpc, K1S_NT, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace zpx

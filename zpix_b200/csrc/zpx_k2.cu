@@ -195,69 +195,78 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
         __syncthreads();
 
         // ---------------- phase 2: colour + coalesced RGBA stores ----------------
+        // One item = RP luma rows x PXW pixels.  V = 2: both rows of a chroma row, 4 px wide, so the
+        // per-chroma-sample terms are computed once per 2x2 (4:2:0) replication; V = 1: 8 px wide.
         {
+            constexpr int RP = V;                    // luma rows per item
+            constexpr int PXW = (V == 2) ? 4 : 8;    // pixels per item row
+            constexpr int NCS = (PXW / H) > 0 ? (PXW / H) : 1;  // chroma samples per item row
             const int W = im->width, Hh = im->height;
             const int x0 = (int)t.mx0 * Cfg::MCU_W, y0 = (int)t.my * Cfg::YROWS;
-            const int ipr = n * (Cfg::MCU_W / 4);  // 4-pixel items per row
-            const int items = ipr * Cfg::YROWS;
-            const uint32_t magic = 0xffffffffu / (uint32_t)ipr + 1u;  // exact it/ipr for it, ipr < 2^16
+            const int ipr = n * (Cfg::MCU_W / PXW);  // items per row(-pair)
+            const int items = ipr * (Cfg::YROWS / RP);
+            const uint32_t magic = ipr > 1 ? 0xffffffffu / (uint32_t)ipr + 1u : 0u;  // exact it/ipr for it, ipr < 2^16
             uint8_t* __restrict__ outp = P.out + im->out_off;
             const bool vec_ok = (W & 3) == 0;
             for (int it = tid; it < items; it += 256) {
-                const int row = (int)__umulhi((uint32_t)it, magic);
-                const int xg = it - row * ipr;
-                const int y = y0 + row, x = x0 + 4 * xg;
+                const int rp = ipr > 1 ? (int)__umulhi((uint32_t)it, magic) : it;
+                const int xg = it - rp * ipr;
+                const int row0 = rp * RP;
+                const int y = y0 + row0, x = x0 + PXW * xg;
                 if (y >= Hh || x >= W) continue;
-                const uint32_t yw = *reinterpret_cast<const uint32_t*>(planeY + row * PY + 4 * xg);
-                uint32_t p0, p1, p2, p3;
-                if (NC == 1) {
-                    // .gray: (Y,Y,Y,255)   color.zig:122-126
-                    p0 = (yw & 0xffu) * 0x010101u | 0xff000000u;
-                    p1 = ((yw >> 8) & 0xffu) * 0x010101u | 0xff000000u;
-                    p2 = ((yw >> 16) & 0xffu) * 0x010101u | 0xff000000u;
-                    p3 = (yw >> 24) * 0x010101u | 0xff000000u;
-                } else {
-                    const int crow = (V == 2) ? (row >> 1) : row;
-                    int rr, gg, bb;
-                    if (H == 1) {
-                        const uint32_t cbw = *reinterpret_cast<const uint32_t*>(planeCb + crow * PC + 4 * xg);
-                        const uint32_t crw = *reinterpret_cast<const uint32_t*>(planeCr + crow * PC + 4 * xg);
-                        chroma_terms(cbw & 0xff, crw & 0xff, rr, gg, bb);
-                        p0 = ycc_pixel(yw & 0xff, rr, gg, bb);
-                        chroma_terms((cbw >> 8) & 0xff, (crw >> 8) & 0xff, rr, gg, bb);
-                        p1 = ycc_pixel((yw >> 8) & 0xff, rr, gg, bb);
-                        chroma_terms((cbw >> 16) & 0xff, (crw >> 16) & 0xff, rr, gg, bb);
-                        p2 = ycc_pixel((yw >> 16) & 0xff, rr, gg, bb);
-                        chroma_terms(cbw >> 24, crw >> 24, rr, gg, bb);
-                        p3 = ycc_pixel(yw >> 24, rr, gg, bb);
-                    } else if (H == 2) {
-                        const uint32_t cbw = *reinterpret_cast<const uint16_t*>(planeCb + crow * PC + 2 * xg);
-                        const uint32_t crw = *reinterpret_cast<const uint16_t*>(planeCr + crow * PC + 2 * xg);
-                        chroma_terms(cbw & 0xff, crw & 0xff, rr, gg, bb);
-                        p0 = ycc_pixel(yw & 0xff, rr, gg, bb);
-                        p1 = ycc_pixel((yw >> 8) & 0xff, rr, gg, bb);
-                        chroma_terms(cbw >> 8, crw >> 8, rr, gg, bb);
-                        p2 = ycc_pixel((yw >> 16) & 0xff, rr, gg, bb);
-                        p3 = ycc_pixel(yw >> 24, rr, gg, bb);
-                    } else {  // H == 4
-                        const uint32_t cbv = planeCb[crow * PC + xg];
-                        const uint32_t crv = planeCr[crow * PC + xg];
-                        chroma_terms(cbv, crv, rr, gg, bb);
-                        p0 = ycc_pixel(yw & 0xff, rr, gg, bb);
-                        p1 = ycc_pixel((yw >> 8) & 0xff, rr, gg, bb);
-                        p2 = ycc_pixel((yw >> 16) & 0xff, rr, gg, bb);
-                        p3 = ycc_pixel(yw >> 24, rr, gg, bb);
+                int rr[NCS], gg[NCS], bb[NCS];
+                if (NC == 3) {
+                    const int crow = (V == 2) ? rp : row0;
+                    const uint8_t* cbp = planeCb + crow * PC + (PXW * xg) / H;
+                    const uint8_t* crp = planeCr + crow * PC + (PXW * xg) / H;
+                    uint32_t cbw[2] = {0, 0}, crw[2] = {0, 0};
+                    if (NCS == 8) {
+                        const uint2 a2 = *reinterpret_cast<const uint2*>(cbp), b2 = *reinterpret_cast<const uint2*>(crp);
+                        cbw[0] = a2.x; cbw[1] = a2.y; crw[0] = b2.x; crw[1] = b2.y;
+                    } else if (NCS == 4) {
+                        cbw[0] = *reinterpret_cast<const uint32_t*>(cbp);
+                        crw[0] = *reinterpret_cast<const uint32_t*>(crp);
+                    } else if (NCS == 2) {
+                        cbw[0] = *reinterpret_cast<const uint16_t*>(cbp);
+                        crw[0] = *reinterpret_cast<const uint16_t*>(crp);
+                    } else {
+                        cbw[0] = *cbp;
+                        crw[0] = *crp;
                     }
+#pragma unroll
+                    for (int k = 0; k < NCS; k++)
+                        chroma_terms((cbw[k >> 2] >> (8 * (k & 3))) & 0xff, (crw[k >> 2] >> (8 * (k & 3))) & 0xff, rr[k], gg[k], bb[k]);
                 }
-                uint8_t* o = outp + ((size_t)y * W + x) * 4;
-                if (vec_ok) {
-                    __stcs(reinterpret_cast<uint4*>(o), make_uint4(p0, p1, p2, p3));
-                } else {
-                    uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
-                    __stcs(o32, p0);
-                    if (x + 1 < W) __stcs(o32 + 1, p1);
-                    if (x + 2 < W) __stcs(o32 + 2, p2);
-                    if (x + 3 < W) __stcs(o32 + 3, p3);
+#pragma unroll
+                for (int r = 0; r < RP; r++) {
+                    if (y + r >= Hh) break;
+                    uint8_t* o = outp + ((size_t)(y + r) * W + x) * 4;
+#pragma unroll
+                    for (int g = 0; g < PXW / 4; g++) {
+                        if (g > 0 && x + 4 * g >= W) break;
+                        const uint32_t yw = *reinterpret_cast<const uint32_t*>(planeY + (row0 + r) * PY + PXW * xg + 4 * g);
+                        uint32_t p[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t yv = (yw >> (8 * j)) & 0xffu;
+                            if (NC == 1) {
+                                p[j] = yv * 0x010101u | 0xff000000u;  // .gray: (Y,Y,Y,255), color.zig:122-126
+                            } else {
+                                const int ci = (4 * g + j) / H;
+                                p[j] = ycc_pixel((int)yv, rr[ci], gg[ci], bb[ci]);
+                            }
+                        }
+                        if (vec_ok) {
+                            __stcs(reinterpret_cast<uint4*>(o) + g, make_uint4(p[0], p[1], p[2], p[3]));
+                        } else {
+                            uint32_t* o32 = reinterpret_cast<uint32_t*>(o) + 4 * g;
+                            const int xx = x + 4 * g;
+                            __stcs(o32, p[0]);
+                            if (xx + 1 < W) __stcs(o32 + 1, p[1]);
+                            if (xx + 2 < W) __stcs(o32 + 2, p[2]);
+                            if (xx + 3 < W) __stcs(o32 + 3, p[3]);
+                        }
+                    }
                 }
             }
         }

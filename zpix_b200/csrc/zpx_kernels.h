@@ -20,6 +20,22 @@ struct K1Params {
 };
 cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s);
 
+// self-synchronising sub-sequence decoder (streams without DRI, or few large intervals)
+struct K1SParams {
+    K1Params k1;
+    const ZpxWarpDev* warps;
+    int n_warps;
+    int n_iv;                 // intervals (domains), for the scan kernel
+    unsigned long long* s_in;   // per sub-sequence: start state used by its latest decode
+    unsigned long long* s_out;  //                   state at its end boundary
+    int* s_n;                   //                   blocks started inside it (then: exclusive prefix)
+    int4* s_dc;                 //                   DC difference sums per component (then: exclusive prefix)
+    int* changed;               // device flag: an end state crossing a warp boundary changed in this sweep
+};
+cudaError_t k1s_launch_sync(const K1SParams& P, int sweep, cudaStream_t s);
+cudaError_t k1s_launch_scan(const K1SParams& P, cudaStream_t s);
+cudaError_t k1s_launch_write(const K1SParams& P, cudaStream_t s);
+
 // ---- K2: fused dequant + IDCT + upsample + colour ------------------------------
 struct K2Params {
     const int16_t* coef;
