@@ -39,6 +39,27 @@ CACHE = os.environ.get("ZPX_SYNTH_CACHE", "/tmp/zpx_synth")
 WORKLOAD = "cfg2: 1024 x 1920x1080 baseline 4:2:0 YCbCr JPEG, DRI = 1 MCU row (120 MCUs), quality 85, per GPU"
 
 
+def reduce_max(value: float, dist, device) -> float:
+    """max over ranks of a per-rank device time (ms); identity when not distributed"""
+    if dist is None:
+        return float(value)
+    import torch
+
+    t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def aggregate_value(pixels_per_rank: int, world: int, ms_per_step: float) -> float:
+    """whole-job Mpixels/s: units all ranks processed / max-over-ranks time"""
+    return world * pixels_per_rank / 1e6 / (ms_per_step / 1e3)
+
+
+def rank_seed_range(n_images: int, rank: int):
+    """weak scaling: every rank decodes its own copy of the same cfg2 batch (seeds 20000 ..)"""
+    return range(20000, 20000 + n_images)
+
+
 def make_workload(n_images: int, rank: int, world: int, barrier):
     from tools import synth_jpeg as S
 
@@ -123,7 +144,7 @@ def run_reference(args, rank, world):
         return
     datas = make_workload(min(args.images, 64), 0, 1, lambda: None)
     threads = os.cpu_count() or 1
-    per_step = max(threads * 2, 32)
+    per_step = max(threads * 8, 64)
     for _ in range(args.warmup):
         cpu_oracle_throughput(datas, threads, threads)
     t0 = time.perf_counter()
@@ -214,12 +235,9 @@ def main():
     launches = ctx.kernel_launches - launches0
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     tm = batch.timing(0)  # per-stage CUDA events of the last step, recorded on the launching stream
-    t = torch.tensor([ms_total], device="cuda")
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = reduce_max(ms_total, dist, "cuda")
     ms_per_step = ms_total / args.steps
-    value = world * pixels / 1e6 / (ms_per_step / 1e3)
+    value = aggregate_value(pixels, world, ms_per_step)
 
     # K2 roofline: average over a few more steps of the fused kernel's own events
     fused_ms, ent_ms = [], []
@@ -257,11 +275,8 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / args.e2e_steps
-    t = torch.tensor([e2e_ms], device="cuda")
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e_value = world * pixels / 1e6 / (e2e_ms / 1e3)
+    e2e_ms = reduce_max(e2e_ms, dist, "cuda")
+    e2e_value = aggregate_value(pixels, world, e2e_ms)
     # spot-check the end-to-end output of one image against the oracle
     if rank == 0:
         from oracle import oracle as O
@@ -279,7 +294,7 @@ def main():
     cpu = None
     if world == 1:
         threads = os.cpu_count() or 1
-        n_dec = max(threads * 8, 64)
+        n_dec = max(threads * 24, 128)  # ~10-20 s of CPU work in total
         v, dt = cpu_oracle_throughput(datas[:64], n_dec, threads)
         v1, dt1 = cpu_oracle_throughput(datas[:64], 16, 1)
         cpu = {"value": v, "unit": "Mpixels/s", "cores": threads, "kind": "port",

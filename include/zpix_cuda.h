@@ -229,6 +229,11 @@ typedef struct zpx_parse_report {
 } zpx_parse_report;
 int32_t zpx_parse_report_of(const uint8_t *buf, size_t len, zpx_image_info *info, zpx_parse_report *rep);
 
+/* The scheduler's partition rule, host only (test hook): contiguous index ranges over n_devices,
+ * balanced by weight (zpx_batch_open uses entropy-coded bytes + a constant per image).
+ * weight 0 = image not scheduled (device_of = -1). */
+int32_t zpx_partition(const uint64_t *weights, int32_t n, int32_t n_devices, int32_t *device_of);
+
 /* ---- knobs (tests / benchmarks) ----------------------------------------- */
 #define ZPX_OPT_ENTROPY_MODE 1  /* 0 auto, 1 lane-per-interval, 2 warp-per-interval/subsequence */
 #define ZPX_OPT_FORCE_GENERIC 2 /* 1: always use the unfused planar IDCT + colour kernels */

@@ -69,6 +69,7 @@ SYMBOLS = [
                                           C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]),
     ("zpx_probe", C.c_int32, [_P, C.c_size_t, C.POINTER(ZpxImageInfo)]),
     ("zpx_parse_report_of", C.c_int32, [_P, C.c_size_t, C.POINTER(ZpxImageInfo), C.POINTER(ZpxParseReport)]),
+    ("zpx_partition", C.c_int32, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     ("zpx_ctx_set_option", C.c_int32, [_P, C.c_int32, C.c_int64]),
     ("zpx_host_alloc", _P, [C.c_size_t]),
     ("zpx_host_free", None, [_P]),

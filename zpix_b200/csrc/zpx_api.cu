@@ -202,15 +202,16 @@ bool fused_eligible(const ZpxParsed& p) {
 
 struct TableDedup {
     std::map<std::string, int> huff_ix, quant_ix;
-    int add_huff(const ZpxHuffHost& h, std::vector<ZpxHuffDev>& out) {
+    int add_huff(const ZpxHuffHost& h, bool is_ac, std::vector<ZpxHuffDev>& out) {
         std::string key((const char*)h.counts, 16);
         key.append((const char*)h.vals, 256);
         key.push_back(h.defined ? 1 : 0);
+        key.push_back(is_ac ? 1 : 0);
         auto it = huff_ix.find(key);
         if (it != huff_ix.end()) return it->second;
         ZpxHuffDev d;
         int malformed = 0;
-        zpx_build_huff_dev(h, &d, &malformed);
+        zpx_build_huff_dev(h, is_ac, &d, &malformed);
         out.push_back(d);
         int ix = (int)out.size() - 1;
         huff_ix.emplace(std::move(key), ix);
@@ -373,7 +374,7 @@ void build_plan(zpx_batch* b, int di) {
             int nb = 0;
             for (int i = 0; i < s.ncomp; i++) {
                 const int c = s.comp[i];
-                const int dci = dd.add_huff(s.dc[i], pl.huff), aci = dd.add_huff(s.ac[i], pl.huff);
+                const int dci = dd.add_huff(s.dc[i], false, pl.huff), aci = dd.add_huff(s.ac[i], true, pl.huff);
                 for (int j = 0; j < p.h[c] * p.v[c]; j++) {
                     sd.blk_comp[nb] = (uint8_t)c;
                     sd.blk_hx[nb] = (uint8_t)(j % p.h[c]);
@@ -689,6 +690,23 @@ int32_t zpx_parse_report_of(const uint8_t* buf, size_t len, zpx_image_info* info
     return ZPX_OK;
 }
 
+int32_t zpx_partition(const uint64_t* weights, int32_t n, int32_t n_devices, int32_t* device_of) {
+    if (n < 0 || n_devices <= 0 || (n > 0 && (!weights || !device_of))) return ZPX_E_INVALID_ARG;
+    uint64_t total = 0;
+    for (int i = 0; i < n; i++) total += weights[i];
+    uint64_t acc = 0;
+    for (int i = 0; i < n; i++) {
+        if (weights[i] == 0) {
+            device_of[i] = -1;
+            continue;
+        }
+        // the device whose share of the total weight contains this image's midpoint: contiguous, monotone
+        device_of[i] = (int32_t)std::min<uint64_t>((uint64_t)n_devices - 1, (acc + weights[i] / 2) * (uint64_t)n_devices / total);
+        acc += weights[i];
+    }
+    return ZPX_OK;
+}
+
 int32_t zpx_ctx_create(const int32_t* device_ids, int32_t n_devices, zpx_ctx** out) {
     if (!out) return ZPX_E_INVALID_ARG;
     *out = nullptr;
@@ -805,12 +823,11 @@ int32_t zpx_batch_open(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* l
         w[i] += 1024;
         total += w[i];
     }
-    uint64_t acc = 0;
+    (void)total;
+    zpx_partition(w.data(), n, nd, b->dev_of.data());
     for (int i = 0; i < n; i++) {
-        if (b->parsed[i].status != 0) continue;
-        int d = total ? (int)std::min<uint64_t>(nd - 1, (acc + w[i] / 2) * nd / total) : 0;
-        acc += w[i];
-        b->dev_of[i] = d;
+        const int d = b->dev_of[i];
+        if (d < 0) continue;
         b->slot_of[i] = (int)b->plans[d].images.size();
         b->plans[d].images.push_back(i);
     }

@@ -22,7 +22,12 @@
 // code or invalid.  Longer codes: smallest l with v16 < limit[l] (v16 = next 16 bits, left aligned),
 // symbol = vals[valoff[l] + (v16 >> (16 - l))]  -- the canonical decode the reference does bit by
 // bit at decoder.zig:946-969; identical results for every code of the table.
+// fast[]: everything the per-symbol step needs in one 32-bit load:
+//   bits 0-5 tot (bits to consume: len+size), 8-12 len, 13-17 size (value bits), 18-24 adv (how far the
+//   zig-zag index moves: DC 1, AC run+1, ZRL 16, EOB 64), bit 31 special (EOB run, DC category > 16);
+//   0 = code longer than ZPX_LUT_BITS or invalid -> canonical search.
 struct ZpxHuffDev {
+    uint32_t fast[ZPX_LUT_SIZE];
     uint16_t lut[ZPX_LUT_SIZE];
     uint32_t limit[17];  // index 1..16
     int32_t valoff[17];  // index 1..16
@@ -187,7 +192,8 @@ struct ZpxParsed {
 // parse one JPEG byte buffer the way decodeInner walks it (decoder.zig:220-373), without
 // decoding any entropy-coded data.  config_only mirrors decodeConfig.
 void zpx_parse_jpeg(const uint8_t* data, size_t len, bool config_only, ZpxParsed* out);
-void zpx_build_huff_dev(const ZpxHuffHost& h, ZpxHuffDev* out, int* malformed);
+void zpx_build_huff_dev(const ZpxHuffHost& h, bool is_ac, ZpxHuffDev* out, int* malformed);
+uint32_t zpx_fast_entry(bool is_ac, int len, int sym);
 void zpx_fill_info(const ZpxParsed& p, zpx_image_info* info);
 
 extern const uint8_t zpx_unzig[64];

@@ -28,30 +28,161 @@ namespace zpx {
 // ---------------------------------------------------------------------------
 // K1a: one lane per restart interval (32 intervals per warp), serial inside the interval.
 //
-// The loop body decodes ONE Huffman symbol per lane per iteration, DC or AC alike (the table, the
-// run/size split and the destination index are selects), so the 32 lanes of a warp -- which sit at
-// different symbols of different blocks -- execute one common instruction stream.  Only the end of a
-// block (flush of the 128-byte block, next block's descriptor) and the rare paths (codes longer than
-// ZPX_LUT_BITS, FF 00 inside a refill word, errors) are divergent.
+// The loop body decodes ONE Huffman symbol per lane per iteration, DC or AC alike, from a 32-bit
+// table entry that already holds code length, value bits, zig-zag advance and total bits
+// (ZpxHuffDev::fast), so the 32 lanes of a warp -- which sit at different symbols of different
+// blocks -- share one short instruction stream; the loop head is a warp vote that keeps them in
+// lock step.  Divergent: the end of a block (flush of the 128-byte block, next block's descriptor) and
+// the rare paths (codes longer than ZPX_LUT_BITS, 0xFF inside a refill word, EOB runs, errors).
+// The stream words are loaded two refills ahead so that their latency overlaps decoding.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, int v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((short)v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_zero16(uint32_t addr) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// stuffed-stream reader with the words loaded two refills ahead
+struct FastReader {
+    const uint32_t* wp;  // next word to LOAD
+    uint32_t w1, w2;     // loaded words: w1 is fed next, then w2
+    uint32_t off;        // byte offset (from the 4-byte aligned base) of w1
+    uint32_t first, end; // valid byte range
+    uint64_t buf;        // unread bits, left aligned
+    int cnt;             // bits in buf (data + zero padding)
+    int pad;             // zero padding bits appended after the data ran out (always at the tail)
+    uint32_t skip;       // next byte is the 0x00 of an FF 00 pair
+
+    __device__ __forceinline__ void init(const uint8_t* blob, uint64_t start, uint32_t len) {
+        const uint64_t a = start & ~(uint64_t)3;
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(blob + a);
+        first = (uint32_t)(start - a);
+        end = first + len;
+        off = 0;
+        w1 = __ldg(base);
+        w2 = __ldg(base + 1);
+        wp = base + 2;
+        buf = 0;
+        cnt = 0;
+        pad = 0;
+        skip = 0;
+        while (cnt <= 32) refill();
+    }
+    __device__ __forceinline__ bool overrun() const { return cnt < pad; }
+
+    // feed one word; precondition cnt <= 32
+    __device__ __forceinline__ void refill() {
+        const uint32_t raw = w1;
+        w1 = w2;
+        const uint32_t o = off;
+        off += 4;
+        if (off + 4 < end + 8) w2 = __ldg(wp++);  // never more than 2 words past the limit (blob is padded)
+        const uint32_t nff = ~raw;
+        const uint32_t hasff = (nff - 0x01010101u) & raw & 0x80808080u;
+        const uint32_t be = __byte_perm(raw, 0, 0x0123);
+        if ((hasff | skip) == 0 && o >= first && o + 4 <= end) {
+            buf |= ((uint64_t)be << 32) >> cnt;
+            cnt += 32;
+            return;
+        }
+        if (o >= end) {  // past the limit: zeros
+            cnt += 32;
+            pad += 32;
+            return;
+        }
+        // byte by byte: range edges, FF 00 pairs
+        uint32_t acc = 0;
+        int nb = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t oo = o + j;
+            const uint32_t b = (be >> (24 - 8 * j)) & 0xffu;
+            if (oo < first || oo >= end) continue;
+            if (skip) {
+                skip = 0;
+                continue;
+            }
+            acc = (acc << 8) | b;
+            nb++;
+            if (b == 0xffu) skip = 1;
+        }
+        if (nb) {
+            const uint32_t w = acc << (32 - 8 * nb);
+            buf |= ((uint64_t)w << 32) >> cnt;
+            cnt += 8 * nb;
+        }
+    }
+};
+
+// rare path of the symbol step: code longer than the first-level table, or a special entry.
+// Returns the fast-entry fields for the symbol, or 0 with err set.
+__device__ __noinline__ uint32_t k1_slow_symbol(const ZpxHuffDev* __restrict__ tab, uint32_t hi, bool isdc, uint32_t e,
+                                                int* err) {
+    if (e == 0) {
+        const uint32_t v16 = hi >> 16;
+        int len = 0;
+        uint32_t sym = 0;
+        for (int l = ZPX_LUT_BITS + 1; l <= 16 && len == 0; l++) {
+            if (v16 < tab->limit[l]) {
+                sym = tab->vals[(tab->valoff[l] + (int)(v16 >> (16 - l))) & 0xff];
+                len = l;
+            }
+        }
+        if (len == 0) {  // the reference reads 16 bits, then BadHuffmanCode (decoder.zig:947-969)
+            *err = ZPX_E_BadHuffmanCode;
+            return 16u | 16u << 8 | 64u << 18;
+        }
+        // same field packing as zpx_fast_entry (zpx_parse.cpp)
+        uint32_t size, adv, special = 0;
+        if (isdc) {
+            size = sym;
+            adv = 1;
+            if (sym > 16) { special = 1; size = 0; }
+        } else {
+            const uint32_t r = sym >> 4, s2 = sym & 15;
+            if (s2 != 0) { size = s2; adv = r + 1; }
+            else if (r == 15) { size = 0; adv = 16; }
+            else if (r == 0) { size = 0; adv = 64; }
+            else { size = 0; adv = 64; special = 1; }
+        }
+        e = ((uint32_t)len + size) | (uint32_t)len << 8 | size << 13 | adv << 18 | special << 31;
+    }
+    if ((e >> 31) && isdc) {  // DC category > 16 (decoder.zig:1370)
+        *err = ZPX_E_ExcessiveDCComponent;
+        e &= 0x7fffffffu;
+    }
+    return e;  // AC special (EOB run) keeps bit 31: the caller reads the run bits
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
-    __shared__ uint4 sblk[8 * NT];
+    __shared__ uint4 sblk[8 * NT];   // per-lane block: [8 rows][NT lanes] x 16 bytes
     __shared__ uint8_t s_unzig[80];  // lane-divergent index: shared, not constant, memory (padded: k+run <= 78)
     const int gid = blockIdx.x * NT + threadIdx.x;
-    LaneBlock<NT> lb;
-    lb.base = sblk + threadIdx.x;
-    lb.clear();
+    for (int r = 0; r < 8; r++) sblk[r * NT + threadIdx.x] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x < 80) s_unzig[threadIdx.x] = threadIdx.x < 64 ? c_unzig[threadIdx.x] : 63;
     __syncthreads();
+    const uint32_t sb = smem_addr(sblk) + threadIdx.x * 16;  // this lane's row 0
+    const uint32_t su = smem_addr(s_unzig);
 
     // lanes past the end of the interval list idle through the loop (the loop head is a warp vote)
     const ZpxIntervalDev iv = P.ivs[gid < P.n_iv ? gid : P.n_iv - 1];
     const ZpxScanDev* __restrict__ sc = &P.scans[iv.scan];
     const ZpxImageDev* __restrict__ im = &P.imgs[sc->img];
-    const int err_eof = (iv.flags & 1) ? ZPX_E_UnexpectedEof : ZPX_E_MissingFF00;
 
-    BitReader br;
+    FastReader br;
     br.init(P.blob, iv.start, iv.len);
 
     const bool interleaved = sc->interleaved != 0;
@@ -60,6 +191,8 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
     const bool planar = im->layout == ZPX_LAYOUT_PLANAR || !interleaved;
     const uint4* __restrict__ bpack = reinterpret_cast<const uint4*>(sc->blk_pack);
     const uint32_t cw = (uint32_t)sc->cw;
+    const uint64_t coef_base = im->coef_base;
+    const uint32_t bpm = (uint32_t)im->bpm;
 
     // position of the current block
     uint32_t mcu = iv.first_mcu, mx = 0, my = 0, bxn = 0, byn = 0;
@@ -72,47 +205,116 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
     }
     int c = 0;
     uint4 bi = bpack[0];
-    const ZpxHuffDev* __restrict__ tdc = &P.huff[bi.x];
-    const ZpxHuffDev* __restrict__ tac = &P.huff[bi.y];
+    const uint32_t* __restrict__ fdc = P.huff[bi.x].fast;
+    const uint32_t* __restrict__ fac = P.huff[bi.y].fast;
 
     int dc0 = 0, dc1 = 0, dc2 = 0, dc3 = 0;
     uint32_t eob_run = 0;
     int k = 0;                       // 0: the next symbol is the block's DC; 1..63: next AC index
     uint32_t left = gid < P.n_iv ? iv.n_blocks : 0;  // blocks still to decode (including the current one)
-    int err = 0;
 
-    // One Huffman symbol per lane per iteration; the vote keeps the warp in lock step.
     while (__any_sync(0xffffffffu, left != 0)) {
         if (left != 0) {
-            SymOut so;
-            err = symbol_step<false>(br, tdc, tac, bi.w, (int)(bi.z & 0xff), k, eob_run, dc0, dc1, dc2, dc3, so);
-            const bool done = so.done;
-            if (so.store) lb.put(s_unzig[so.kk], so.v);
+            if (br.cnt <= 32) br.refill();
+            if (br.cnt <= 32) br.refill();  // a word with FF 00 pairs or a range edge feeds fewer than 32 bits
+            const uint32_t hi = (uint32_t)(br.buf >> 32);
+            const bool isdc = k == 0;
+            const uint32_t* __restrict__ ftab = isdc ? fdc : fac;
+            uint32_t e = __ldg(ftab + (hi >> (32 - ZPX_LUT_BITS)));
+            int err = 0;
+            if ((int)e <= 0) {  // longer code, invalid code, EOB run or DC category > 16: about 1 % of the symbols
+                e = k1_slow_symbol(reinterpret_cast<const ZpxHuffDev*>(ftab), hi, isdc, e, &err);
+            }
+            if (bi.w & (isdc ? 0x10000u : 0x20000u)) err = ZPX_E_UninitializedHuffmanTable;
+            const int len = (int)((e >> 8) & 31u), size = (int)((e >> 13) & 31u);
+            int tot = (int)(e & 63u);
+            const int adv = (int)((e >> 18) & 127u);
+            // RECEIVE + EXTEND (decoder.zig:1115-1134): size bits after the code
+            const uint32_t t = (uint32_t)((br.buf << len) >> 32);
+            int v = (int)((t >> 1) >> (31 - size));
+            v += (~((int)t >> 31)) & (1 - (1 << size));  // first bit 0 -> negative; size 0 -> 0
+            const int kk = k + adv - 1;  // zig-zag index the value goes to
+            bool store = size != 0;
+            if (isdc) {
+                // decoder.zig:1366-1376
+                const int comp = (int)(bi.z & 0xff);
+                int dc = comp == 0 ? dc0 : comp == 1 ? dc1 : comp == 2 ? dc2 : dc3;
+                dc += v;
+                if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
+                v = dc;
+                store = true;
+                if ((dc < -32768 || dc > 32767) && !err) err = ZPX_E_COEF_RANGE;
+                k = 1;
+                if (eob_run > 0) {  // decoder.zig:1379-1380 (End-Of-Band run)
+                    eob_run--;
+                    k = 64;
+                }
+            } else {
+                if (kk > 63) {  // decoder.zig:1393-1395: run past the block end, the value bits stay unread
+                    tot = len;
+                    store = false;
+                }
+                k += adv;
+            }
+            if ((e >> 31) && !isdc) {
+                // (r, 0) with 0 < r < 15: eob_run = (1 << r | next r bits) - 1; r is not in the entry,
+                // recover it from the symbol table
+                const ZpxHuffDev* __restrict__ tab = reinterpret_cast<const ZpxHuffDev*>(ftab);
+                const uint32_t s16 = __ldg(&tab->lut[hi >> (32 - ZPX_LUT_BITS)]);
+                uint32_t sym = s16 >> 8;
+                if ((s16 & 0xff) == 0) {
+                    const uint32_t v16 = hi >> 16;
+                    for (int l = ZPX_LUT_BITS + 1; l <= 16; l++)
+                        if (v16 < tab->limit[l]) { sym = tab->vals[(tab->valoff[l] + (int)(v16 >> (16 - l))) & 0xff]; break; }
+                }
+                const int r = (int)(sym >> 4);
+                eob_run = (1u << r) | (uint32_t)((br.buf << len) >> (64 - r));
+                eob_run = (eob_run - 1) & 0xffffu;
+                tot = len + r;
+            }
+            br.buf <<= tot;
+            br.cnt -= tot;
+            if (store) {
+                const uint32_t nat = lds_u8(su + kk);
+                sts_u16(sb + (nat >> 3) * (NT * 16) + (nat & 7) * 2, v);
+            }
             if (err) {
                 // a symbol that needed bits past the limit is the reference's MissingFF00 / UnexpectedEof,
                 // whatever the garbage decoded to
-                if (br.overrun()) err = err_eof;
+                if (br.overrun()) err = (iv.flags & 1) ? ZPX_E_UnexpectedEof : ZPX_E_MissingFF00;
                 report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + (iv.n_blocks - left), err);
                 left = 0;
-            } else if (done) {
+            } else if (k > 63) {
                 if (br.overrun()) {
-                    report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + (iv.n_blocks - left), err_eof);
+                    report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + (iv.n_blocks - left),
+                           (iv.flags & 1) ? ZPX_E_UnexpectedEof : ZPX_E_MissingFF00);
                     left = 0;
                 } else {
-                    // ---- hand the block to HBM ----
-                    const int comp = (int)(bi.z & 0xff);
-                    int bx, by;
-                    if (interleaved) {
-                        bx = (int)(bi.w & 0xff) * (int)mx + (int)((bi.z >> 8) & 0xff);
-                        by = (int)((bi.w >> 8) & 0xff) * (int)my + (int)((bi.z >> 16) & 0xff);
-                    } else {
-                        bx = (int)bxn;
-                        by = (int)byn;
-                    }
+                    // ---- hand the block to HBM: slot s of the 128-byte line holds row s ^ key ----
+                    uint32_t bx;
                     uint64_t blk;
-                    if (planar) blk = im->comp_base[comp] + (uint64_t)by * im->comp_bw[comp] + bx;
-                    else blk = im->coef_base + (uint64_t)mcu * im->bpm + (bi.z >> 24);
-                    lb.flush(P.coef + blk * 8, bx & 7);
+                    if (interleaved) {
+                        bx = (bi.w & 0xff) * mx + ((bi.z >> 8) & 0xff);
+                        if (planar) {
+                            const int comp = (int)(bi.z & 0xff);
+                            const uint32_t by = ((bi.w >> 8) & 0xff) * my + ((bi.z >> 16) & 0xff);
+                            blk = im->comp_base[comp] + (uint64_t)by * im->comp_bw[comp] + bx;
+                        } else {
+                            blk = coef_base + (uint64_t)mcu * bpm + (bi.z >> 24);
+                        }
+                    } else {
+                        bx = bxn;
+                        const int comp = (int)(bi.z & 0xff);
+                        blk = im->comp_base[comp] + (uint64_t)byn * im->comp_bw[comp] + bx;
+                    }
+                    uint4* __restrict__ dst = P.coef + blk * 8;
+                    const uint32_t key = bx & 7;
+#pragma unroll
+                    for (uint32_t slot = 0; slot < 8; slot++) {
+                        const uint32_t a = sb + (slot ^ key) * (NT * 16);
+                        dst[slot] = lds_v4(a);
+                        sts_zero16(a);
+                    }
                     // ---- next block ----
                     left--;
                     k = 0;
@@ -123,8 +325,8 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
                             if (++mx == mxx) { mx = 0; my++; }
                         }
                         bi = bpack[c];
-                        tdc = &P.huff[bi.x];
-                        tac = &P.huff[bi.y];
+                        fdc = P.huff[bi.x].fast;
+                        fac = P.huff[bi.y].fast;
                     } else if (++bxn == cw) {
                         bxn = 0;
                         byn++;

@@ -451,6 +451,7 @@ static void derive(ZpxParsed* o) {
         return;
     }
     if (o->ncomp < 3) return;
+    if (o->h[1] <= 0 || o->v[1] <= 0 || o->h[0] <= 0 || o->v[0] <= 0) return;  // SOF rejected half way
     int hr = o->h[0] / o->h[1], vr = o->v[0] / o->v[1];
     switch (hr << 4 | vr) {
         case 0x11: o->ratio = ZPX_RATIO_444; break;
@@ -508,7 +509,24 @@ void zpx_parse_jpeg(const uint8_t* data, size_t len, bool config_only, ZpxParsed
 }
 
 // decoder.zig:1070-1109 restated for a ZPX_LUT_BITS-bit first level
-void zpx_build_huff_dev(const ZpxHuffHost& h, ZpxHuffDev* o, int* malformed) {
+// fields of ZpxHuffDev::fast for a code of length len that decodes to sym
+uint32_t zpx_fast_entry(bool is_ac, int len, int sym) {
+    uint32_t size, adv, special = 0;
+    if (!is_ac) {
+        size = (uint32_t)sym;
+        adv = 1;
+        if (sym > 16) { special = 1; size = 0; }
+    } else {
+        const int r = sym >> 4, s2 = sym & 15;
+        if (s2 != 0) { size = (uint32_t)s2; adv = (uint32_t)r + 1; }
+        else if (r == 15) { size = 0; adv = 16; }
+        else if (r == 0) { size = 0; adv = 64; }
+        else { size = 0; adv = 64; special = 1; }
+    }
+    return ((uint32_t)len + size) | (uint32_t)len << 8 | size << 13 | adv << 18 | special << 31;
+}
+
+void zpx_build_huff_dev(const ZpxHuffHost& h, bool is_ac, ZpxHuffDev* o, int* malformed) {
     memset(o, 0, sizeof(*o));
     *malformed = 0;
     if (!h.defined) return;
@@ -532,8 +550,12 @@ void zpx_build_huff_dev(const ZpxHuffHost& h, ZpxHuffDev* o, int* malformed) {
                     uint32_t c = code + (uint32_t)j;
                     uint32_t base = c << (ZPX_LUT_BITS - l);
                     uint16_t v = (uint16_t)((uint16_t)h.vals[index + j] << 8 | (uint16_t)l);
+                    const uint32_t f = zpx_fast_entry(is_ac, l, h.vals[index + j]);
                     for (uint32_t k = 0; k < (1u << (ZPX_LUT_BITS - l)); k++)
-                        if ((base | k) < ZPX_LUT_SIZE) o->lut[base | k] = v;
+                        if ((base | k) < ZPX_LUT_SIZE) {
+                            o->lut[base | k] = v;
+                            o->fast[base | k] = f;
+                        }
                 }
             }
             code += (uint32_t)cnt;
