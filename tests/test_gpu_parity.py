@@ -198,6 +198,55 @@ def test_cfg4_sample(jpeg, ctx):
     _assert_same(jpeg, ctx, datas)
 
 
+PROGRESSIVE_FIXTURES = [
+    "video-001.progressive.jpeg", "video-001.q50.410.progressive.jpeg", "video-001.q50.411.progressive.jpeg",
+    "video-001.q50.420.progressive.jpeg", "video-001.q50.422.progressive.jpeg", "video-001.q50.440.progressive.jpeg",
+    "video-001.q50.444.progressive.jpeg", "video-005.gray.q50.progressive.jpeg", "video-005.gray.q50.2x2.progressive.jpeg",
+    "video-001.separate.dc.progression.jpeg", "video-001.separate.dc.progression.progressive.jpeg",
+]
+
+
+def test_progressive_fixtures(jpeg, ctx, fixtures_dir, golden_dir):
+    """SOF2 frames (spectral selection + successive approximation, 6-14 scans) on the GPU: RGBA == oracle
+    == committed sha256, and == the baseline twin (the reference's own `decode + progressive` test)."""
+    datas = [_read(fixtures_dir, n) for n in PROGRESSIVE_FIXTURES]
+    _assert_same(jpeg, ctx, datas, PROGRESSIVE_FIXTURES)
+    outs, st, _ = _gpu_batch(jpeg, ctx, datas)
+    gold = json.load(open(os.path.join(golden_dir, "rgba_sha256.json")))
+    for n, o in zip(PROGRESSIVE_FIXTURES, outs):
+        assert hashlib.sha256(o.tobytes()).hexdigest() == gold[n], n
+    pairs = [n for n in PROGRESSIVE_FIXTURES if n.endswith(".progressive.jpeg")]
+    base, _, _ = _gpu_batch(jpeg, ctx, [_read(fixtures_dir, n.replace(".progressive", "")) for n in pairs])
+    for n, b in zip(pairs, base):
+        assert np.array_equal(b, outs[PROGRESSIVE_FIXTURES.index(n)]), n
+
+
+def test_progressive_coefficients_match_oracle(jpeg, ctx, fixtures_dir):
+    for name in ["video-001.q50.420.progressive.jpeg", "video-005.gray.q50.progressive.jpeg", "video-001.progressive.jpeg"]:
+        data = _read(fixtures_dir, name)
+        _, recs = O.decode(data, tap=True)
+        with jpeg.Batch(ctx, [data]) as b:
+            b.upload()
+            b.decode()
+            co = b.coefficients(0)
+        assert co.shape[0] == recs.shape[0], name
+        assert np.array_equal(co.astype(np.int32), recs[:, 3:]), name
+
+
+def test_cfg5_sample(jpeg, ctx):
+    """BASELINE.json configs[4] at reduced count: mixed batch of Adobe CMYK, YCbCrK (intent) and
+    progressive 4:2:0 at 1920x1080, plus progressive gray / 4:4:4 / DRI variants at small sizes."""
+    datas = S.make_batch(5, 2, 1920, 1080, mode="CMYK")
+    datas += S.make_batch(5, 1, 1920, 1080, first=2, mode="CMYK", ycck=True)
+    datas += S.make_batch(5, 3, 1920, 1080, first=3, subsampling="4:2:0", progressive=True)
+    datas += [S.encode(50010, 333, 211, subsampling="4:4:4", progressive=True),
+              S.encode(50011, 333, 211, mode="L", progressive=True),
+              S.encode(50012, 333, 211, subsampling="4:2:2", progressive=True, restart_rows=1),
+              S.encode(50013, 97, 64, subsampling="4:2:0", progressive=True, restart_blocks=3),
+              S.encode(50014, 300, 200, mode="CMYK", progressive=True)]
+    _assert_same(jpeg, ctx, datas)
+
+
 def test_fused_equals_generic(jpeg, fixtures_dir):
     """The fused kernel and the unfused IDCT->planes->colour path give identical bytes."""
     datas = [_read(fixtures_dir, n) for n in BASELINE_FIXTURES] + S.make_batch(2, 2, 1920, 1080, subsampling="4:2:0", restart_rows=1)

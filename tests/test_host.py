@@ -84,7 +84,6 @@ def test_parser_matches_oracle_on_fixtures(zlib, fixtures_dir):
         img = O.decode(data)
         inf, rep = _report(zlib, data)
         prog = "progressive" in name or "separate.dc" in name
-        # progressive frames parse fine but are not decoded on the GPU by this build
         assert rep.status == 0, name
         assert (inf.width, inf.height) == (img.width, img.height)
         assert inf.variant == img.variant, name

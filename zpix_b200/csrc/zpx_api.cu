@@ -115,6 +115,11 @@ struct DevicePlan {
     std::vector<ZpxHuffDev> huff;
     std::vector<ZpxQuantDev> quant;
     std::vector<FusedGroup> groups;
+    std::vector<ZpxIntervalDev> ivs_prog;            // intervals of progressive scans (appended after the sequential ones)
+    std::vector<std::vector<uint32_t>> prog_lists;   // per scan ordinal: indices (into the final interval array)
+    std::vector<size_t> prog_off;                    // byte offsets of those lists in the descriptor buffer
+    std::vector<std::pair<uint64_t, uint64_t>> prog_zero;  // (first block, blocks) of progressive images: zeroed before the scans
+    size_t n_seq = 0;                                // sequential intervals = ivs[0, n_seq)
     std::vector<ZpxWarpDev> warps;  // self-synchronising mode: one entry per warp
     size_t n_subs = 0;
     bool sub_mode = false;
@@ -184,7 +189,7 @@ const char* const kErrNames[] = {
 
 // can this image be decoded on the GPU by this build?
 int unsupported_reason(const ZpxParsed& p) {
-    if (p.progressive) return ZPX_E_UNSUPPORTED_STREAM;
+    (void)p;
     return 0;
 }
 
@@ -287,6 +292,9 @@ void build_plan(zpx_batch* b, int di) {
                     for (int i = 0; i < s.ncomp; i++)
                         if (s.comp[i] == c) zz = s.quant[i];
             im.qidx[c] = dd.add_quant(zz, pl.quant);
+            // the fused kernel multiplies with 8-bit quantisers (dp2a); 16-bit tables take the unfused path
+            for (int z = 0; z < 64; z++)
+                if (zz[z] > 255 || zz[z] < 0) im.fused = 0;
         }
         // output
         im.out_off = pl.out_bytes;
@@ -432,18 +440,30 @@ void build_plan(zpx_batch* b, int di) {
                     d.n_blocks = (uint32_t)(coded_before(x1) - coded_before(x0));
                 }
                 d.sub_first = d.nsub = d.sub_bytes = d.pad0 = 0;
-                pl.ivs.push_back(d);
+                if (p.progressive) {
+                    if (pl.prog_lists.size() <= (size_t)sd.scan_index) pl.prog_lists.resize(sd.scan_index + 1);
+                    pl.prog_lists[sd.scan_index].push_back((uint32_t)pl.ivs_prog.size());  // fixed up below
+                    pl.ivs_prog.push_back(d);
+                } else {
+                    pl.ivs.push_back(d);
+                }
             }
         }
+        if (p.progressive) pl.prog_zero.push_back({im.coef_base, nblocks});
         pl.imgs.push_back(im);
     }
+    // progressive intervals go after the sequential ones
+    pl.n_seq = pl.ivs.size();
+    for (auto& l : pl.prog_lists)
+        for (uint32_t& ix : l) ix += (uint32_t)pl.n_seq;
+    pl.ivs.insert(pl.ivs.end(), pl.ivs_prog.begin(), pl.ivs_prog.end());
     // entropy mode: with enough restart intervals to fill the GPU, one lane per interval decodes each
     // once, serially; otherwise the self-synchronising decoder parallelises inside the intervals
     const int64_t mode = b->ctx->opt_entropy_mode;
-    pl.sub_mode = mode == 2 || (mode == 0 && pl.ivs.size() < 16384);
+    pl.sub_mode = mode == 2 || (mode == 0 && pl.n_seq < 16384);
     if (pl.sub_mode) {
         const uint32_t submax = b->ctx->opt_subseq > 0 ? (uint32_t)align_up((size_t)b->ctx->opt_subseq, 4) : 256u;
-        for (size_t k = 0; k < pl.ivs.size(); k++) {
+        for (size_t k = 0; k < pl.n_seq; k++) {
             ZpxIntervalDev& d = pl.ivs[k];
             const uint32_t span = (uint32_t)(d.start & 3) + d.len;
             uint32_t sub = (uint32_t)align_up((span + 31) / 32, 4);
@@ -469,6 +489,8 @@ void build_plan(zpx_batch* b, int di) {
     pl.off_quant = place(pl.quant.size() * sizeof(ZpxQuantDev));
     pl.off_generic = place(pl.generic.size() * sizeof(uint32_t));
     pl.off_warps = place(pl.warps.size() * sizeof(ZpxWarpDev));
+    pl.prog_off.clear();
+    for (auto& l : pl.prog_lists) pl.prog_off.push_back(place(l.size() * sizeof(uint32_t)));
     for (FusedGroup& g : pl.groups) g.tiles_off = place(g.tiles.size() * sizeof(ZpxTileDev));
     pl.desc_bytes = off;
     memset(&pl.timing, 0, sizeof(pl.timing));
@@ -500,7 +522,7 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
     K1Params k1;
     k1.blob = (const uint8_t*)dc.blob.p;
     k1.ivs = (const ZpxIntervalDev*)(desc + pl.off_ivs);
-    k1.n_iv = (int)pl.ivs.size();
+    k1.n_iv = (int)pl.n_seq;
     k1.scans = (const ZpxScanDev*)(desc + pl.off_scans);
     k1.imgs = (const ZpxImageDev*)(desc + pl.off_imgs);
     k1.huff = (const ZpxHuffDev*)(desc + pl.off_huff);
@@ -528,7 +550,7 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         CU(ctx, k1s_launch_sync(ks, 0, st));
         k1_launches++;
         bool multi = false;
-        for (const ZpxIntervalDev& d : pl.ivs) multi = multi || d.nsub > 32;
+        for (size_t k = 0; k < pl.n_seq; k++) multi = multi || pl.ivs[k].nsub > 32;
         for (int sweep = 1; multi; sweep++) {
             CU(ctx, cudaMemsetAsync(ks.changed, 0, sizeof(int), st));
             CU(ctx, k1s_launch_sync(ks, sweep, st));
@@ -540,6 +562,14 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         CU(ctx, k1s_launch_scan(ks, st));
         CU(ctx, k1s_launch_write(ks, st));
         k1_launches += 2;
+    }
+    // ---- K3: progressive frames, one launch per scan ordinal over zeroed coefficient grids ----
+    for (const auto& z : pl.prog_zero)
+        CU(ctx, cudaMemsetAsync((uint8_t*)dc.coef.p + z.first * 128, 0, z.second * 128, st));
+    for (size_t k = 0; k < pl.prog_lists.size(); k++) {
+        if (pl.prog_lists[k].empty()) continue;
+        CU(ctx, k3_launch_progressive(k1, (const uint32_t*)(desc + pl.prog_off[k]), (int)pl.prog_lists[k].size(), st));
+        k1_launches++;
     }
     CU(ctx, cudaEventRecord(dc.ev[1], st));
 
@@ -872,6 +902,8 @@ int32_t zpx_batch_upload(zpx_batch* b) {
         memcpy(hd + pl.off_quant, pl.quant.data(), pl.quant.size() * sizeof(ZpxQuantDev));
         memcpy(hd + pl.off_generic, pl.generic.data(), pl.generic.size() * sizeof(uint32_t));
         memcpy(hd + pl.off_warps, pl.warps.data(), pl.warps.size() * sizeof(ZpxWarpDev));
+        for (size_t k = 0; k < pl.prog_lists.size(); k++)
+            memcpy(hd + pl.prog_off[k], pl.prog_lists[k].data(), pl.prog_lists[k].size() * sizeof(uint32_t));
         if (pl.sub_mode) {
             CU(ctx, dc.subs.ensure(align_up(pl.n_subs, 64) * 36 + 256));
             CU(ctx, dc.hflag.ensure(64));

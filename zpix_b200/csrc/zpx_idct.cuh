@@ -116,6 +116,45 @@ __device__ __forceinline__ uint32_t pack4_sat_u8(int v0, int v1, int v2, int v3)
     return d;
 }
 
+// signed 16-bit x unsigned 8-bit two-way dot product (SASS IDP.2A.LO/HI.S16.U8): with b = q_even |
+// q_odd << 24, lo gives a.lo16 * q_even and hi gives a.hi16 * q_odd -- unpack + dequantise of a
+// coefficient in one instruction (8-bit quantiser tables, decoder.zig:645-647).
+__device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(0));
+    return d;
+}
+
+// Same as dequant_idct_block below for quantisers that fit 8 bits: `qp` holds, per row, four words
+// q[2j] | q[2j+1] << 24.  The <<11 prescale of columns 0 and 4 (idct.zig:100-101) is applied after
+// the product ((c*q)<<11, wrapping).
+template <typename LoadRow>
+__device__ __forceinline__ void dequant_idct_block_q8(LoadRow ld, const uint32_t* __restrict__ qp, uint32_t (&px)[16]) {
+    int b[64];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint4 c = ld(r);
+        const uint4 q = *reinterpret_cast<const uint4*>(qp + r * 4);
+        const int s0 = dp2a_lo_su(c.x, q.x) << 11, s1 = dp2a_hi_su(c.x, q.x);
+        const int s2 = dp2a_lo_su(c.y, q.y), s3 = dp2a_hi_su(c.y, q.y);
+        const int s4 = dp2a_lo_su(c.z, q.z) << 11, s5 = dp2a_hi_su(c.z, q.z);
+        const int s6 = dp2a_lo_su(c.w, q.w), s7 = dp2a_hi_su(c.w, q.w);
+        idct_row(s0, s1, s2, s3, s4, s5, s6, s7, &b[r * 8]);
+    }
+#pragma unroll
+    for (int x = 0; x < 8; x++) idct_col(&b[x]);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        px[2 * r + 0] = pack4_level_shift(b[r * 8 + 0], b[r * 8 + 1], b[r * 8 + 2], b[r * 8 + 3]);
+        px[2 * r + 1] = pack4_level_shift(b[r * 8 + 4], b[r * 8 + 5], b[r * 8 + 6], b[r * 8 + 7]);
+    }
+}
+
 // Dequantise + IDCT one block.  `ld(r)` returns row r of the block as a uint4 of 8 int16 (natural
 // order); `q` points at the block's quantiser in natural order with columns 0 and 4 pre-multiplied
 // by 2048 (int32[64], warp-uniform address).  Result: 8 rows x 2 words of level-shifted pixels.

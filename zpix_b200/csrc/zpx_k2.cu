@@ -63,9 +63,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Shared memory (dynamic):
 //   [0,16)     two mbarriers
 //   [16,32)    reserved
-//   QS         3 x 64 int32 quantisers (columns 0/4 prescaled by 2048)
+//   QS         3 x 32 words: 8-bit quantisers packed q[2j] | q[2j+1] << 24 (dp2a operands)
 //   PL         Y plane 8V rows x PY bytes, then Cb, Cr: 8 rows x PC bytes each
-//   ST0, ST1   coefficient stages, tmax * BPM * 128 bytes each
+//   ST0..      NS coefficient stages, tmax * BPM * 128 bytes each (ring fed by bulk copies)
 template <int H, int V, int NC>
 struct K2Cfg {
     static constexpr int BPM = NC == 1 ? 1 : H * V + 2;
@@ -73,23 +73,23 @@ struct K2Cfg {
     static constexpr int MCU_W = 8 * H;
     __host__ __device__ static int pitch_y(int tmax) { return tmax * MCU_W + 16; }
     __host__ __device__ static int pitch_c(int tmax) { return tmax * 8 + 16; }
-    __host__ __device__ static size_t smem_bytes(int tmax) {
+    __host__ __device__ static size_t smem_bytes(int tmax, int ns) {
         size_t s = 32 + 3 * 64 * 4;
         s += (size_t)YROWS * pitch_y(tmax);
         if (NC == 3) s += (size_t)2 * 8 * pitch_c(tmax);
         s = (s + 127) & ~(size_t)127;
-        s += (size_t)2 * tmax * BPM * 128;
+        s += (size_t)ns * tmax * BPM * 128;
         return s;
     }
 };
 
-template <int H, int V, int NC>
+template <int H, int V, int NC, int NS>
 __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
     using Cfg = K2Cfg<H, V, NC>;
     constexpr int BPM = Cfg::BPM;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-    int* qs = reinterpret_cast<int*>(smem + 32);
+    uint32_t* qs = reinterpret_cast<uint32_t*>(smem + 32);
     const int PY = Cfg::pitch_y(P.tmax), PC = Cfg::pitch_c(P.tmax);
     uint8_t* planeY = smem + 32 + 3 * 64 * 4;
     uint8_t* planeCb = planeY + Cfg::YROWS * PY;
@@ -101,8 +101,7 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
 
     const int tid = threadIdx.x;
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int i = 0; i < NS; i++) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -111,49 +110,75 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
     int tile = blockIdx.x;
     if (tile >= P.ntiles) return;
 
-    // prologue: fetch the first tile
-    if (tid == 0) {
-        const ZpxTileDev t = P.tiles[tile];
-        const ZpxImageDev* im = &P.imgs[t.img];
-        const uint64_t blk0 = im->coef_base + ((uint64_t)t.my * im->mxx + t.mx0) * BPM;
-        const uint32_t bytes = (uint32_t)t.n * BPM * 128;
-        mbar_arrive_expect_tx(&bars[0], bytes);
-        bulk_g2s(stage0, coef + blk0 * 8, bytes, &bars[0]);
-    }
+    // Per-stage tile context and quantisers live in shared memory: written when the tile's bulk copy
+    // is issued (NS-1 iterations ahead), read after the mbarrier wait -- no global-load latency and no
+    // extra barrier on the per-tile critical path.
+    struct TileCtx {
+        uint32_t n, mx0, my, img;
+        int32_t width, height;
+        uint64_t out_off;
+    };
+    __shared__ TileCtx ctx[NS];
+    __shared__ __align__(16) uint32_t qsm[NS][3 * 32];  // per row four words q[2j] | q[2j+1] << 24 (dp2a operands)
+    (void)qs;
 
-    uint32_t phase0 = 0, phase1 = 0;
-    int stage = 0;
-    int cur_img = -1;
-    for (; tile < P.ntiles; tile += gridDim.x) {
-        const ZpxTileDev t = P.tiles[tile];
-        const ZpxImageDev* __restrict__ im = &P.imgs[t.img];
-        const int n = t.n;
-
-        // prefetch the next tile into the other stage (free since the barrier after last phase 1)
-        const int next = tile + gridDim.x;
-        if (tid == 0 && next < P.ntiles) {
-            const ZpxTileDev tn = P.tiles[next];
-            const ZpxImageDev* imn = &P.imgs[tn.img];
+    // issue the bulk copy of one tile into a stage and publish its context (thread 0);
+    // threads < 32*NC stage the image's quantisers when the image changes
+    int pf_img = -1;  // image whose quantisers were staged last (uniform)
+    auto fetch = [&](const ZpxTileDev tn, int stg) {
+        const ZpxImageDev* __restrict__ imn = &P.imgs[tn.img];
+        if (tid == 0) {
             const uint64_t blk0 = imn->coef_base + ((uint64_t)tn.my * imn->mxx + tn.mx0) * BPM;
             const uint32_t bytes = (uint32_t)tn.n * BPM * 128;
-            mbar_arrive_expect_tx(&bars[stage ^ 1], bytes);
-            bulk_g2s(stage0 + (size_t)(stage ^ 1) * stage_bytes, coef + blk0 * 8, bytes, &bars[stage ^ 1]);
+            mbar_arrive_expect_tx(&bars[stg], bytes);
+            bulk_g2s(stage0 + (size_t)stg * stage_bytes, coef + blk0 * 8, bytes, &bars[stg]);
+            TileCtx c;
+            c.n = tn.n;
+            c.mx0 = tn.mx0;
+            c.my = tn.my;
+            c.img = tn.img;
+            c.width = imn->width;
+            c.height = imn->height;
+            c.out_off = imn->out_off;
+            ctx[stg] = c;
         }
-
-        // quantisers of this image (uniform branch)
-        if ((int)t.img != cur_img) {
-            cur_img = (int)t.img;
-            if (tid < 64 * NC) {
-                const int c = tid >> 6, k = tid & 63;
-                int q = P.quant[im->qidx[c]].q[k];
-                if ((k & 7) == 0 || (k & 7) == 4) q <<= 11;  // prescale of idct.zig:100-101 folded in
-                qs[tid] = q;
+        if (tid < 32 * NC) {
+            // (every stage keeps its own copy: a later tile of another image must not disturb it)
+            const int c = tid >> 5, k = tid & 31;
+            if ((int)tn.img != pf_img) {
+                const int* q = P.quant[imn->qidx[c]].q;
+                qsm[stg][c * 32 + k] = (uint32_t)q[2 * k] | (uint32_t)q[2 * k + 1] << 24;
+            } else {
+                const int prev = stg == 0 ? NS - 1 : stg - 1;
+                qsm[stg][c * 32 + k] = qsm[prev][c * 32 + k];
             }
-            __syncthreads();
+        }
+        pf_img = (int)tn.img;
+    };
+    // prologue: the first NS-1 tiles of this CTA
+    for (int i = 0; i < NS - 1; i++) {
+        if (tile + i * (int)gridDim.x < P.ntiles) fetch(P.tiles[tile + i * (int)gridDim.x], i);
+        __syncthreads();  // the copy of qsm[prev] above must see the previous stage's values
+    }
+    // descriptor of the tile to prefetch next, loaded one iteration early (its latency is hidden)
+    ZpxTileDev tn_pf = P.tiles[min(tile + (NS - 1) * (int)gridDim.x, P.ntiles - 1)];
+
+    uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+    int stage = 0;
+    for (; tile < P.ntiles; tile += gridDim.x) {
+        // prefetch NS-1 tiles ahead; that stage was consumed one iteration ago (barrier after phase 1)
+        {
+            const int ahead = tile + (NS - 1) * (int)gridDim.x;
+            const int stg = stage == 0 ? NS - 1 : stage - 1;
+            if (ahead < P.ntiles) fetch(tn_pf, stg);
+            tn_pf = P.tiles[min(ahead + (int)gridDim.x, P.ntiles - 1)];
         }
 
-        mbar_wait(&bars[stage], stage ? phase1 : phase0);
-        if (stage) phase1 ^= 1; else phase0 ^= 1;
+        mbar_wait(&bars[stage], (phase_bits >> stage) & 1u);
+        phase_bits ^= 1u << stage;
+        const TileCtx t = ctx[stage];
+        const int n = (int)t.n;
+        const uint32_t* __restrict__ qs_t = qsm[stage];
 
         // ---------------- phase 1: one thread per 8x8 block ----------------
         const uint4* st = reinterpret_cast<const uint4*>(stage0 + (size_t)stage * stage_bytes);
@@ -163,7 +188,7 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
             int slot, bxa;        // block index inside the stage; absolute component-x of the block
             uint8_t* dst;
             int pitch;
-            const int* q;
+            const uint32_t* q;
             if (i < nY) {
                 const int nH = n * H;
                 const int vy = (V == 2 && i >= nH) ? 1 : 0;
@@ -173,7 +198,7 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
                 bxa = (int)t.mx0 * H + bx;
                 dst = planeY + (vy * 8) * PY + bx * 8;
                 pitch = PY;
-                q = qs;
+                q = qs_t;
             } else {
                 const int j = i - nY;
                 const int c = j >= n ? 1 : 0;
@@ -182,12 +207,12 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
                 bxa = (int)t.mx0 + m;
                 dst = (c ? planeCr : planeCb) + m * 8;
                 pitch = PC;
-                q = qs + 64 * (1 + c);
+                q = qs_t + 32 * (1 + c);
             }
             const uint4* blk = st + slot * 8;
             const int key = bxa & 7;
             uint32_t px[16];
-            dequant_idct_block([&](int r) { return blk[r ^ key]; }, q, px);
+            dequant_idct_block_q8([&](int r) { return blk[r ^ key]; }, q, px);
 #pragma unroll
             for (int r = 0; r < 8; r++)
                 *reinterpret_cast<uint2*>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
@@ -201,12 +226,12 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
             constexpr int RP = V;                    // luma rows per item
             constexpr int PXW = (V == 2) ? 4 : 8;    // pixels per item row
             constexpr int NCS = (PXW / H) > 0 ? (PXW / H) : 1;  // chroma samples per item row
-            const int W = im->width, Hh = im->height;
+            const int W = t.width, Hh = t.height;
             const int x0 = (int)t.mx0 * Cfg::MCU_W, y0 = (int)t.my * Cfg::YROWS;
             const int ipr = n * (Cfg::MCU_W / PXW);  // items per row(-pair)
             const int items = ipr * (Cfg::YROWS / RP);
             const uint32_t magic = ipr > 1 ? 0xffffffffu / (uint32_t)ipr + 1u : 0u;  // exact it/ipr for it, ipr < 2^16
-            uint8_t* __restrict__ outp = P.out + im->out_off;
+            uint8_t* __restrict__ outp = P.out + t.out_off;
             const bool vec_ok = (W & 3) == 0;
             for (int it = tid; it < items; it += 256) {
                 const int rp = ipr > 1 ? (int)__umulhi((uint32_t)it, magic) : it;
@@ -271,30 +296,29 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
             }
         }
         __syncthreads();
-        stage ^= 1;
+        stage = stage + 1 == NS ? 0 : stage + 1;
     }
 }
 
-template <int H, int V, int NC>
-static cudaError_t launch_fused_t(const K2Params& P, int grid, cudaStream_t s) {
+template <int H, int V, int NC, int NS>
+static cudaError_t launch_fused_ns(const K2Params& P, int grid, cudaStream_t s) {
     using Cfg = K2Cfg<H, V, NC>;
-    const size_t smem = Cfg::smem_bytes(P.tmax);
-    cudaError_t e = cudaFuncSetAttribute(k2_fused<H, V, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = Cfg::smem_bytes(P.tmax, NS);
+    cudaError_t e = cudaFuncSetAttribute(k2_fused<H, V, NC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k2_fused<H, V, NC><<<grid, 256, smem, s>>>(P);
+    k2_fused<H, V, NC, NS><<<grid, 256, smem, s>>>(P);
     return cudaGetLastError();
 }
 
-int k2_fused_bpm(int h, int v, int nc) { return nc == 1 ? 1 : h * v + 2; }
-
-size_t k2_fused_smem(int h, int v, int nc, int tmax) {
-    size_t s = 32 + 3 * 64 * 4;
-    s += (size_t)(8 * v) * (tmax * 8 * h + 16);
-    if (nc == 3) s += (size_t)2 * 8 * (tmax * 8 + 16);
-    s = (s + 127) & ~(size_t)127;
-    s += (size_t)2 * tmax * k2_fused_bpm(h, v, nc) * 128;
-    return s;
+// three stages when two CTAs of that size still fit one SM (227 KB), else two
+template <int H, int V, int NC>
+static cudaError_t launch_fused_t(const K2Params& P, int grid, cudaStream_t s) {
+    using Cfg = K2Cfg<H, V, NC>;
+    if (2 * (Cfg::smem_bytes(P.tmax, 3) + 1024) <= 227 * 1024) return launch_fused_ns<H, V, NC, 3>(P, grid, s);
+    return launch_fused_ns<H, V, NC, 2>(P, grid, s);
 }
+
+int k2_fused_bpm(int h, int v, int nc) { return nc == 1 ? 1 : h * v + 2; }
 
 cudaError_t k2_launch_fused(int h, int v, int nc, const K2Params& P, int grid, cudaStream_t s) {
     if (nc == 1) return launch_fused_t<1, 1, 1>(P, grid, s);

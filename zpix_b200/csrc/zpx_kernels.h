@@ -36,6 +36,9 @@ cudaError_t k1s_launch_sync(const K1SParams& P, int sweep, cudaStream_t s);
 cudaError_t k1s_launch_scan(const K1SParams& P, cudaStream_t s);
 cudaError_t k1s_launch_write(const K1SParams& P, cudaStream_t s);
 
+// progressive scans (zpx_k3.cu): one lane per listed interval, read-modify-write of the coefficient grids
+cudaError_t k3_launch_progressive(const K1Params& P, const uint32_t* list, int n_list, cudaStream_t s);
+
 // ---- K2: fused dequant + IDCT + upsample + colour ------------------------------
 struct K2Params {
     const int16_t* coef;
@@ -47,7 +50,6 @@ struct K2Params {
     int tmax;  // largest tile (MCUs): fixes the shared-memory layout
 };
 int k2_fused_bpm(int h, int v, int nc);
-size_t k2_fused_smem(int h, int v, int nc, int tmax);
 cudaError_t k2_launch_fused(int h, int v, int nc, const K2Params& P, int grid, cudaStream_t s);
 
 // ---- generic unfused path -------------------------------------------------------
