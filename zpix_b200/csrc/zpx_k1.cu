@@ -127,58 +127,77 @@ struct FastReader {
 };
 
 // rare path of the symbol step: code longer than the first-level table, or a special entry.
-// Returns the fast-entry fields for the symbol, or 0 with err set.
-__device__ __noinline__ uint32_t k1_slow_symbol(const ZpxHuffDev* __restrict__ tab, uint32_t hi, bool isdc, uint32_t e,
-                                                int* err) {
+// Returns the fast-entry fields for the symbol in the low word (bit 31 kept for an AC End-Of-Band
+// run, with its r in bits 25-28) and an error code in the high word.
+__device__ __noinline__ unsigned long long k1_slow_symbol(const ZpxHuffDev* __restrict__ tab, uint32_t hi, bool isdc,
+                                                          uint32_t e) {
+    int err = 0;
+    uint32_t sym = 0;
+    int len = (int)((e >> 8) & 31u);
     if (e == 0) {
         const uint32_t v16 = hi >> 16;
-        int len = 0;
-        uint32_t sym = 0;
+        len = 0;
         for (int l = ZPX_LUT_BITS + 1; l <= 16 && len == 0; l++) {
             if (v16 < tab->limit[l]) {
                 sym = tab->vals[(tab->valoff[l] + (int)(v16 >> (16 - l))) & 0xff];
                 len = l;
             }
         }
-        if (len == 0) {  // the reference reads 16 bits, then BadHuffmanCode (decoder.zig:947-969)
-            *err = ZPX_E_BadHuffmanCode;
-            return 16u | 16u << 8 | 64u << 18;
-        }
-        // same field packing as zpx_fast_entry (zpx_parse.cpp)
-        uint32_t size, adv, special = 0;
-        if (isdc) {
-            size = sym;
-            adv = 1;
-            if (sym > 16) { special = 1; size = 0; }
-        } else {
-            const uint32_t r = sym >> 4, s2 = sym & 15;
-            if (s2 != 0) { size = s2; adv = r + 1; }
-            else if (r == 15) { size = 0; adv = 16; }
-            else if (r == 0) { size = 0; adv = 64; }
-            else { size = 0; adv = 64; special = 1; }
-        }
-        e = ((uint32_t)len + size) | (uint32_t)len << 8 | size << 13 | adv << 18 | special << 31;
+        if (len == 0)  // the reference reads 16 bits, then BadHuffmanCode (decoder.zig:947-969)
+            return (unsigned long long)(16u | 16u << 8 | 64u << 18) | ((unsigned long long)ZPX_E_BadHuffmanCode << 32);
+    } else {
+        // special first-level entry: recover the symbol from the 16-bit table
+        sym = (uint32_t)tab->lut[hi >> (32 - ZPX_LUT_BITS)] >> 8;
     }
-    if ((e >> 31) && isdc) {  // DC category > 16 (decoder.zig:1370)
-        *err = ZPX_E_ExcessiveDCComponent;
-        e &= 0x7fffffffu;
+    // same field packing as zpx_fast_entry (zpx_parse.cpp)
+    uint32_t size, adv, special = 0, rr = 0;
+    if (isdc) {
+        size = sym;
+        adv = 1;
+        if (sym > 16) {  // DC category > 16 (decoder.zig:1370)
+            size = 0;
+            err = ZPX_E_ExcessiveDCComponent;
+        }
+    } else {
+        const uint32_t r = sym >> 4, s2 = sym & 15;
+        if (s2 != 0) { size = s2; adv = r + 1; }
+        else if (r == 15) { size = 0; adv = 16; }
+        else if (r == 0) { size = 0; adv = 64; }
+        else { size = 0; adv = 64; special = 1; rr = r; }
     }
-    return e;  // AC special (EOB run) keeps bit 31: the caller reads the run bits
+    e = ((uint32_t)len + size) | (uint32_t)len << 8 | size << 13 | adv << 18 | rr << 25 | special << 31;
+    return (unsigned long long)e | ((unsigned long long)(uint32_t)err << 32);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
-    __shared__ uint4 sblk[8 * NT];   // per-lane block: [8 rows][NT lanes] x 16 bytes
-    __shared__ uint8_t s_unzig[80];  // lane-divergent index: shared, not constant, memory (padded: k+run <= 78)
-    const int gid = blockIdx.x * NT + threadIdx.x;
-    for (int r = 0; r < 8; r++) sblk[r * NT + threadIdx.x] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x < 80) s_unzig[threadIdx.x] = threadIdx.x < 64 ? c_unzig[threadIdx.x] : 63;
-    __syncthreads();
-    const uint32_t sb = smem_addr(sblk) + threadIdx.x * 16;  // this lane's row 0
-    const uint32_t su = smem_addr(s_unzig);
+// ---------------------------------------------------------------------------
+// The kernel.  Per CTA (NT lanes = NT consecutive restart intervals, usually 2-3 images):
+//   setup   the distinct scans and Huffman tables of the CTA's intervals are collected; the tables'
+//           first-level LUTs (K1_SLB bits) and the scans' per-block descriptors are staged in shared
+//           memory, so the per-symbol lookup is one LDS and a block end touches no global descriptor.
+//           CTAs with more than K1_MAXT tables / K1_MAXS scans fall back to the global LUTs.
+//   loop    K1_T symbol steps per warp vote; a lane that finishes a block idles until the vote, then
+//           the block-end code (flush + next block) runs once for all lanes that finished.
+// ---------------------------------------------------------------------------
+constexpr int K1_SLB = 9;     // bits of the shared-memory first-level LUT
+constexpr int K1_MAXT = 12;   // Huffman tables cached per CTA (static shared memory stays under 48 KB)
+constexpr int K1_MAXS = 8;    // scans cached per CTA
+constexpr int K1_T = 2;       // symbol steps per vote
 
-    // lanes past the end of the interval list idle through the loop (the loop head is a warp vote)
-    const ZpxIntervalDev iv = P.ivs[gid < P.n_iv ? gid : P.n_iv - 1];
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+template <int NT, bool SMEM>
+__device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxIntervalDev& iv, const bool live, const uint32_t sb,
+                                             const uint32_t su, const uint32_t sdesc /* smem: this lane's scan's blk table */,
+                                             const uint32_t slut /* smem: LUT slots base */) {
     const ZpxScanDev* __restrict__ sc = &P.scans[iv.scan];
     const ZpxImageDev* __restrict__ im = &P.imgs[sc->img];
 
@@ -194,7 +213,6 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
     const uint64_t coef_base = im->coef_base;
     const uint32_t bpm = (uint32_t)im->bpm;
 
-    // position of the current block
     uint32_t mcu = iv.first_mcu, mx = 0, my = 0, bxn = 0, byn = 0;
     if (interleaved) {
         mx = mcu % mxx;
@@ -204,137 +222,227 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
         bxn = iv.first_block - byn * cw;
     }
     int c = 0;
-    uint4 bi = bpack[0];
-    const uint32_t* __restrict__ fdc = P.huff[bi.x].fast;
-    const uint32_t* __restrict__ fac = P.huff[bi.y].fast;
+    // bi: x = DC table (SMEM: shared address of its LUT slot; else table index), y = AC likewise,
+    //     z = comp | hx << 8 | vy << 16 | slot << 24, w = h | v << 8 | undefined-table flags
+    uint4 bi = SMEM ? lds_u128(sdesc) : bpack[0];
+    const uint32_t* __restrict__ gdc = SMEM ? nullptr : P.huff[bi.x].fast;
+    const uint32_t* __restrict__ gac = SMEM ? nullptr : P.huff[bi.y].fast;
 
     int dc0 = 0, dc1 = 0, dc2 = 0, dc3 = 0;
     uint32_t eob_run = 0;
-    int k = 0;                       // 0: the next symbol is the block's DC; 1..63: next AC index
-    uint32_t left = gid < P.n_iv ? iv.n_blocks : 0;  // blocks still to decode (including the current one)
+    int k = 0;                             // 0: next symbol is the block's DC; 1..63: next AC index; > 63: block done
+    uint32_t left = live ? iv.n_blocks : 0;  // blocks still to decode (including the current one)
+    int err = 0;
 
     while (__any_sync(0xffffffffu, left != 0)) {
-        if (left != 0) {
-            if (br.cnt <= 32) br.refill();
-            if (br.cnt <= 32) br.refill();  // a word with FF 00 pairs or a range edge feeds fewer than 32 bits
-            const uint32_t hi = (uint32_t)(br.buf >> 32);
-            const bool isdc = k == 0;
-            const uint32_t* __restrict__ ftab = isdc ? fdc : fac;
-            uint32_t e = __ldg(ftab + (hi >> (32 - ZPX_LUT_BITS)));
-            int err = 0;
-            if ((int)e <= 0) {  // longer code, invalid code, EOB run or DC category > 16: about 1 % of the symbols
-                e = k1_slow_symbol(reinterpret_cast<const ZpxHuffDev*>(ftab), hi, isdc, e, &err);
-            }
-            if (bi.w & (isdc ? 0x10000u : 0x20000u)) err = ZPX_E_UninitializedHuffmanTable;
-            const int len = (int)((e >> 8) & 31u), size = (int)((e >> 13) & 31u);
-            int tot = (int)(e & 63u);
-            const int adv = (int)((e >> 18) & 127u);
-            // RECEIVE + EXTEND (decoder.zig:1115-1134): size bits after the code
-            const uint32_t t = (uint32_t)((br.buf << len) >> 32);
-            int v = (int)((t >> 1) >> (31 - size));
-            v += (~((int)t >> 31)) & (1 - (1 << size));  // first bit 0 -> negative; size 0 -> 0
-            const int kk = k + adv - 1;  // zig-zag index the value goes to
-            bool store = size != 0;
-            if (isdc) {
-                // decoder.zig:1366-1376
-                const int comp = (int)(bi.z & 0xff);
-                int dc = comp == 0 ? dc0 : comp == 1 ? dc1 : comp == 2 ? dc2 : dc3;
-                dc += v;
-                if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
-                v = dc;
-                store = true;
-                if ((dc < -32768 || dc > 32767) && !err) err = ZPX_E_COEF_RANGE;
-                k = 1;
-                if (eob_run > 0) {  // decoder.zig:1379-1380 (End-Of-Band run)
-                    eob_run--;
-                    k = 64;
+#pragma unroll
+        for (int u = 0; u < K1_T; u++) {
+            if (left != 0 && k <= 63) {
+                if (br.cnt <= 32) br.refill();
+                if (br.cnt <= 32) br.refill();  // a word with FF 00 pairs or a range edge feeds fewer than 32 bits
+                const uint32_t hi = (uint32_t)(br.buf >> 32);
+                const bool isdc = k == 0;
+                uint32_t e;
+                if (SMEM) e = lds_u32((isdc ? bi.x : bi.y) + ((hi >> (32 - K1_SLB)) << 2));
+                else e = __ldg((isdc ? gdc : gac) + (hi >> (32 - ZPX_LUT_BITS)));
+                if ((int)e <= 0) {  // longer code, invalid code, EOB run or DC category > 16: about 1 % of the symbols
+                    const ZpxHuffDev* __restrict__ tab;
+                    if (SMEM) {
+                        const uint32_t slot = ((isdc ? bi.x : bi.y) - slut) >> (K1_SLB + 2);
+                        tab = &P.huff[lds_u32(slut + (K1_MAXT << (K1_SLB + 2)) + slot * 4)];
+                    } else {
+                        tab = reinterpret_cast<const ZpxHuffDev*>(isdc ? gdc : gac);
+                    }
+                    const uint32_t e10 = SMEM ? __ldg(&tab->fast[hi >> (32 - ZPX_LUT_BITS)]) : e;
+                    const unsigned long long r = k1_slow_symbol(tab, hi, isdc, e10);
+                    e = (uint32_t)r;
+                    err = (int)(r >> 32);
+                    if (e >> 31) {
+                        // (r, 0) with 0 < r < 15 (decoder.zig:1399-1407): eob_run = (1 << r | next r bits) - 1
+                        const int len = (int)((e >> 8) & 31u), rr = (int)((e >> 25) & 15u);
+                        eob_run = (1u << rr) | (uint32_t)((br.buf << len) >> (64 - rr));
+                        eob_run = (eob_run - 1) & 0xffffu;
+                        e = (e & 0x01ffffc0u) | (uint32_t)(len + rr);  // consume code + run bits, adv stays 64
+                    }
                 }
-            } else {
-                if (kk > 63) {  // decoder.zig:1393-1395: run past the block end, the value bits stay unread
-                    tot = len;
-                    store = false;
+                if (bi.w & (isdc ? 0x10000u : 0x20000u)) err = ZPX_E_UninitializedHuffmanTable;
+                const int len = (int)((e >> 8) & 31u), size = (int)((e >> 13) & 31u);
+                int tot = (int)(e & 63u);
+                const int adv = (int)((e >> 18) & 127u);
+                // RECEIVE + EXTEND (decoder.zig:1115-1134): size bits after the code
+                const uint32_t t = (uint32_t)((br.buf << len) >> 32);
+                int v = (int)((t >> 1) >> (31 - size));
+                v += (~((int)t >> 31)) & (1 - (1 << size));  // first bit 0 -> negative; size 0 -> 0
+                const int kk = k + adv - 1;                    // zig-zag index the value goes to
+                bool store = size != 0;
+                if (isdc) {
+                    // decoder.zig:1366-1376
+                    const int comp = (int)(bi.z & 0xff);
+                    int dc = comp == 0 ? dc0 : comp == 1 ? dc1 : comp == 2 ? dc2 : dc3;
+                    dc += v;
+                    if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
+                    v = dc;
+                    store = true;
+                    if ((dc < -32768 || dc > 32767) && !err) err = ZPX_E_COEF_RANGE;
+                    k = 1;
+                    if (eob_run > 0) {  // decoder.zig:1379-1380 (End-Of-Band run)
+                        eob_run--;
+                        k = 64;
+                    }
+                } else {
+                    if (kk > 63) {  // decoder.zig:1393-1395: run past the block end, the value bits stay unread
+                        tot = len;
+                        store = false;
+                    }
+                    k += adv;
                 }
-                k += adv;
-            }
-            if ((e >> 31) && !isdc) {
-                // (r, 0) with 0 < r < 15: eob_run = (1 << r | next r bits) - 1; r is not in the entry,
-                // recover it from the symbol table
-                const ZpxHuffDev* __restrict__ tab = reinterpret_cast<const ZpxHuffDev*>(ftab);
-                const uint32_t s16 = __ldg(&tab->lut[hi >> (32 - ZPX_LUT_BITS)]);
-                uint32_t sym = s16 >> 8;
-                if ((s16 & 0xff) == 0) {
-                    const uint32_t v16 = hi >> 16;
-                    for (int l = ZPX_LUT_BITS + 1; l <= 16; l++)
-                        if (v16 < tab->limit[l]) { sym = tab->vals[(tab->valoff[l] + (int)(v16 >> (16 - l))) & 0xff]; break; }
+                br.buf <<= tot;
+                br.cnt -= tot;
+                if (store) {
+                    const uint32_t nat = lds_u8(su + kk);
+                    sts_u16(sb + (nat >> 3) * (NT * 16) + (nat & 7) * 2, v);
                 }
-                const int r = (int)(sym >> 4);
-                eob_run = (1u << r) | (uint32_t)((br.buf << len) >> (64 - r));
-                eob_run = (eob_run - 1) & 0xffffu;
-                tot = len + r;
+                if (err) k = 64;
             }
-            br.buf <<= tot;
-            br.cnt -= tot;
-            if (store) {
-                const uint32_t nat = lds_u8(su + kk);
-                sts_u16(sb + (nat >> 3) * (NT * 16) + (nat & 7) * 2, v);
-            }
-            if (err) {
+        }
+        if (left != 0 && k > 63) {
+            if (err || br.overrun()) {
                 // a symbol that needed bits past the limit is the reference's MissingFF00 / UnexpectedEof,
                 // whatever the garbage decoded to
                 if (br.overrun()) err = (iv.flags & 1) ? ZPX_E_UnexpectedEof : ZPX_E_MissingFF00;
                 report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + (iv.n_blocks - left), err);
                 left = 0;
-            } else if (k > 63) {
-                if (br.overrun()) {
-                    report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + (iv.n_blocks - left),
-                           (iv.flags & 1) ? ZPX_E_UnexpectedEof : ZPX_E_MissingFF00);
-                    left = 0;
-                } else {
-                    // ---- hand the block to HBM: slot s of the 128-byte line holds row s ^ key ----
-                    uint32_t bx;
-                    uint64_t blk;
-                    if (interleaved) {
-                        bx = (bi.w & 0xff) * mx + ((bi.z >> 8) & 0xff);
-                        if (planar) {
-                            const int comp = (int)(bi.z & 0xff);
-                            const uint32_t by = ((bi.w >> 8) & 0xff) * my + ((bi.z >> 16) & 0xff);
-                            blk = im->comp_base[comp] + (uint64_t)by * im->comp_bw[comp] + bx;
-                        } else {
-                            blk = coef_base + (uint64_t)mcu * bpm + (bi.z >> 24);
-                        }
-                    } else {
-                        bx = bxn;
+            } else {
+                // ---- hand the block to HBM: slot s of the 128-byte line holds row s ^ key ----
+                uint32_t bx;
+                uint64_t blk;
+                if (interleaved) {
+                    bx = (bi.w & 0xff) * mx + ((bi.z >> 8) & 0xff);
+                    if (planar) {
                         const int comp = (int)(bi.z & 0xff);
-                        blk = im->comp_base[comp] + (uint64_t)byn * im->comp_bw[comp] + bx;
+                        const uint32_t by = ((bi.w >> 8) & 0xff) * my + ((bi.z >> 16) & 0xff);
+                        blk = im->comp_base[comp] + (uint64_t)by * im->comp_bw[comp] + bx;
+                    } else {
+                        blk = coef_base + (uint64_t)mcu * bpm + (bi.z >> 24);
                     }
-                    uint4* __restrict__ dst = P.coef + blk * 8;
-                    const uint32_t key = bx & 7;
+                } else {
+                    bx = bxn;
+                    const int comp = (int)(bi.z & 0xff);
+                    blk = im->comp_base[comp] + (uint64_t)byn * im->comp_bw[comp] + bx;
+                }
+                uint4* __restrict__ dst = P.coef + blk * 8;
+                const uint32_t key = bx & 7;
 #pragma unroll
-                    for (uint32_t slot = 0; slot < 8; slot++) {
-                        const uint32_t a = sb + (slot ^ key) * (NT * 16);
-                        dst[slot] = lds_v4(a);
-                        sts_zero16(a);
+                for (uint32_t slot = 0; slot < 8; slot++) {
+                    const uint32_t a = sb + (slot ^ key) * (NT * 16);
+                    dst[slot] = lds_v4(a);
+                    sts_zero16(a);
+                }
+                // ---- next block ----
+                left--;
+                k = 0;
+                if (interleaved) {
+                    if (++c == nblk) {
+                        c = 0;
+                        mcu++;
+                        if (++mx == mxx) { mx = 0; my++; }
                     }
-                    // ---- next block ----
-                    left--;
-                    k = 0;
-                    if (interleaved) {
-                        if (++c == nblk) {
-                            c = 0;
-                            mcu++;
-                            if (++mx == mxx) { mx = 0; my++; }
-                        }
+                    if (SMEM) {
+                        bi = lds_u128(sdesc + c * 16);
+                    } else {
                         bi = bpack[c];
-                        fdc = P.huff[bi.x].fast;
-                        fac = P.huff[bi.y].fast;
-                    } else if (++bxn == cw) {
-                        bxn = 0;
-                        byn++;
+                        gdc = P.huff[bi.x].fast;
+                        gac = P.huff[bi.y].fast;
                     }
+                } else if (++bxn == cw) {
+                    bxn = 0;
+                    byn++;
                 }
             }
         }
     }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
+    __shared__ uint4 sblk[8 * NT];   // per-lane block: [8 rows][NT lanes] x 16 bytes
+    __shared__ uint8_t s_unzig[80];  // lane-divergent index: shared, not constant, memory (padded: k+run <= 78)
+    __shared__ __align__(16) uint32_t s_lut[(K1_MAXT << K1_SLB) + K1_MAXT];  // LUT slots, then the slots' table indices
+    __shared__ uint4 s_desc[K1_MAXS][ZPX_MAX_BLK_PER_MCU];
+    __shared__ uint32_t s_scan[K1_MAXS];
+    __shared__ uint32_t s_lane_scan[NT];
+    __shared__ int s_nscan, s_ntab, s_ok;
+
+    const int tid = threadIdx.x;
+    const int gid = blockIdx.x * NT + tid;
+    for (int r = 0; r < 8; r++) sblk[r * NT + tid] = make_uint4(0, 0, 0, 0);
+    if (tid < 80) s_unzig[tid] = tid < 64 ? c_unzig[tid] : 63;
+    // lanes past the end of the interval list idle through the loop (the loop head is a warp vote)
+    const bool live = gid < P.n_iv;
+    const ZpxIntervalDev iv = P.ivs[live ? gid : P.n_iv - 1];
+    s_lane_scan[tid] = iv.scan;
+    __syncthreads();
+
+    // ---- collect the CTA's scans and tables (one thread; a few dozen steps) ----
+    if (tid == 0) {
+        int ns = 0, nt = 0, ok = 1;
+        uint32_t* tab_ids = s_lut + (K1_MAXT << K1_SLB);
+        for (int l = 0; l < NT && ok; l++) {
+            const uint32_t scn = s_lane_scan[l];
+            if (l > 0 && scn == s_lane_scan[l - 1]) continue;
+            int f = -1;
+            for (int i = 0; i < ns; i++)
+                if (s_scan[i] == scn) f = i;
+            if (f >= 0) continue;
+            if (ns == K1_MAXS) { ok = 0; break; }
+            const ZpxScanDev* sc = &P.scans[scn];
+            const int nb = sc->interleaved ? sc->nblk : 1;
+            for (int b = 0; b < nb && ok; b++) {
+                uint4 d = reinterpret_cast<const uint4*>(sc->blk_pack)[b];
+                uint32_t ids[2] = {d.x, d.y};
+                for (int j = 0; j < 2; j++) {
+                    int slot = -1;
+                    for (int i = 0; i < nt; i++)
+                        if (tab_ids[i] == ids[j]) slot = i;
+                    if (slot < 0) {
+                        if (nt == K1_MAXT) { ok = 0; break; }
+                        slot = nt++;
+                        tab_ids[slot] = ids[j];
+                    }
+                    ids[j] = (uint32_t)__cvta_generic_to_shared(s_lut) + ((uint32_t)slot << (K1_SLB + 2));
+                }
+                d.x = ids[0];
+                d.y = ids[1];
+                s_desc[ns][b] = d;
+            }
+            s_scan[ns++] = scn;
+        }
+        s_nscan = ns;
+        s_ntab = nt;
+        s_ok = ok;
+    }
+    __syncthreads();
+    const bool cached = s_ok != 0;
+    uint32_t sdesc = 0;
+    if (cached) {
+        // stage the LUTs: entry i of the K1_SLB-bit table = entry 2^(10-SLB)*i of the 10-bit one if its code fits
+        const int nt = s_ntab;
+        const uint32_t* tab_ids = s_lut + (K1_MAXT << K1_SLB);
+        for (int i = tid; i < (nt << K1_SLB); i += NT) {
+            const int slot = i >> K1_SLB, ix = i & ((1 << K1_SLB) - 1);
+            uint32_t e = __ldg(&P.huff[tab_ids[slot]].fast[ix << (ZPX_LUT_BITS - K1_SLB)]);
+            if (((e >> 8) & 31u) > (uint32_t)K1_SLB) e = 0;
+            s_lut[i] = e;
+        }
+        for (int i = 0; i < s_nscan; i++)
+            if (s_scan[i] == iv.scan) sdesc = (uint32_t)__cvta_generic_to_shared(&s_desc[i][0]);
+    }
+    __syncthreads();
+    const uint32_t sb = smem_addr(sblk) + tid * 16;  // this lane's row 0
+    const uint32_t su = smem_addr(s_unzig);
+    const uint32_t slut = smem_addr(s_lut);
+    if (cached) k1_lane_loop<NT, true>(P, iv, live, sb, su, sdesc, slut);
+    else k1_lane_loop<NT, false>(P, iv, live, sb, su, 0, 0);
 }
 
 cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s) {
