@@ -145,8 +145,9 @@ struct zpx_ctx {
     int last_cuda = 0;
     std::string last_cuda_str;
     std::atomic<uint64_t> launches{0};
-    int64_t opt_entropy_mode = 0, opt_force_generic = 0, opt_subseq = 0;
+    int64_t opt_entropy_mode = 0, opt_force_generic = 0, opt_subseq = 0, opt_pipeline_chunk = 0, opt_lanes_per_warp = 0;
     bool busy = false;
+    zpx_ctx* shadow = nullptr;  // second set of device buffers/streams for the chunk pipeline of zpx_decode_batch_rgba
 };
 
 struct zpx_batch {
@@ -528,6 +529,7 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
     k1.huff = (const ZpxHuffDev*)(desc + pl.off_huff);
     k1.coef = (uint4*)dc.coef.p;
     k1.status = (unsigned long long*)dc.status.p;
+    k1.lanes_per_warp = ctx->opt_lanes_per_warp == 16 ? 16 : 32;
     if (k1.n_iv > 0 && !pl.sub_mode) {
         CU(ctx, k1_launch_lane_per_interval(k1, st));
         k1_launches++;
@@ -769,6 +771,7 @@ int32_t zpx_ctx_create(const int32_t* device_ids, int32_t n_devices, zpx_ctx** o
 
 void zpx_ctx_destroy(zpx_ctx* c) {
     if (!c) return;
+    if (c->shadow) zpx_ctx_destroy(c->shadow);
     for (DeviceCtx& d : c->devs) {
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
@@ -801,6 +804,8 @@ int32_t zpx_ctx_set_option(zpx_ctx* c, int32_t option, int64_t value) {
         case ZPX_OPT_ENTROPY_MODE: c->opt_entropy_mode = value; return ZPX_OK;
         case ZPX_OPT_FORCE_GENERIC: c->opt_force_generic = value; return ZPX_OK;
         case ZPX_OPT_SUBSEQ_BYTES: c->opt_subseq = value; return ZPX_OK;
+        case ZPX_OPT_PIPELINE_CHUNK: c->opt_pipeline_chunk = value; return ZPX_OK;
+        case ZPX_OPT_LANES_PER_WARP: c->opt_lanes_per_warp = value; return ZPX_OK;
     }
     return ZPX_E_INVALID_ARG;
 }
@@ -1122,8 +1127,8 @@ void zpx_batch_close(zpx_batch* b) {
     delete b;
 }
 
-int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* lens, int32_t n,
-                              uint8_t* const* out, const size_t* out_stride, int32_t* status) {
+static int32_t decode_range_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* lens, int32_t n,
+                                 uint8_t* const* out, const size_t* out_stride, int32_t* status) {
     zpx_batch* b = nullptr;
     int e = zpx_batch_open(ctx, bufs, lens, n, &b);
     if (e) return e;
@@ -1132,6 +1137,54 @@ int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const si
     if (!e) e = zpx_batch_fetch_rgba(b, out, out_stride, status);
     zpx_batch_close(b);
     return e;
+}
+
+// Large batches are cut into chunks that flow through two sets of device buffers and streams
+// (context + shadow context, one host thread each): while one chunk's RGBA travels back over PCIe,
+// the next chunk is parsed, uploaded and decoded.  Images are independent, so chunking changes
+// nothing in the results.
+int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* lens, int32_t n,
+                              uint8_t* const* out, const size_t* out_stride, int32_t* status) {
+    if (!ctx || n < 0 || (n > 0 && (!bufs || !lens || !out))) return ZPX_E_INVALID_ARG;
+    int32_t chunk = ctx->opt_pipeline_chunk > 0 ? (int32_t)ctx->opt_pipeline_chunk : 128;
+    if (ctx->opt_pipeline_chunk < 0 || n < 2 * chunk) return decode_range_rgba(ctx, bufs, lens, n, out, out_stride, status);
+    if (!ctx->shadow) {
+        std::vector<int32_t> ids;
+        for (const DeviceCtx& d : ctx->devs) ids.push_back(d.dev);
+        int e = zpx_ctx_create(ids.data(), (int32_t)ids.size(), &ctx->shadow);
+        if (e) return e;
+    }
+    ctx->shadow->opt_entropy_mode = ctx->opt_entropy_mode;
+    ctx->shadow->opt_force_generic = ctx->opt_force_generic;
+    ctx->shadow->opt_subseq = ctx->opt_subseq;
+    ctx->shadow->opt_lanes_per_warp = ctx->opt_lanes_per_warp;
+    const int32_t n_chunks = (n + chunk - 1) / chunk;
+    std::atomic<int32_t> next(0);
+    int32_t rc[2] = {0, 0};
+    std::vector<int32_t> st(status ? 0 : n);
+    int32_t* stp = status ? status : st.data();
+    auto worker = [&](int w) {
+        zpx_ctx* c = w == 0 ? ctx : ctx->shadow;
+        for (;;) {
+            const int32_t k = next.fetch_add(1);
+            if (k >= n_chunks) break;
+            const int32_t i0 = k * chunk, cnt = std::min(chunk, n - i0);
+            const int e = decode_range_rgba(c, bufs + i0, lens + i0, cnt, out + i0, out_stride ? out_stride + i0 : nullptr, stp + i0);
+            if (e) {
+                rc[w] = e;
+                if (w == 1) {  // surface the CUDA error text on the caller's context
+                    ctx->last_cuda = c->last_cuda;
+                    ctx->last_cuda_str = c->last_cuda_str;
+                }
+                break;
+            }
+        }
+    };
+    std::thread t1(worker, 1);
+    worker(0);
+    t1.join();
+    ctx->launches += ctx->shadow->launches.exchange(0);
+    return rc[0] ? rc[0] : rc[1];
 }
 
 }  // extern "C"

@@ -54,74 +54,89 @@ __device__ __forceinline__ void sts_zero16(uint32_t addr) {
 }
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// stuffed-stream reader with the words loaded two refills ahead
+// Stuffed-stream reader.  `nw` always holds the next word of the stream, loaded when the previous one
+// was fed (a predicated load straight into nw's register: nothing waits for it until the next refill,
+// several symbols later).  feed() is straight-line code for the common case (32 data bits, no 0xFF,
+// inside the range); edges, FF 00 pairs and the end of the data take feed_slow().
 struct FastReader {
-    const uint32_t* wp;  // next word to LOAD
-    uint32_t w1, w2;     // loaded words: w1 is fed next, then w2
-    uint32_t off;        // byte offset (from the 4-byte aligned base) of w1
-    uint32_t first, end; // valid byte range
-    uint64_t buf;        // unread bits, left aligned
-    int cnt;             // bits in buf (data + zero padding)
-    int pad;             // zero padding bits appended after the data ran out (always at the tail)
-    uint32_t skip;       // next byte is the 0x00 of an FF 00 pair
+    const uint32_t* base;  // 4-byte aligned base of the interval
+    uint32_t off;          // byte offset (from base) of nw
+    uint32_t first, end;   // valid byte range
+    uint32_t nw;           // base[off / 4]
+    uint64_t buf;          // unread bits, left aligned
+    int cnt;               // bits in buf (data + zero padding)
+    int pad;               // zero padding bits appended after the data ran out (always at the tail)
+    uint32_t skip;         // next byte is the 0x00 of an FF 00 pair
 
     __device__ __forceinline__ void init(const uint8_t* blob, uint64_t start, uint32_t len) {
         const uint64_t a = start & ~(uint64_t)3;
-        const uint32_t* base = reinterpret_cast<const uint32_t*>(blob + a);
+        base = reinterpret_cast<const uint32_t*>(blob + a);
         first = (uint32_t)(start - a);
         end = first + len;
         off = 0;
-        w1 = __ldg(base);
-        w2 = __ldg(base + 1);
-        wp = base + 2;
+        nw = __ldg(base);
         buf = 0;
         cnt = 0;
         pad = 0;
         skip = 0;
-        while (cnt <= 32) refill();
+        feed_slow();  // the first word may start before `first`
     }
     __device__ __forceinline__ bool overrun() const { return cnt < pad; }
 
-    // feed one word; precondition cnt <= 32
-    __device__ __forceinline__ void refill() {
-        const uint32_t raw = w1;
-        w1 = w2;
-        const uint32_t o = off;
-        off += 4;
-        if (off + 4 < end + 8) w2 = __ldg(wp++);  // never more than 2 words past the limit (blob is padded)
+    // make sure more than 32 bits are buffered
+    __device__ __forceinline__ void feed() {
+        const bool need = cnt <= 32;
+        const uint32_t raw = nw;
         const uint32_t nff = ~raw;
         const uint32_t hasff = (nff - 0x01010101u) & raw & 0x80808080u;
-        const uint32_t be = __byte_perm(raw, 0, 0x0123);
-        if ((hasff | skip) == 0 && o >= first && o + 4 <= end) {
-            buf |= ((uint64_t)be << 32) >> cnt;
+        const bool fast = need && (hasff | skip) == 0 && off + 4 <= end;  // off >= first after init
+        if (fast) {
+            buf |= ((uint64_t)__byte_perm(raw, 0, 0x0123) << 32) >> cnt;
             cnt += 32;
-            return;
+            off += 4;
         }
-        if (o >= end) {  // past the limit: zeros
-            cnt += 32;
-            pad += 32;
-            return;
+        {
+            const uint32_t* p = base + (off >> 2);
+            asm volatile(
+                "{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p ld.global.nc.u32 %0, [%1];\n}\n"
+                : "+r"(nw)
+                : "l"(p), "r"((uint32_t)fast));
         }
-        // byte by byte: range edges, FF 00 pairs
-        uint32_t acc = 0;
-        int nb = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t oo = o + j;
-            const uint32_t b = (be >> (24 - 8 * j)) & 0xffu;
-            if (oo < first || oo >= end) continue;
-            if (skip) {
-                skip = 0;
+        if (need && !fast) feed_slow();
+    }
+
+    // byte by byte: range edges, FF 00 pairs, zero padding past the limit; until cnt > 32
+    __device__ __forceinline__ void feed_slow() {
+        while (cnt <= 32) {
+            const uint32_t o = off;
+            if (o >= end) {
+                cnt += 32;
+                pad += 32;
                 continue;
             }
-            acc = (acc << 8) | b;
-            nb++;
-            if (b == 0xffu) skip = 1;
-        }
-        if (nb) {
-            const uint32_t w = acc << (32 - 8 * nb);
-            buf |= ((uint64_t)w << 32) >> cnt;
-            cnt += 8 * nb;
+            const uint32_t be = __byte_perm(nw, 0, 0x0123);
+            uint32_t acc = 0;
+            int nb = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t oo = o + j;
+                const uint32_t b = (be >> (24 - 8 * j)) & 0xffu;
+                if (oo < first || oo >= end) continue;
+                if (skip) {
+                    skip = 0;
+                    continue;
+                }
+                acc = (acc << 8) | b;
+                nb++;
+                if (b == 0xffu) skip = 1;
+            }
+            if (nb) {
+                const uint32_t w = acc << (32 - 8 * nb);
+                buf |= ((uint64_t)w << 32) >> cnt;
+                cnt += 8 * nb;
+            }
+            off += 4;
+            nw = __ldg(base + (off >> 2));  // at most one word past the limit: the blob is padded
         }
     }
 };
@@ -181,7 +196,6 @@ __device__ __noinline__ unsigned long long k1_slow_symbol(const ZpxHuffDev* __re
 constexpr int K1_SLB = 9;     // bits of the shared-memory first-level LUT
 constexpr int K1_MAXT = 12;   // Huffman tables cached per CTA (static shared memory stays under 48 KB)
 constexpr int K1_MAXS = 8;    // scans cached per CTA
-constexpr int K1_T = 2;       // symbol steps per vote
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
@@ -194,6 +208,37 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
     return v;
 }
 
+// slow-path wrapper shared by the DC and AC steps: returns the entry fields, sets err / eob_run
+template <bool SMEM>
+__device__ __forceinline__ uint32_t k1_rare(const K1Params& P, const FastReader& br, uint32_t hi, bool isdc, uint32_t e,
+                                            uint32_t lut_addr, const uint32_t* gtab, uint32_t slut, uint32_t& eob_run, int& err) {
+    const ZpxHuffDev* __restrict__ tab;
+    if (SMEM) {
+        const uint32_t slot = (lut_addr - slut) >> (K1_SLB + 2);
+        tab = &P.huff[lds_u32(slut + (K1_MAXT << (K1_SLB + 2)) + slot * 4)];
+    } else {
+        tab = reinterpret_cast<const ZpxHuffDev*>(gtab);
+    }
+    const uint32_t e10 = SMEM ? __ldg(&tab->fast[hi >> (32 - ZPX_LUT_BITS)]) : e;
+    const unsigned long long r = k1_slow_symbol(tab, hi, isdc, e10);
+    e = (uint32_t)r;
+    err = (int)(r >> 32);
+    if (e >> 31) {
+        // (r, 0) with 0 < r < 15 (decoder.zig:1399-1407): eob_run = (1 << r | next r bits) - 1
+        const int len = (int)((e >> 8) & 31u), rr = (int)((e >> 25) & 15u);
+        eob_run = (1u << rr) | (uint32_t)((br.buf << len) >> (64 - rr));
+        eob_run = (eob_run - 1) & 0xffffu;
+        e = (e & 0x01ffffc0u) | (uint32_t)(len + rr);  // consume code + run bits, adv stays 64
+    }
+    return e;
+}
+
+// Block-synchronous main loop: the 32 lanes of a warp decode their k-th block together --
+//   DC symbol (all lanes), AC symbols until every lane's block is complete (a warp vote per symbol; a
+//   lane whose block ended idles), block end (all lanes: flush the 128-byte block, next descriptor).
+// Lanes of a warp sit at the same block phase of the MCU (all on luma or all on chroma), so the number
+// of AC iterations is close to the lanes' own symbol counts, and the block-end code runs once per
+// block for all lanes instead of once per symbol for a few.
 template <int NT, bool SMEM>
 __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxIntervalDev& iv, const bool live, const uint32_t sb,
                                              const uint32_t su, const uint32_t sdesc /* smem: this lane's scan's blk table */,
@@ -230,72 +275,65 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
 
     int dc0 = 0, dc1 = 0, dc2 = 0, dc3 = 0;
     uint32_t eob_run = 0;
-    int k = 0;                             // 0: next symbol is the block's DC; 1..63: next AC index; > 63: block done
     uint32_t left = live ? iv.n_blocks : 0;  // blocks still to decode (including the current one)
-    int err = 0;
 
     while (__any_sync(0xffffffffu, left != 0)) {
-#pragma unroll
-        for (int u = 0; u < K1_T; u++) {
-            if (left != 0 && k <= 63) {
-                if (br.cnt <= 32) br.refill();
-                if (br.cnt <= 32) br.refill();  // a word with FF 00 pairs or a range edge feeds fewer than 32 bits
+        int k = 64;  // > 63: no block in flight on this lane
+        int err = 0;
+        if (left != 0) {
+            // ---- DC (decoder.zig:1366-1376) ----
+            br.feed();
+            const uint32_t hi = (uint32_t)(br.buf >> 32);
+            uint32_t e;
+            if (SMEM) e = lds_u32(bi.x + ((hi >> (32 - K1_SLB)) << 2));
+            else e = __ldg(gdc + (hi >> (32 - ZPX_LUT_BITS)));
+            if ((int)e <= 0) e = k1_rare<SMEM>(P, br, hi, true, e, bi.x, gdc, slut, eob_run, err);
+            if (bi.w & 0x10000u) err = ZPX_E_UninitializedHuffmanTable;
+            const int len = (int)((e >> 8) & 31u), size = (int)((e >> 13) & 31u);
+            const uint32_t t = (uint32_t)((br.buf << len) >> 32);
+            int v = (int)((t >> 1) >> (31 - size));
+            v += (~((int)t >> 31)) & (1 - (1 << size));
+            const int comp = (int)(bi.z & 0xff);
+            int dc = comp == 0 ? dc0 : comp == 1 ? dc1 : comp == 2 ? dc2 : dc3;
+            dc += v;
+            if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
+            if ((dc < -32768 || dc > 32767) && !err) err = ZPX_E_COEF_RANGE;
+            br.buf <<= (len + size);
+            br.cnt -= (len + size);
+            sts_u16(sb, dc);
+            k = 1;
+            if (eob_run > 0) {  // decoder.zig:1379-1380 (End-Of-Band run)
+                eob_run--;
+                k = 64;
+            }
+            if (err) k = 64;
+            else if (k == 1 && (bi.w & 0x20000u)) {
+                err = ZPX_E_UninitializedHuffmanTable;
+                k = 64;
+            }
+        }
+        // ---- AC (decoder.zig:1383-1411): one symbol per lane per vote ----
+        while (__any_sync(0xffffffffu, k <= 63)) {
+            if (k <= 63) {
+                br.feed();
                 const uint32_t hi = (uint32_t)(br.buf >> 32);
-                const bool isdc = k == 0;
                 uint32_t e;
-                if (SMEM) e = lds_u32((isdc ? bi.x : bi.y) + ((hi >> (32 - K1_SLB)) << 2));
-                else e = __ldg((isdc ? gdc : gac) + (hi >> (32 - ZPX_LUT_BITS)));
-                if ((int)e <= 0) {  // longer code, invalid code, EOB run or DC category > 16: about 1 % of the symbols
-                    const ZpxHuffDev* __restrict__ tab;
-                    if (SMEM) {
-                        const uint32_t slot = ((isdc ? bi.x : bi.y) - slut) >> (K1_SLB + 2);
-                        tab = &P.huff[lds_u32(slut + (K1_MAXT << (K1_SLB + 2)) + slot * 4)];
-                    } else {
-                        tab = reinterpret_cast<const ZpxHuffDev*>(isdc ? gdc : gac);
-                    }
-                    const uint32_t e10 = SMEM ? __ldg(&tab->fast[hi >> (32 - ZPX_LUT_BITS)]) : e;
-                    const unsigned long long r = k1_slow_symbol(tab, hi, isdc, e10);
-                    e = (uint32_t)r;
-                    err = (int)(r >> 32);
-                    if (e >> 31) {
-                        // (r, 0) with 0 < r < 15 (decoder.zig:1399-1407): eob_run = (1 << r | next r bits) - 1
-                        const int len = (int)((e >> 8) & 31u), rr = (int)((e >> 25) & 15u);
-                        eob_run = (1u << rr) | (uint32_t)((br.buf << len) >> (64 - rr));
-                        eob_run = (eob_run - 1) & 0xffffu;
-                        e = (e & 0x01ffffc0u) | (uint32_t)(len + rr);  // consume code + run bits, adv stays 64
-                    }
-                }
-                if (bi.w & (isdc ? 0x10000u : 0x20000u)) err = ZPX_E_UninitializedHuffmanTable;
+                if (SMEM) e = lds_u32(bi.y + ((hi >> (32 - K1_SLB)) << 2));
+                else e = __ldg(gac + (hi >> (32 - ZPX_LUT_BITS)));
+                if ((int)e <= 0) e = k1_rare<SMEM>(P, br, hi, false, e, bi.y, gac, slut, eob_run, err);
                 const int len = (int)((e >> 8) & 31u), size = (int)((e >> 13) & 31u);
                 int tot = (int)(e & 63u);
                 const int adv = (int)((e >> 18) & 127u);
-                // RECEIVE + EXTEND (decoder.zig:1115-1134): size bits after the code
                 const uint32_t t = (uint32_t)((br.buf << len) >> 32);
                 int v = (int)((t >> 1) >> (31 - size));
-                v += (~((int)t >> 31)) & (1 - (1 << size));  // first bit 0 -> negative; size 0 -> 0
+                v += (~((int)t >> 31)) & (1 - (1 << size));  // first bit 0 -> negative
                 const int kk = k + adv - 1;                    // zig-zag index the value goes to
                 bool store = size != 0;
-                if (isdc) {
-                    // decoder.zig:1366-1376
-                    const int comp = (int)(bi.z & 0xff);
-                    int dc = comp == 0 ? dc0 : comp == 1 ? dc1 : comp == 2 ? dc2 : dc3;
-                    dc += v;
-                    if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
-                    v = dc;
-                    store = true;
-                    if ((dc < -32768 || dc > 32767) && !err) err = ZPX_E_COEF_RANGE;
-                    k = 1;
-                    if (eob_run > 0) {  // decoder.zig:1379-1380 (End-Of-Band run)
-                        eob_run--;
-                        k = 64;
-                    }
-                } else {
-                    if (kk > 63) {  // decoder.zig:1393-1395: run past the block end, the value bits stay unread
-                        tot = len;
-                        store = false;
-                    }
-                    k += adv;
+                if (kk > 63) {  // decoder.zig:1393-1395: run past the block end, the value bits stay unread
+                    tot = len;
+                    store = false;
                 }
+                k += adv;
                 br.buf <<= tot;
                 br.cnt -= tot;
                 if (store) {
@@ -305,7 +343,8 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 if (err) k = 64;
             }
         }
-        if (left != 0 && k > 63) {
+        // ---- block end ----
+        if (left != 0) {
             if (err || br.overrun()) {
                 // a symbol that needed bits past the limit is the reference's MissingFF00 / UnexpectedEof,
                 // whatever the garbage decoded to
@@ -313,7 +352,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + (iv.n_blocks - left), err);
                 left = 0;
             } else {
-                // ---- hand the block to HBM: slot s of the 128-byte line holds row s ^ key ----
+                // hand the block to HBM: slot s of the 128-byte line holds row s ^ key
                 uint32_t bx;
                 uint64_t blk;
                 if (interleaved) {
@@ -338,9 +377,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                     dst[slot] = lds_v4(a);
                     sts_zero16(a);
                 }
-                // ---- next block ----
                 left--;
-                k = 0;
                 if (interleaved) {
                     if (++c == nblk) {
                         c = 0;
@@ -363,7 +400,10 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     }
 }
 
-template <int NT>
+// LPW = lanes of each warp that carry an interval.  The kernel is bound by the latency of a warp's
+// serial step, not by issue slots; with LPW = 16 a warp has half the divergent work per step (fewer
+// block ends, refills and cache misses to wait for) and twice as many warps fill the idle issue slots.
+template <int NT, int LPW>
 __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
     __shared__ uint4 sblk[8 * NT];   // per-lane block: [8 rows][NT lanes] x 16 bytes
     __shared__ uint8_t s_unzig[80];  // lane-divergent index: shared, not constant, memory (padded: k+run <= 78)
@@ -374,11 +414,11 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
     __shared__ int s_nscan, s_ntab, s_ok;
 
     const int tid = threadIdx.x;
-    const int gid = blockIdx.x * NT + tid;
+    const int gid = (blockIdx.x * (NT / 32) + (tid >> 5)) * LPW + (tid & 31);
     for (int r = 0; r < 8; r++) sblk[r * NT + tid] = make_uint4(0, 0, 0, 0);
     if (tid < 80) s_unzig[tid] = tid < 64 ? c_unzig[tid] : 63;
-    // lanes past the end of the interval list idle through the loop (the loop head is a warp vote)
-    const bool live = gid < P.n_iv;
+    // lanes past the end of the interval list (or beyond LPW) idle through the loop (its head is a warp vote)
+    const bool live = gid < P.n_iv && (tid & 31) < LPW;
     const ZpxIntervalDev iv = P.ivs[live ? gid : P.n_iv - 1];
     s_lane_scan[tid] = iv.scan;
     __syncthreads();
@@ -448,7 +488,12 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
 cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s) {
     if (P.n_iv <= 0) return cudaSuccess;
     constexpr int NT = 128;
-    k1_lane_per_interval<NT><<<(P.n_iv + NT - 1) / NT, NT, 0, s>>>(P);
+    if (P.lanes_per_warp == 16) {
+        constexpr int per_cta = (NT / 32) * 16;
+        k1_lane_per_interval<NT, 16><<<(P.n_iv + per_cta - 1) / per_cta, NT, 0, s>>>(P);
+    } else {
+        k1_lane_per_interval<NT, 32><<<(P.n_iv + NT - 1) / NT, NT, 0, s>>>(P);
+    }
     return cudaGetLastError();
 }
 

@@ -17,6 +17,7 @@ struct K1Params {
     const ZpxHuffDev* huff;
     uint4* coef;                  // 8 x uint4 per block
     unsigned long long* status;   // per image: smallest error key, ZPX_STATUS_NONE if none
+    int lanes_per_warp;           // lane-per-interval kernel: 32 or 16 intervals per warp
 };
 cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s);
 
