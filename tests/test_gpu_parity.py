@@ -286,6 +286,27 @@ def test_native_variant_matches_reference_planes(jpeg, fixtures_dir):
         assert np.array_equal(img.rgbaPixels().reshape(ref.height, ref.width, 4), ref.rgbaPixels())
 
 
+def test_one_call_chunk_pipeline(jpeg, fixtures_dir):
+    """zpx_decode_batch_rgba cuts large batches into chunks that alternate between two sets of device
+    buffers; results and per-image status must not depend on the chunking."""
+    names = BASELINE_FIXTURES + PROGRESSIVE_FIXTURES
+    datas = [_read(fixtures_dir, n) for n in names]
+    bad = datas[3][: len(datas[3]) // 2]
+    batch = (datas + [bad]) * 12  # 312 inputs -> chunks of 128/64/32
+    want = [_oracle_rgba(d) for d in datas + [bad]]
+    for chunk in (0, 64, 32, -1):
+        c = jpeg.Context()
+        c.set_option(4, chunk)
+        outs, st = jpeg.decodeBatchOneCall(batch, c)
+        for i, (o, s) in enumerate(zip(outs, st)):
+            w, err = want[i % len(want)]
+            if w is None:
+                assert s != 0 and jpeg.lib.zpx_error_name(s).decode() == err
+            else:
+                assert s == 0 and np.array_equal(o, w), (chunk, i)
+        c.close()
+
+
 def test_empty_batch_and_api_contract(jpeg, ctx):
     outs, st, _ = _gpu_batch(jpeg, ctx, [])
     assert outs == [] and st == []

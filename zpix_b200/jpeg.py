@@ -191,6 +191,28 @@ def decodeBatch(buffers: Sequence[bytes], ctx: Optional[Context] = None, raise_o
     return res
 
 
+def decodeBatchOneCall(buffers: Sequence[bytes], ctx: Optional[Context] = None):
+    """The single C-ABI call `zpx_decode_batch_rgba` (what the Zig `jpeg.decodeBatch` binds): header
+    parse, upload, kernels and download, pipelined in chunks for large batches.
+    Returns (list of HxWx4 uint8 arrays or None, list of status codes)."""
+    ctx = ctx or default_context()
+    n = len(buffers)
+    keep = [np.frombuffer(b, dtype=np.uint8) for b in buffers]
+    infos = []
+    for a in keep:
+        inf = ZpxImageInfo()
+        lib.zpx_probe(a.ctypes.data if a.size else None, a.size, C.byref(inf))
+        infos.append(inf)
+    outs = [np.empty((i.height, i.width, 4), np.uint8) if (i.status == 0 and i.width > 0 and i.height > 0) else None for i in infos]
+    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in keep])
+    lens = (C.c_size_t * max(n, 1))(*[a.size for a in keep])
+    optr = (C.c_void_p * max(n, 1))(*[o.ctypes.data if o is not None else None for o in outs])
+    st = (C.c_int32 * max(n, 1))()
+    _check(ctx.handle, lib.zpx_decode_batch_rgba(ctx.handle, ptrs, lens, n, optr, None, st))
+    st = list(st)[:n]
+    return [o if s == 0 else None for o, s in zip(outs, st)], st
+
+
 def loadBatch(paths: Sequence[str], ctx: Optional[Context] = None, raise_on_error: bool = False):
     bufs = []
     for p in paths:
