@@ -100,7 +100,7 @@ struct BitReader {
     // true if a symbol needed bits the stream does not have
     __device__ __forceinline__ bool overrun() const { return used() > fed; }
 
-    // append up to one word; precondition cnt <= 32
+    // append up to one word, byte by byte (range edges, FF 00 pairs, zeros past the limit)
     __device__ __forceinline__ void fill_once() {
         const uint32_t off = widx * 4;
         if (off >= bnd && !bpassed) {
@@ -116,15 +116,6 @@ struct BitReader {
         widx++;
         nextw = __ldg(words + widx);  // at most one word past the limit: the blob is padded
         const uint32_t be = __byte_perm(raw, 0, 0x0123);
-        const uint32_t nff = ~raw;
-        const bool has_ff = ((nff - 0x01010101u) & ~nff & 0x80808080u) != 0;
-        if (!has_ff && !skip && off >= first && off + 4 <= end) {
-            buf |= ((uint64_t)be << 32) >> cnt;
-            cnt += 32;
-            fed += 32;
-            return;
-        }
-        // slow path: byte by byte (range edges, FF 00 pairs)
         uint32_t acc = 0;
         int nb = 0;
 #pragma unroll
@@ -147,8 +138,31 @@ struct BitReader {
             fed += 8 * nb;
         }
     }
+    // make sure more than 32 bits are buffered.  Common case (a whole word of data without 0xFF) is
+    // straight-line code; the next word is loaded by a predicated load straight into nextw's register,
+    // so nothing waits for it until the next refill.
     __device__ __forceinline__ void fill() {
-        while (cnt <= 32) fill_once();
+        const bool need = cnt <= 32;
+        const uint32_t off = widx * 4;
+        const uint32_t raw = nextw;
+        const uint32_t nff = ~raw;
+        const uint32_t hasff = (nff - 0x01010101u) & raw & 0x80808080u;
+        const bool fast = need && (hasff | skip) == 0 && off >= first && off + 4 <= end && (bpassed || off < bnd);
+        if (fast) {
+            buf |= ((uint64_t)__byte_perm(raw, 0, 0x0123) << 32) >> cnt;
+            cnt += 32;
+            fed += 32;
+            widx++;
+        }
+        {
+            const uint32_t* p = words + widx;
+            asm volatile(
+                "{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p ld.global.nc.u32 %0, [%1];\n}\n"
+                : "+r"(nextw)
+                : "l"(p), "r"((uint32_t)fast));
+        }
+        if (need && !fast)
+            while (cnt <= 32) fill_once();
     }
     __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(buf >> 32); }
     __device__ __forceinline__ void consume(int n) {
