@@ -353,6 +353,21 @@ void build_plan(zpx_batch* b, int di) {
             const int per_row = (p.mxx + tcap - 1) / tcap;
             const int tn = (p.mxx + per_row - 1) / per_row;
             g.tmax = std::max(g.tmax, tn);
+            if (nc == 1 && p.mxx * 2 <= tcap) {
+                // narrow gray image: a tile is several whole MCU rows (contiguous in the coefficient stream)
+                const int nr_max = std::min(16, tcap / p.mxx);
+                g.tmax = std::max(g.tmax, nr_max * p.mxx);
+                for (int my = 0; my < p.myy; my += nr_max) {
+                    const int nr = std::min(nr_max, p.myy - my);
+                    ZpxTileDev t;
+                    t.img = (uint32_t)k;
+                    t.my = (uint16_t)my;
+                    t.n = (uint16_t)(nr * p.mxx);
+                    t.mx0 = 0;
+                    t.pad = (uint32_t)nr | (uint32_t)p.mxx << 16;
+                    g.tiles.push_back(t);
+                }
+            } else
             for (int my = 0; my < p.myy; my++)
                 for (int mx0 = 0; mx0 < p.mxx; mx0 += tn) {
                     ZpxTileDev t;

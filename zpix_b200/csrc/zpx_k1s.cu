@@ -59,9 +59,11 @@ __device__ __forceinline__ void lane_setup(const K1Params& P, const ZpxWarpDev w
 }
 
 // Decode (without output) from state `in` until the first symbol that starts at or after the
-// sub-sequence boundary, or the data runs out.  Invalid codes advance one bit (any deterministic
-// rule works: true states of a well-formed stream never meet one; errors are reported by k1s_write).
-// Called by the lanes in `mask` together; the vote at the loop head keeps them in lock step.
+// sub-sequence boundary, or the data runs out.  Only the bit count and the zig-zag advance of each
+// symbol matter here (one 32-bit entry of ZpxHuffDev::fast); values are extracted for DC symbols only,
+// to accumulate the per-component sums of DC differences.  Invalid codes advance one bit (any
+// deterministic rule works: true states of a well-formed stream never meet one; errors are reported
+// by k1s_write).  Called by the lanes in `mask` together; the vote keeps them in lock step.
 __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, const LaneCtx& L, unsigned long long in,
                                                           unsigned mask, int& n_out, int4& dc_out) {
     BitReader br;
@@ -71,10 +73,9 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
     const int nblk = sc->interleaved ? sc->nblk : 1;
     const uint4* __restrict__ bpack = reinterpret_cast<const uint4*>(sc->blk_pack);
     int n = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-    uint32_t eob_run = 0;
     uint4 bi = bpack[c];
-    const ZpxHuffDev* __restrict__ tdc = &P.huff[bi.x];
-    const ZpxHuffDev* __restrict__ tac = &P.huff[bi.y];
+    const uint32_t* __restrict__ fdc = P.huff[bi.x].fast;
+    const uint32_t* __restrict__ fac = P.huff[bi.y].fast;
     bool go = true;
     while (__any_sync(mask, go)) {
         if (go) {
@@ -82,15 +83,52 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
             if ((br.bpassed && u >= br.B) || (br.pad && u >= br.fed)) {
                 go = false;
             } else {
-                n += k == 0;
-                SymOut so;
-                symbol_step<true>(br, tdc, tac, bi.w, (int)(bi.z & 0xff), k, eob_run, d0, d1, d2, d3, so);
-                if (so.done) {
+                br.fill();
+                const uint32_t hi = br.peek32();
+                const bool isdc = k == 0;
+                const uint32_t* __restrict__ ftab = isdc ? fdc : fac;
+                uint32_t e = __ldg(ftab + (hi >> (32 - ZPX_LUT_BITS)));
+                if ((int)e <= 0) {
+                    // longer code / invalid code / EOB run / DC category > 16 (about 1 % of the symbols)
+                    const ZpxHuffDev* __restrict__ tab = reinterpret_cast<const ZpxHuffDev*>(ftab);
+                    const HuffSym hs = huff_decode(tab, hi);
+                    if (hs.len == 0) {
+                        e = 1u;  // invalid: one bit further, same state (tot = 1, adv = 0)
+                    } else if (isdc) {
+                        const uint32_t size = hs.sym > 16 ? 0u : hs.sym;
+                        e = ((uint32_t)hs.len + size) | (uint32_t)hs.len << 8 | size << 13 | 1u << 18;
+                    } else {
+                        const uint32_t r = hs.sym >> 4, s2 = hs.sym & 15;
+                        uint32_t size = s2, adv = r + 1, extra = 0;
+                        if (s2 == 0) {
+                            size = 0;
+                            adv = r == 15 ? 16 : 64;
+                            extra = (r != 15) ? r : 0;  // EOB run: r more bits belong to the symbol
+                        }
+                        e = ((uint32_t)hs.len + size + extra) | (uint32_t)hs.len << 8 | size << 13 | adv << 18;
+                    }
+                }
+                const int len = (int)((e >> 8) & 31u), size = (int)((e >> 13) & 31u);
+                int tot = (int)(e & 63u);
+                const int adv = (int)((e >> 18) & 127u);
+                if (isdc && adv) {
+                    const uint32_t t = (uint32_t)((br.buf << len) >> 32);
+                    int v = (int)((t >> 1) >> (31 - size));
+                    v += (~((int)t >> 31)) & (1 - (1 << size));
+                    const int comp = (int)(bi.z & 0xff);
+                    if (comp == 0) d0 += v; else if (comp == 1) d1 += v; else if (comp == 2) d2 += v; else d3 += v;
+                    n++;
+                } else if (k + adv - 1 > 63 && size != 0) {
+                    tot = len;  // decoder.zig:1393-1395: run past the block end, the value bits stay unread
+                }
+                k += adv;
+                br.consume(tot);
+                if (k > 63) {
                     k = 0;
                     c = c + 1 == nblk ? 0 : c + 1;
                     bi = bpack[c];
-                    tdc = &P.huff[bi.x];
-                    tac = &P.huff[bi.y];
+                    fdc = P.huff[bi.x].fast;
+                    fac = P.huff[bi.y].fast;
                 }
             }
         }

@@ -76,6 +76,7 @@ struct K2Cfg {
     __host__ __device__ static size_t smem_bytes(int tmax, int ns) {
         size_t s = 32 + 3 * 64 * 4;
         s += (size_t)YROWS * pitch_y(tmax);
+        if (NC == 1) s += 2048;  // gray tiles may span up to 16 MCU rows, each with 16 bytes of row padding
         if (NC == 3) s += (size_t)2 * 8 * pitch_c(tmax);
         s = (s + 127) & ~(size_t)127;
         s += (size_t)ns * tmax * BPM * 128;
@@ -90,11 +91,12 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     uint32_t* qs = reinterpret_cast<uint32_t*>(smem + 32);
-    const int PY = Cfg::pitch_y(P.tmax), PC = Cfg::pitch_c(P.tmax);
+    const int PY0 = Cfg::pitch_y(P.tmax), PC = Cfg::pitch_c(P.tmax);
+    const int PY = PY0;  // layout constant; gray tiles use a per-tile pitch inside the same area
     uint8_t* planeY = smem + 32 + 3 * 64 * 4;
     uint8_t* planeCb = planeY + Cfg::YROWS * PY;
     uint8_t* planeCr = planeCb + 8 * PC;
-    size_t st_off = 32 + 3 * 64 * 4 + (size_t)Cfg::YROWS * PY + (NC == 3 ? (size_t)2 * 8 * PC : 0);
+    size_t st_off = 32 + 3 * 64 * 4 + (size_t)Cfg::YROWS * PY + (NC == 3 ? (size_t)2 * 8 * PC : 2048);
     st_off = (st_off + 127) & ~(size_t)127;
     uint8_t* stage0 = smem + st_off;
     const uint32_t stage_bytes = (uint32_t)P.tmax * BPM * 128;
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
         uint32_t n, mx0, my, img;
         int32_t width, height;
         uint64_t out_off;
+        uint32_t nr, wt;  // gray: the tile is nr whole MCU rows of wt MCUs (n = nr * wt); else nr = 1, wt = n
     };
     __shared__ TileCtx ctx[NS];
     __shared__ __align__(16) uint32_t qsm[NS][3 * 32];  // per row four words q[2j] | q[2j+1] << 24 (dp2a operands)
@@ -140,6 +143,8 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
             c.width = imn->width;
             c.height = imn->height;
             c.out_off = imn->out_off;
+            c.nr = tn.pad & 0xffu ? tn.pad & 0xffu : 1u;
+            c.wt = tn.pad >> 16 ? tn.pad >> 16 : tn.n;
             ctx[stg] = c;
         }
         if (tid < 32 * NC) {
@@ -189,7 +194,16 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
             uint8_t* dst;
             int pitch;
             const uint32_t* q;
-            if (i < nY) {
+            if (NC == 1) {
+                // gray: blocks of nr whole MCU rows, row-major
+                const int wt = (int)t.wt;
+                const int r = i / wt, col = i - r * wt;
+                slot = i;
+                bxa = col;
+                pitch = wt * 8 + 16;
+                dst = planeY + (r * 8) * pitch + col * 8;
+                q = qs_t;
+            } else if (i < nY) {
                 const int nH = n * H;
                 const int vy = (V == 2 && i >= nH) ? 1 : 0;
                 const int bx = i - vy * nH;
@@ -228,8 +242,10 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
             constexpr int NCS = (PXW / H) > 0 ? (PXW / H) : 1;  // chroma samples per item row
             const int W = t.width, Hh = t.height;
             const int x0 = (int)t.mx0 * Cfg::MCU_W, y0 = (int)t.my * Cfg::YROWS;
-            const int ipr = n * (Cfg::MCU_W / PXW);  // items per row(-pair)
-            const int items = ipr * (Cfg::YROWS / RP);
+            const int wt = (NC == 1) ? (int)t.wt : n;
+            const int PYt = (NC == 1) ? wt * 8 + 16 : PY;
+            const int ipr = wt * (Cfg::MCU_W / PXW);  // items per row(-pair)
+            const int items = ipr * ((NC == 1 ? (int)t.nr * 8 : Cfg::YROWS) / RP);
             const uint32_t magic = ipr > 1 ? 0xffffffffu / (uint32_t)ipr + 1u : 0u;  // exact it/ipr for it, ipr < 2^16
             uint8_t* __restrict__ outp = P.out + t.out_off;
             const bool vec_ok = (W & 3) == 0;
@@ -269,7 +285,7 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
 #pragma unroll
                     for (int g = 0; g < PXW / 4; g++) {
                         if (g > 0 && x + 4 * g >= W) break;
-                        const uint32_t yw = *reinterpret_cast<const uint32_t*>(planeY + (row0 + r) * PY + PXW * xg + 4 * g);
+                        const uint32_t yw = *reinterpret_cast<const uint32_t*>(planeY + (row0 + r) * PYt + PXW * xg + 4 * g);
                         uint32_t p[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
