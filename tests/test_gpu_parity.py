@@ -331,3 +331,27 @@ def test_idct_and_colour_exhaustive_blocks(jpeg, ctx):
             Image.fromarray(px, "RGB").save(buf, "JPEG", quality=q, subsampling=sub)
             datas.append(buf.getvalue())
     _assert_same(jpeg, ctx, datas)
+
+
+def test_cpp_host_layer_end_to_end(fixtures_dir, tmp_path):
+    """cpp/zpix.hpp (C++ mirror of jpeg.load / loadBatch / rgbaPixels) over the same C ABI: hashes of the RGBA bytes
+    equal the oracle's."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "zpix_demo"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(root, "cpp", "zpix_demo.cpp"), "-o", str(exe),
+                           "-L" + os.path.join(root, "zpix_b200"), "-lzpixcuda", "-Wl,-rpath," + os.path.join(root, "zpix_b200")])
+    names = ["video-001.jpeg", "video-005.gray.jpeg", "video-001.cmyk.jpeg", "video-001.q50.420.progressive.jpeg"]
+    paths = [os.path.join(fixtures_dir, n) for n in names]
+    r = subprocess.run([str(exe)] + paths, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == len(names)
+    for p, line in zip(paths, lines):
+        want = O.decode(open(p, "rb").read())
+        h = 1469598103934665603
+        for b in want.rgbaPixels().tobytes():
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        assert line.split()[1] == f"{want.width}x{want.height}"
+        assert line.split()[2] == f"fnv1a={h:016x}", line
