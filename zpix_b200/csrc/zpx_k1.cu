@@ -41,6 +41,11 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void sts_u16(uint32_t addr, int v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((short)v) : "memory");
 }
@@ -94,6 +99,8 @@ struct FastReader {
             buf |= ((uint64_t)__byte_perm(raw, 0, 0x0123) << 32) >> cnt;
             cnt += 32;
             off += 4;
+            // L1 allocates 32-byte sectors: ask for the sector four ahead when entering a new one
+            if ((off & 31u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(base) + off + 128));
         }
         {
             const uint32_t* p = base + (off >> 2);
@@ -336,10 +343,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 k += adv;
                 br.buf <<= tot;
                 br.cnt -= tot;
-                if (store) {
-                    const uint32_t nat = lds_u8(su + kk);
-                    sts_u16(sb + (nat >> 3) * (NT * 16) + (nat & 7) * 2, v);
-                }
+                if (store) sts_u16(sb + lds_u16(su + 2 * kk), v);
                 if (err) k = 64;
             }
         }
@@ -406,7 +410,9 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
 template <int NT, int LPW>
 __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
     __shared__ uint4 sblk[8 * NT];   // per-lane block: [8 rows][NT lanes] x 16 bytes
-    __shared__ uint8_t s_unzig[80];  // lane-divergent index: shared, not constant, memory (padded: k+run <= 78)
+    // zig-zag index -> byte offset of that coefficient inside the lane's block (row * NT*16 + column * 2);
+    // lane-divergent index: shared, not constant, memory (padded: k + run <= 78)
+    __shared__ uint16_t s_unzig[80];
     __shared__ __align__(16) uint32_t s_lut[(K1_MAXT << K1_SLB) + K1_MAXT];  // LUT slots, then the slots' table indices
     __shared__ uint4 s_desc[K1_MAXS][ZPX_MAX_BLK_PER_MCU];
     __shared__ uint32_t s_scan[K1_MAXS];
@@ -416,7 +422,10 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
     const int tid = threadIdx.x;
     const int gid = (blockIdx.x * (NT / 32) + (tid >> 5)) * LPW + (tid & 31);
     for (int r = 0; r < 8; r++) sblk[r * NT + tid] = make_uint4(0, 0, 0, 0);
-    if (tid < 80) s_unzig[tid] = tid < 64 ? c_unzig[tid] : 63;
+    if (tid < 80) {
+        const int nat = tid < 64 ? c_unzig[tid] : 63;
+        s_unzig[tid] = (uint16_t)((nat >> 3) * (NT * 16) + (nat & 7) * 2);
+    }
     // lanes past the end of the interval list (or beyond LPW) idle through the loop (its head is a warp vote)
     const bool live = gid < P.n_iv && (tid & 31) < LPW;
     const ZpxIntervalDev iv = P.ivs[live ? gid : P.n_iv - 1];
@@ -478,9 +487,13 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
             if (s_scan[i] == iv.scan) sdesc = (uint32_t)__cvta_generic_to_shared(&s_desc[i][0]);
     }
     __syncthreads();
-    const uint32_t sb = smem_addr(sblk) + tid * 16;  // this lane's row 0
-    const uint32_t su = smem_addr(s_unzig);
-    const uint32_t slut = smem_addr(s_lut);
+    uint32_t sb = smem_addr(sblk) + tid * 16;  // this lane's row 0
+    uint32_t su = smem_addr(s_unzig);
+    uint32_t slut = smem_addr(s_lut);
+    // opaque copies: keeps the shared-window address arithmetic out of the symbol loop
+    asm volatile("mov.u32 %0, %0;" : "+r"(sb));
+    asm volatile("mov.u32 %0, %0;" : "+r"(su));
+    asm volatile("mov.u32 %0, %0;" : "+r"(slut));
     if (cached) k1_lane_loop<NT, true>(P, iv, live, sb, su, sdesc, slut);
     else k1_lane_loop<NT, false>(P, iv, live, sb, su, 0, 0);
 }
