@@ -416,6 +416,12 @@ void build_plan(zpx_batch* b, int di) {
                 }
             }
             sd.nblk = nb;
+            sd.rotate = 0;
+            if (s.ncomp > 1 && nb == s.ncomp) {
+                bool same = true;
+                for (int i = 1; i < nb; i++) same = same && sd.blk_dc[i] == sd.blk_dc[0] && sd.blk_ac[i] == sd.blk_ac[0];
+                sd.rotate = same ? 1 : 0;
+            }
             if (s.ncomp == 1) {
                 const int c = s.comp[0];
                 sd.cw = std::min(im.comp_bw[c], (p.width + 7) / 8);

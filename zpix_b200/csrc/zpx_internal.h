@@ -83,6 +83,11 @@ struct ZpxScanDev {
     int32_t restart_interval;
     int32_t scan_index;  // ordinal of the scan inside the image (error ordering)
     int32_t cw, ch;      // non-interleaved: coded blocks per row / rows = blocks intersecting the image
+    // 1: every block of the MCU uses the same DC and the same AC table and each component has one block:
+    // parsing does not depend on the block phase, so the self-synchronising decoder leaves it out of
+    // its state and attributes DC sums by phase relative to the sub-sequence start (zpx_k1s.cu)
+    int32_t rotate;
+    int32_t pad1[3];
     // per block inside one MCU of this scan
     uint8_t blk_comp[ZPX_MAX_BLK_PER_MCU]; // frame component index
     uint8_t blk_hx[ZPX_MAX_BLK_PER_MCU];

@@ -72,6 +72,10 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
     const ZpxScanDev* __restrict__ sc = L.sc;
     const int nblk = sc->interleaved ? sc->nblk : 1;
     const uint4* __restrict__ bpack = reinterpret_cast<const uint4*>(sc->blk_pack);
+    // rotate mode: the phase is not part of the state; c counts blocks relative to this sub-sequence and
+    // the DC sums are kept per relative phase (k1s_scan rotates them into components)
+    const bool rotate = sc->rotate != 0;
+    if (rotate) c = 0;
     int n = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
     uint4 bi = bpack[c];
     const uint32_t* __restrict__ fdc = P.huff[bi.x].fast;
@@ -115,7 +119,7 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
                     const uint32_t t = (uint32_t)((br.buf << len) >> 32);
                     int v = (int)((t >> 1) >> (31 - size));
                     v += (~((int)t >> 31)) & (1 - (1 << size));
-                    const int comp = (int)(bi.z & 0xff);
+                    const int comp = rotate ? c : (int)(bi.z & 0xff);
                     if (comp == 0) d0 += v; else if (comp == 1) d1 += v; else if (comp == 2) d2 += v; else d3 += v;
                     n++;
                 } else if (k + adv - 1 > 63 && size != 0) {
@@ -135,7 +139,9 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
     }
     n_out = n;
     dc_out = make_int4(d0, d1, d2, d3);
-    return pack_state(br.rawpos(), c, k);
+    // a DC symbol decoded in rotate mode belongs to relative phase c *before* the block ends; when the
+    // sub-sequence ends inside a block, that block's phase is (c) and was counted -- nothing to fix
+    return pack_state(br.rawpos(), rotate ? 0 : c, k);
 }
 
 // ---------------------------------------------------------------------------
@@ -211,6 +217,9 @@ __global__ void __launch_bounds__(K1S_NT) k1s_scan(const K1SParams P) {
     const int lane = threadIdx.x & 31;
     if (d >= P.n_iv) return;
     const ZpxIntervalDev* iv = &P.k1.ivs[d];
+    const ZpxScanDev* sc = &P.k1.scans[iv->scan];
+    const bool rotate = sc->rotate != 0;
+    const int nblk = sc->nblk;
     const uint32_t nsub = iv->nsub, base = iv->sub_first;
     int cn = 0;
     int4 cd = make_int4(0, 0, 0, 0);
@@ -218,19 +227,41 @@ __global__ void __launch_bounds__(K1S_NT) k1s_scan(const K1SParams P) {
         const uint32_t i = i0 + lane;
         int n = 0;
         int4 v = make_int4(0, 0, 0, 0);
+        int kstart = 0;
         if (i < nsub) {
             n = P.s_n[base + i];
             v = P.s_dc[base + i];
+            kstart = (int)((P.s_in[base + i] >> 40) & 0xff);
         }
         int sn = n;
-        int4 sv = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int tn = __shfl_up_sync(0xffffffffu, sn, o);
+            if (lane >= o) sn += tn;
+        }
+        const int excl_n = cn + sn - n;
+        if (rotate) {
+            // v holds the DC sums by phase relative to the sub-sequence (relative block 0 is the block in
+            // flight at its start); the first block STARTED here is block excl_n of the segment
+            const int t0 = kstart != 0 ? 1 : 0;
+            const int rot = ((excl_n - t0) % nblk + nblk) % nblk;
+            int r[4] = {0, 0, 0, 0};
+            const int src[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                if (t < nblk) {
+                    const int p = (t + rot) % nblk;
+                    const int comp = sc->blk_comp[p];
+                    if (comp == 0) r[0] += src[t]; else if (comp == 1) r[1] += src[t]; else if (comp == 2) r[2] += src[t]; else r[3] += src[t];
+                }
+            v = make_int4(r[0], r[1], r[2], r[3]);
+        }
+        int4 sv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
             const int tx = __shfl_up_sync(0xffffffffu, sv.x, o), ty = __shfl_up_sync(0xffffffffu, sv.y, o);
             const int tz = __shfl_up_sync(0xffffffffu, sv.z, o), tw = __shfl_up_sync(0xffffffffu, sv.w, o);
             if (lane >= o) {
-                sn += tn;
                 sv.x += tx;
                 sv.y += ty;
                 sv.z += tz;
@@ -238,7 +269,7 @@ __global__ void __launch_bounds__(K1S_NT) k1s_scan(const K1SParams P) {
             }
         }
         if (i < nsub) {
-            P.s_n[base + i] = cn + sn - n;
+            P.s_n[base + i] = excl_n;
             P.s_dc[base + i] = make_int4(cd.x + sv.x - v.x, cd.y + sv.y - v.y, cd.z + sv.z - v.z, cd.w + sv.w - v.w);
         }
         cn += __shfl_sync(0xffffffffu, sn, 31);
@@ -283,6 +314,12 @@ __global__ void __launch_bounds__(K1S_NT) k1s_write(const K1SParams P) {
     const int nblk = interleaved ? sc->nblk : 1;
     const bool planar = im->layout == ZPX_LAYOUT_PLANAR || !interleaved;
     const uint4* __restrict__ bpack = reinterpret_cast<const uint4*>(sc->blk_pack);
+    if (sc->rotate) {
+        // the phase was left out of the state: block excl_n of the segment has phase excl_n % nblk; a block in
+        // flight at the start is the one before it
+        const int j0 = excl_n;
+        c = k != 0 ? (j0 + nblk - 1) % nblk : j0 % nblk;
+    }
     uint4 bi = bpack[c];
     const ZpxHuffDev* __restrict__ tdc = &P.k1.huff[bi.x];
     const ZpxHuffDev* __restrict__ tac = &P.k1.huff[bi.y];

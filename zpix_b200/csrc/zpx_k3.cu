@@ -60,6 +60,26 @@ struct Bits {
 // coefficient `nat` (natural index) of a block whose rows are stored XOR-swizzled by key
 __device__ __forceinline__ short* cptr(short* blk, int key, int nat) { return blk + (((nat >> 3) ^ key) << 3) + (nat & 7); }
 
+// Refinement passes read the coefficients they refine.  The block is copied to shared memory once
+// (eight 16-byte loads in flight together: one memory latency per block instead of one per
+// coefficient), refined there, and written back.  Layout in shared memory: plain, stored-slot order.
+constexpr int K3_NT = 64;
+__device__ __forceinline__ void block_load(short* sm, const short* blk) {
+    const uint4* g = reinterpret_cast<const uint4*>(blk);
+    uint4* d = reinterpret_cast<uint4*>(sm);
+    uint4 r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = g[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] = r[i];
+}
+__device__ __forceinline__ void block_store(short* blk, const short* sm) {
+    uint4* g = reinterpret_cast<uint4*>(blk);
+    const uint4* d = reinterpret_cast<const uint4*>(sm);
+#pragma unroll
+    for (int i = 0; i < 8; i++) g[i] = d[i];
+}
+
 // refineNonZeroes (decoder.zig:1522-1549)
 __device__ int refine_non_zeroes(Bits& bs, short* blk, int key, const uint8_t* unzig, int zig, int zig_end, int nz, int delta) {
     for (; zig <= zig_end; zig++) {
@@ -78,12 +98,16 @@ __device__ int refine_non_zeroes(Bits& bs, short* blk, int key, const uint8_t* u
 
 }  // namespace
 
-__global__ void __launch_bounds__(64) k3_progressive(const K1Params P, const uint32_t* __restrict__ list, const int n_list) {
+__global__ void __launch_bounds__(K3_NT) k3_progressive(const K1Params P, const uint32_t* __restrict__ list, const int n_list) {
     __shared__ uint8_t s_unzig[64];
+    __shared__ __align__(16) short s_blk[K3_NT / 32][64];  // one block per interval for the refinement passes
     if (threadIdx.x < 64) s_unzig[threadIdx.x] = c_unzig[threadIdx.x];
     __syncthreads();
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n_list) return;
+    // One interval per WARP, decoded by lane 0: the nested, data-dependent loops of spectral selection /
+    // refinement make lanes of one warp diverge completely (32-fold serialisation when every lane carries
+    // its own interval), and the kernel is latency-bound anyway.
+    const int gid = blockIdx.x * (K3_NT / 32) + (threadIdx.x >> 5);
+    if (gid >= n_list || (threadIdx.x & 31) != 0) return;
     const ZpxIntervalDev iv = P.ivs[list[gid]];
     const ZpxScanDev* __restrict__ sc = &P.scans[iv.scan];
     const ZpxImageDev* __restrict__ im = &P.imgs[sc->img];
@@ -119,24 +143,33 @@ __global__ void __launch_bounds__(64) k3_progressive(const K1Params P, const uin
             bx = (int)bxn;
             by = (int)byn;
         }
-        short* blk = reinterpret_cast<short*>(P.coef) + (im->comp_base[comp] + (uint64_t)by * im->comp_bw[comp] + bx) * 64;
+        short* gblk = reinterpret_cast<short*>(P.coef) + (im->comp_base[comp] + (uint64_t)by * im->comp_bw[comp] + bx) * 64;
+        // AC refinement works on a shared-memory copy; every other pass only writes (or ORs one bit)
+        const bool cached = ah != 0 && ss != 0;
+        short* blk = cached ? s_blk[threadIdx.x >> 5] : gblk;
+        if (cached) block_load(blk, gblk);
         const int key = bx & 7;
         const ZpxHuffDev* __restrict__ tdc = &P.huff[sc->blk_dc[c]];
         const ZpxHuffDev* __restrict__ tac = &P.huff[sc->blk_ac[c]];
+        const uint32_t tflags = sc->blk_pack[c][3];  // bit 16: DC table undefined, bit 17: AC table undefined
+        const bool dc_undef = (tflags & 0x10000u) != 0, ac_undef = (tflags & 0x20000u) != 0;
 
         if (ah != 0) {
             // ---- successive-approximation refinement (decoder.zig:1459-1518) ----
             const int delta = 1 << al;
             if (ss == 0) {
                 if (bs.bit()) {
+                    // b[0] |= delta (decoder.zig:1464-1467) as a one-way atomic OR on the 32-bit word that holds
+                    // the coefficient: no read latency on the lane's serial path
                     short* p = cptr(blk, key, 0);
-                    *p = (short)(*p | delta);
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+                    atomicOr(reinterpret_cast<unsigned int*>(a & ~(uintptr_t)3), (unsigned int)(delta & 0xffff) << ((a & 2) ? 16 : 0));
                 }
             } else {
                 int zig = ss;
                 if (eob_run == 0) {
                     while (zig <= se) {
-                        if (!tac->defined) { err = ZPX_E_UninitializedHuffmanTable; break; }
+                        if (ac_undef) { err = ZPX_E_UninitializedHuffmanTable; break; }
                         const int sym = bs.huff(tac);
                         if (sym < 0) { err = ZPX_E_BadHuffmanCode; break; }
                         const int r = sym >> 4, s = sym & 15;
@@ -171,7 +204,7 @@ __global__ void __launch_bounds__(64) k3_progressive(const K1Params P, const uin
             int zig = ss;
             if (zig == 0) {
                 zig++;
-                if (!tdc->defined) { err = ZPX_E_UninitializedHuffmanTable; break; }
+                if (dc_undef) { err = ZPX_E_UninitializedHuffmanTable; break; }
                 const int t = bs.huff(tdc);
                 if (t < 0) { err = ZPX_E_BadHuffmanCode; break; }
                 if (t > 16) { err = ZPX_E_ExcessiveDCComponent; break; }
@@ -184,7 +217,7 @@ __global__ void __launch_bounds__(64) k3_progressive(const K1Params P, const uin
                 eob_run--;
             } else {
                 while (zig <= se) {
-                    if (!tac->defined) { err = ZPX_E_UninitializedHuffmanTable; break; }
+                    if (ac_undef) { err = ZPX_E_UninitializedHuffmanTable; break; }
                     const int sym = bs.huff(tac);
                     if (sym < 0) { err = ZPX_E_BadHuffmanCode; break; }
                     const int r = sym >> 4, s = sym & 15;
@@ -207,6 +240,7 @@ __global__ void __launch_bounds__(64) k3_progressive(const K1Params P, const uin
                 }
             }
         }
+        if (cached) block_store(gblk, blk);
         if (bs.br.overrun()) err = err_eof;
         if (err) break;
 
@@ -229,7 +263,8 @@ __global__ void __launch_bounds__(64) k3_progressive(const K1Params P, const uin
 
 cudaError_t k3_launch_progressive(const K1Params& P, const uint32_t* list, int n_list, cudaStream_t s) {
     if (n_list <= 0) return cudaSuccess;
-    k3_progressive<<<(n_list + 63) / 64, 64, 0, s>>>(P, list, n_list);
+    const int per_cta = K3_NT / 32;
+    k3_progressive<<<(n_list + per_cta - 1) / per_cta, K3_NT, 0, s>>>(P, list, n_list);
     return cudaGetLastError();
 }
 
