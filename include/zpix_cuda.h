@@ -33,6 +33,9 @@
  * host memory for callers that want the fast copy path (optional).
  *
  * Threading: a zpx_ctx is NOT thread-safe; use one per calling thread.
+ * A context owns ONE set of device buffers: zpx_batch_upload makes that batch resident and evicts the
+ * previous one (whose decode / fetch calls then return ZPX_E_BAD_STATE).  Open as many batches as you
+ * like; keep one in the upload..fetch phase per context.
  * Errors: int32_t, 0 = ok.  No C++ exception and no abort crosses this ABI.
  * There is NO CPU fallback: every decode entry point fails with
  * ZPX_E_CUDA / ZPX_E_NO_DEVICE when no CUDA device is usable.

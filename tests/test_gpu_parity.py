@@ -307,6 +307,26 @@ def test_one_call_chunk_pipeline(jpeg, fixtures_dir):
         c.close()
 
 
+def test_one_resident_batch_per_context(jpeg, fixtures_dir):
+    """A context has one set of device buffers: a second upload evicts the first batch (BAD_STATE, never
+    silently wrong pixels)."""
+    c = jpeg.Context()
+    a = jpeg.Batch(c, [_read(fixtures_dir, "video-001.jpeg")])
+    b = jpeg.Batch(c, [_read(fixtures_dir, "video-005.gray.jpeg")])
+    a.upload()
+    a.decode()
+    b.upload()
+    with pytest.raises(jpeg.JpegError) as e:
+        a.fetch_rgba()
+    assert e.value.name == "BadState"
+    b.decode()
+    outs, st = b.fetch_rgba()
+    assert st == [0] and np.array_equal(outs[0], O.decode(_read(fixtures_dir, "video-005.gray.jpeg")).rgbaPixels())
+    a.close()
+    b.close()
+    c.close()
+
+
 def test_empty_batch_and_api_contract(jpeg, ctx):
     outs, st, _ = _gpu_batch(jpeg, ctx, [])
     assert outs == [] and st == []

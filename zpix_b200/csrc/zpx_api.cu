@@ -147,6 +147,7 @@ struct zpx_ctx {
     std::atomic<uint64_t> launches{0};
     int64_t opt_entropy_mode = 0, opt_force_generic = 0, opt_subseq = 0, opt_pipeline_chunk = 0, opt_lanes_per_warp = 0;
     bool busy = false;
+    const zpx_batch* resident = nullptr;  // the batch whose data currently occupies the device buffers
     zpx_ctx* shadow = nullptr;  // second set of device buffers/streams for the chunk pipeline of zpx_decode_batch_rgba
 };
 
@@ -905,6 +906,14 @@ int32_t zpx_batch_upload(zpx_batch* b) {
     if (!b) return ZPX_E_INVALID_ARG;
     zpx_ctx* ctx = b->ctx;
     const int nd = (int)ctx->devs.size();
+    // a context has ONE set of device buffers: uploading a batch evicts the previous one
+    if (ctx->resident && ctx->resident != b) {
+        for (DeviceCtx& dc : ctx->devs) {
+            cudaSetDevice(dc.dev);
+            cudaStreamSynchronize(dc.stream);
+        }
+    }
+    ctx->resident = b;
     // allocate and stage
     for (int di = 0; di < nd; di++) {
         DevicePlan& pl = b->plans[di];
@@ -966,6 +975,7 @@ int32_t zpx_batch_decode(zpx_batch* b, void* stream) {
     zpx_ctx* ctx = b->ctx;
     const int nd = (int)ctx->devs.size();
     if (stream && nd != 1) return ZPX_E_INVALID_ARG;
+    if (b->n > 0 && ctx->resident != b) return ZPX_E_BAD_STATE;  // another batch was uploaded on this context since
     for (int di = 0; di < nd; di++)
         if (!b->plans[di].images.empty() && !b->plans[di].uploaded) return ZPX_E_BAD_STATE;
     b->status_ready = false;
@@ -1008,6 +1018,11 @@ int32_t zpx_batch_fetch_rgba(zpx_batch* b, uint8_t* const* out, const size_t* ou
     if (!b || (b->n > 0 && !out)) return ZPX_E_INVALID_ARG;
     zpx_ctx* ctx = b->ctx;
     const int nd = (int)ctx->devs.size();
+    if (b->n > 0 && ctx->resident != b) {
+        bool any = false;
+        for (int di = 0; di < nd; di++) any = any || !b->plans[di].images.empty();
+        if (any) return ZPX_E_BAD_STATE;  // its results were evicted by a later upload on this context
+    }
     for (int di = 0; di < nd; di++)
         if (!b->plans[di].images.empty() && !b->plans[di].decoded) return ZPX_E_BAD_STATE;
     int e = finalize_status(b);
@@ -1141,6 +1156,7 @@ int32_t zpx_batch_fetch_coefficients(zpx_batch* b, int32_t i, int16_t* out, size
 
 void zpx_batch_close(zpx_batch* b) {
     if (!b) return;
+    if (b->ctx->resident == b) b->ctx->resident = nullptr;
     for (DeviceCtx& dc : b->ctx->devs) {
         cudaSetDevice(dc.dev);
         cudaStreamSynchronize(dc.stream);
