@@ -60,12 +60,6 @@ __device__ __forceinline__ void idct_row(int x0, int x4, int x3, int x7, int x1,
     o[7] = (x7 - x1) >> 8;
 }
 
-#ifdef ZPX_SHIFT_ON_FMA
-__device__ __forceinline__ int sra14(int x) { return __mulhi(x, 1 << 18); }
-#else
-__device__ __forceinline__ int sra14(int x) { return x >> 14; }
-#endif
-
 // Column pass on one column (stride 8 inside b), in place.  idct.zig:149-199.
 __device__ __forceinline__ void idct_col(int* b) {
     int y0 = (b[8 * 0] << 8) + 8192;
@@ -96,16 +90,14 @@ __device__ __forceinline__ void idct_col(int* b) {
     y2 = (R2 * (y4 + y5) + 128) >> 8;
     y4 = (R2 * (y4 - y5) + 128) >> 8;
 
-    // x >> 14 == mulhi(x, 2^18) for every int32 x (floor division): moves these shifts from the ALU pipe
-    // (the kernel's busiest) to the FMA pipe
-    b[8 * 0] = sra14(y7 + y1);
-    b[8 * 1] = sra14(y3 + y2);
-    b[8 * 2] = sra14(y0 + y4);
-    b[8 * 3] = sra14(y8 + y6);
-    b[8 * 4] = sra14(y8 - y6);
-    b[8 * 5] = sra14(y0 - y4);
-    b[8 * 6] = sra14(y3 - y2);
-    b[8 * 7] = sra14(y7 - y1);
+    b[8 * 0] = (y7 + y1) >> 14;
+    b[8 * 1] = (y3 + y2) >> 14;
+    b[8 * 2] = (y0 + y4) >> 14;
+    b[8 * 3] = (y8 + y6) >> 14;
+    b[8 * 4] = (y8 - y6) >> 14;
+    b[8 * 5] = (y0 - y4) >> 14;
+    b[8 * 6] = (y3 - y2) >> 14;
+    b[8 * 7] = (y7 - y1) >> 14;
 }
 
 // pack four int32 to bytes with signed saturation to [-128,127], then +128 (== ^0x80 on each byte)
