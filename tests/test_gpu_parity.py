@@ -286,6 +286,23 @@ def test_native_variant_matches_reference_planes(jpeg, fixtures_dir):
         assert np.array_equal(img.rgbaPixels().reshape(ref.height, ref.width, 4), ref.rgbaPixels())
 
 
+def test_native_cmyk_variant(jpeg, fixtures_dir):
+    """4-component frames come back as Image{.CMYK} holding applyBlack's interleave (decoder.zig:852-901;
+    the YCbCrK branch :811-846 by intent), and rgbaPixels() of it is the GPU's RGBA."""
+    cases = [_read(fixtures_dir, "video-001.cmyk.jpeg"), S.encode(51234, 120, 88, "CMYK"),
+             S.encode(51235, 100, 72, "CMYK", ycck=True)]
+    for data in cases:
+        ref = O.decode(data)
+        img = jpeg.loadFromBuffer(data)
+        assert img.tag == "CMYK" == ref.variant_name
+        m = img.CMYK
+        assert m.stride == ref.stride == 4 * ref.width
+        assert np.array_equal(m.pixels.reshape(ref.height, ref.width, 4), ref.pix.reshape(ref.height, ref.width, 4))
+        assert np.array_equal(img.rgbaPixels().reshape(ref.height, ref.width, 4), ref.rgbaPixels())
+        c = m.at(3, 5)
+        assert c.toRGBA()[0] >> 8 == int(ref.rgbaPixels()[5, 3, 0])
+
+
 def test_one_call_chunk_pipeline(jpeg, fixtures_dir):
     """zpx_decode_batch_rgba cuts large batches into chunks that alternate between two sets of device
     buffers; results and per-image status must not depend on the chunking."""

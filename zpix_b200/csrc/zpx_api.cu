@@ -94,7 +94,7 @@ struct DeviceCtx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr};
-    DevBuf blob, coef, out, planes, desc, status, subs;
+    DevBuf blob, coef, out, planes, desc, status, subs, scratch;
     HostBuf stage, hdesc, hstatus, hflag;
 };
 
@@ -804,6 +804,7 @@ void zpx_ctx_destroy(zpx_ctx* c) {
         d.desc.release();
         d.status.release();
         d.subs.release();
+        d.scratch.release();
         d.hflag.release();
         d.stage.release();
         d.hdesc.release();
@@ -1094,9 +1095,20 @@ int32_t zpx_batch_fetch_native(zpx_batch* b, uint8_t* const* out, int32_t* statu
         zpx_fill_info(p, &info);
         if (p.variant == ZPX_VARIANT_RGBA) {
             CU(ctx, cudaMemcpyAsync(out[i], (const uint8_t*)dc.out.p + im.out_off, info.native_len, cudaMemcpyDeviceToHost, dc.stream));
-        } else if (im.fused || p.variant == ZPX_VARIANT_CMYK) {
-            // planes only exist on the unfused path; CMYK's native interleave is not materialised
+        } else if (im.fused) {
+            // planes only exist on the unfused path (ZPX_OPT_FORCE_GENERIC routes every image there)
             b->status[i] = ZPX_E_UNSUPPORTED_STREAM;
+        } else if (p.variant == ZPX_VARIANT_CMYK) {
+            // Image{.CMYK}: applyBlack's interleave, built from the planes on demand (4-component frames
+            // always take the unfused path)
+            CU(ctx, dc.scratch.ensure(info.native_len));
+            K2GParams kg{};
+            kg.planes = (uint8_t*)dc.planes.p;
+            kg.imgs = (const ZpxImageDev*)((const uint8_t*)dc.desc.p + pl.off_imgs);
+            CU(ctx, k2g_launch_cmyk_native(kg, (uint32_t)b->slot_of[i], (size_t)p.width * p.height, (uint8_t*)dc.scratch.p, dc.stream));
+            ctx->launches++;
+            CU(ctx, cudaMemcpyAsync(out[i], dc.scratch.p, info.native_len, cudaMemcpyDeviceToHost, dc.stream));
+            CU(ctx, cudaStreamSynchronize(dc.stream));  // scratch is reused by the next image
         } else {
             CU(ctx, cudaMemcpyAsync(out[i], (const uint8_t*)dc.planes.p + im.plane_off[0], info.native_len, cudaMemcpyDeviceToHost, dc.stream));
         }

@@ -443,6 +443,44 @@ __global__ void __launch_bounds__(256) k2g_colour(const K2GParams P) {
     reinterpret_cast<uint32_t*>(P.out + im->out_off)[idx] = px;
 }
 
+// The reference's own return value for 4-component frames: Image{.CMYK} whose pixels are what applyBlack
+// leaves (decoder.zig:852-901: 255 - plane, >>1 replication; :811-846 for YCbCrK: RGB of the YCbCr planes
+// in C,M,Y and 255 - black in K).  rgbaPixels() of that image is what k2g_colour writes.
+__global__ void __launch_bounds__(256) k2g_cmyk_native(const K2GParams P, const uint32_t img, uint8_t* __restrict__ dst) {
+    const ZpxImageDev* __restrict__ im = &P.imgs[img];
+    const int W = im->width, Hh = im->height;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)W * Hh) return;
+    const int y = (int)(idx / W), x = (int)(idx - (size_t)y * W);
+    const uint8_t* __restrict__ pl = P.planes;
+    uint32_t px;
+    if (im->mode == ZPX_MODE_CMYK) {
+        px = 0;
+        for (int t = 0; t < 4; t++) {
+            const bool sub = im->h[t] != im->h[0] || im->v[t] != im->v[0];
+            const int sx = sub ? x >> 1 : x, sy = sub ? y >> 1 : y;
+            px |= (255u - pl[im->plane_off[t] + (size_t)sy * im->plane_stride[t] + sx]) << (8 * t);
+        }
+    } else {
+        const int hr = im->h[0] / im->h[1], vr = im->v[0] / im->v[1];
+        const int cx = x / hr, cy = y / vr;
+        const uint8_t Y = pl[im->plane_off[0] + (size_t)y * im->plane_stride[0] + x];
+        const uint8_t Cb = pl[im->plane_off[1] + (size_t)cy * im->plane_stride[1] + cx];
+        const uint8_t Cr = pl[im->plane_off[2] + (size_t)cy * im->plane_stride[2] + cx];
+        int rr, gg, bb;
+        chroma_terms(Cb, Cr, rr, gg, bb);
+        px = ycc_pixel(Y, rr, gg, bb) & 0x00ffffffu;
+        px |= (255u - pl[im->plane_off[3] + (size_t)y * im->plane_stride[3] + x]) << 24;
+    }
+    reinterpret_cast<uint32_t*>(dst)[idx] = px;
+}
+
+cudaError_t k2g_launch_cmyk_native(const K2GParams& P, uint32_t img, size_t pixels, uint8_t* dst, cudaStream_t s) {
+    if (pixels == 0) return cudaSuccess;
+    k2g_cmyk_native<<<(unsigned)((pixels + 255) / 256), 256, 0, s>>>(P, img, dst);
+    return cudaGetLastError();
+}
+
 cudaError_t k2g_launch(const K2GParams& P, int n_list, int max_blocks, size_t max_pixels, cudaStream_t s) {
     if (n_list <= 0) return cudaSuccess;
     dim3 g1((max_blocks + 127) / 128, n_list);

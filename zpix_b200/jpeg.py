@@ -235,12 +235,12 @@ def _native_image(inf: ZpxImageInfo, native: np.ndarray, rgba: np.ndarray) -> _i
         return _image.Image("YCbCr", _image.YCbCrImage(y, cb, cr, inf.y_stride, inf.c_stride, ratio, rect, native), device_rgba=flat)
     if v == "RGBA":
         return _image.Image("RGBA", _image.RGBAImage(native, 4 * inf.width, rect), device_rgba=flat)
-    raise JpegError(105, "CMYK native variant is not materialised; use decodeBatch for RGBA")
+    return _image.Image("CMYK", _image.CMYKImage(native, 4 * inf.width, rect), device_rgba=flat)
 
 
 def loadFromBuffer(buffer: bytes, ctx: Optional[Context] = None) -> _image.Image:
     """src/jpeg/root.zig:10.  Returns the same Image variant the reference returns (.Gray/.YCbCr/.RGBA),
-    with planes computed on the GPU; CMYK frames come back as their rgbaPixels() (.RGBA)."""
+    .CMYK for 4-component frames), planes / interleave computed on the GPU."""
     ctx = ctx or default_context()
     ctx.set_option(2, 1)  # native planes only exist on the unfused path
     try:
@@ -253,8 +253,6 @@ def loadFromBuffer(buffer: bytes, ctx: Optional[Context] = None) -> _image.Image
             outs, st = b.fetch_rgba()
             if st[0] != 0:
                 raise JpegError(st[0])
-            if VARIANTS[inf.variant] == "CMYK":
-                return _rgba_image(inf, outs[0])
             nat, st2 = b.fetch_native()
             if st2[0] != 0:
                 raise JpegError(st2[0])
