@@ -261,6 +261,43 @@ def test_fused_equals_generic(jpeg, fixtures_dir):
     c2.close()
 
 
+def _damaged(data: bytes, seed: int, n_trunc: int, n_flip: int):
+    """Truncations and single-byte damage inside the entropy-coded part of `data`."""
+    rng = np.random.default_rng(seed)
+    first_sos = data.index(b"\xff\xda")
+    out = []
+    for k in rng.integers(first_sos + 14, len(data) - 2, n_trunc):
+        out.append(data[: int(k)])
+    for k in rng.integers(first_sos + 14, len(data) - 2, n_flip):
+        d = bytearray(data)
+        v = int(rng.integers(0, 255))
+        if v == 0xFF or d[int(k)] == 0xFF or d[int(k) - 1] == 0xFF:
+            continue  # keep the marker structure: those cases are the host parser's (test_host)
+        d[int(k)] = v
+        out.append(bytes(d))
+    return out
+
+
+def test_damaged_progressive_streams_match_oracle(jpeg, ctx, fixtures_dir):
+    """Truncated / bit-damaged progressive files: same error name as the oracle (UnexpectedEof,
+    BadHuffmanCode, UnexpectedHuffmanCode, TooManyCoefficients, ...) or, when the damage still decodes,
+    the same pixels.  Exercises the refinement pass's skipped-by-count correction bits on bad input."""
+    datas = []
+    for name, seed in [("video-001.q50.420.progressive.jpeg", 1), ("video-005.gray.q50.progressive.jpeg", 2),
+                       ("video-001.separate.dc.progression.progressive.jpeg", 3)]:
+        datas += _damaged(_read(fixtures_dir, name), seed, 12, 40)
+    datas += _damaged(S.encode(50021, 160, 120, subsampling="4:2:0", progressive=True, restart_rows=1), 4, 6, 20)
+    _assert_same(jpeg, ctx, datas)
+
+
+def test_damaged_baseline_streams_match_oracle(jpeg, ctx, fixtures_dir):
+    datas = []
+    for name, seed in [("video-001.q50.420.jpeg", 5), ("video-001.restart2.jpeg", 6), ("video-005.gray.jpeg", 7),
+                       ("video-001.cmyk.jpeg", 8)]:
+        datas += _damaged(_read(fixtures_dir, name), seed, 10, 30)
+    _assert_same(jpeg, ctx, datas)
+
+
 def test_native_variant_matches_reference_planes(jpeg, fixtures_dir):
     """jpeg.load mirror (N2): .YCbCr / .Gray planes with makeImg's exact strides, on every block whose
     origin is inside bounds (the reference's own `check`, decoder.zig:1803-1836)."""

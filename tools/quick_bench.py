@@ -23,6 +23,7 @@ ap.add_argument("--generic", type=int, default=0)
 ap.add_argument("--emode", type=int, default=0)
 ap.add_argument("--subb", type=int, default=0)
 ap.add_argument("--lpw", type=int, default=0)
+ap.add_argument("--prog", type=int, default=0)
 a = ap.parse_args()
 
 print("cpus", os.cpu_count())
@@ -32,6 +33,8 @@ if a.mode == "YCbCr":
     kw["subsampling"] = a.sub
 if a.dri:
     kw["restart_rows"] = a.dri
+if a.prog:
+    kw["progressive"] = True
 base = S.make_batch(2, a.distinct, a.w, a.h, cache_dir="/tmp/zpx_synth", **kw)
 datas = [base[i % a.distinct] for i in range(a.n)]
 print(f"synth {a.distinct} images in {time.time()-t:.1f}s, avg {sum(map(len, base))/len(base):.0f} B")

@@ -116,7 +116,7 @@ struct DevicePlan {
     std::vector<ZpxQuantDev> quant;
     std::vector<FusedGroup> groups;
     std::vector<ZpxIntervalDev> ivs_prog;            // intervals of progressive scans (appended after the sequential ones)
-    std::vector<std::vector<uint32_t>> prog_lists;   // per scan ordinal: indices (into the final interval array)
+    std::vector<std::vector<uint32_t>> prog_lists;   // per dependency level: indices (into the final interval array)
     std::vector<size_t> prog_off;                    // byte offsets of those lists in the descriptor buffer
     std::vector<std::pair<uint64_t, uint64_t>> prog_zero;  // (first block, blocks) of progressive images: zeroed before the scans
     size_t n_seq = 0;                                // sequential intervals = ivs[0, n_seq)
@@ -382,6 +382,21 @@ void build_plan(zpx_batch* b, int di) {
             g.bytes += nblocks * 128 + (uint64_t)4 * p.width * p.height;
         }
         // scans and intervals
+        // Progressive scans are launched by dependency level, not by ordinal: a scan has to wait only for
+        // earlier scans that touch the same coefficients (a common component and overlapping spectral
+        // bands), e.g. libjpeg's 10-scan script needs 3 launches instead of 10.
+        std::vector<int> level(p.scans.size(), 0);
+        if (p.progressive) {
+            for (size_t a = 0; a < p.scans.size(); a++) {
+                for (size_t t = 0; t < a; t++) {
+                    const ZpxScanHost &x = p.scans[a], &y = p.scans[t];
+                    bool share = false;
+                    for (int i = 0; i < x.ncomp; i++)
+                        for (int j = 0; j < y.ncomp; j++) share = share || x.comp[i] == y.comp[j];
+                    if (share && x.ss <= y.se && y.ss <= x.se) level[a] = std::max(level[a], level[t] + 1);
+                }
+            }
+        }
         int scan_index = 0;
         for (const ZpxScanHost& s : p.scans) {
             ZpxScanDev sd;
@@ -464,8 +479,9 @@ void build_plan(zpx_batch* b, int di) {
                 }
                 d.sub_first = d.nsub = d.sub_bytes = d.pad0 = 0;
                 if (p.progressive) {
-                    if (pl.prog_lists.size() <= (size_t)sd.scan_index) pl.prog_lists.resize(sd.scan_index + 1);
-                    pl.prog_lists[sd.scan_index].push_back((uint32_t)pl.ivs_prog.size());  // fixed up below
+                    const size_t lv = (size_t)level[sd.scan_index];
+                    if (pl.prog_lists.size() <= lv) pl.prog_lists.resize(lv + 1);
+                    pl.prog_lists[lv].push_back((uint32_t)pl.ivs_prog.size());  // fixed up below
                     pl.ivs_prog.push_back(d);
                 } else {
                     pl.ivs.push_back(d);
@@ -477,6 +493,9 @@ void build_plan(zpx_batch* b, int di) {
     }
     // progressive intervals go after the sequential ones
     pl.n_seq = pl.ivs.size();
+    // longest scans first: a launch is as long as its slowest warp, so the big ones must not start last
+    for (auto& l : pl.prog_lists)
+        std::stable_sort(l.begin(), l.end(), [&](uint32_t a, uint32_t b) { return pl.ivs_prog[a].len > pl.ivs_prog[b].len; });
     for (auto& l : pl.prog_lists)
         for (uint32_t& ix : l) ix += (uint32_t)pl.n_seq;
     pl.ivs.insert(pl.ivs.end(), pl.ivs_prog.begin(), pl.ivs_prog.end());
