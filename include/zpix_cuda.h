@@ -106,7 +106,10 @@ extern "C" {
 #define ZPX_E_INVALID_ARG 102
 #define ZPX_E_BAD_STATE 103     /* calls made in the wrong order for this batch */
 #define ZPX_E_COEF_RANGE 104    /* a coefficient does not fit int16 (non-conforming 8-bit stream) */
-#define ZPX_E_UNSUPPORTED_STREAM 105 /* stream shape this build does not decode on the GPU yet; see zpx_error_name */
+#define ZPX_E_UNSUPPORTED_STREAM 105 /* stream shape this build does not decode on the GPU: an End-Of-Band run
+                                        in a self-synchronising sequential scan, or one left open across a scan
+                                        boundary (the reference's eob_run survives scans, decoder.zig:144/:1451);
+                                        both only occur in corrupt files */
 #define ZPX_E_MALFORMED_TABLE 106    /* DHT on which the reference itself panics (over-subscribed code) */
 
 /* ---- image variants jpeg.load returns (src/image/image.zig:24-33) ------- */

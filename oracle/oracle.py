@@ -36,6 +36,8 @@ class _ZoImage(C.Structure):
         ("c_stride", C.c_size_t),
         ("subsample_ratio", C.c_int32),
         ("ycck_intent", C.c_int32),
+        ("eob_carry", C.c_int32),
+        ("pad0", C.c_int32),
     ]
 
 
@@ -81,6 +83,8 @@ def lib():
         L.zo_decode_config.restype = C.c_int
         L.zo_rgba_pixels.argtypes = [C.POINTER(_ZoImage), C.c_void_p]
         L.zo_rgba_pixels.restype = None
+        L.zo_last_eob_carry.argtypes = []
+        L.zo_last_eob_carry.restype = C.c_int
         L.zo_free.argtypes = [C.POINTER(_ZoImage)]
         L.zo_free.restype = None
         L.zo_error_name.argtypes = [C.c_int]
@@ -112,6 +116,7 @@ class Image:
         self.variant_name = VARIANT_NAMES[raw.variant]
         self.width, self.height = raw.width, raw.height
         self.ycck_intent = bool(raw.ycck_intent)
+        self.eob_carry = bool(raw.eob_carry)
         self.subsample_ratio = RATIO_NAMES.get(raw.subsample_ratio) if raw.variant == YCBCR else None
         L = lib()
         rgba = np.empty((raw.height, raw.width, 4), dtype=np.uint8)
@@ -142,6 +147,11 @@ class Image:
     def rgbaPixels(self) -> np.ndarray:
         """Image.rgbaPixels (image.zig:103): tight H x W x 4 uint8."""
         return self._rgba
+
+
+def last_eob_carry() -> bool:
+    """True if the latest decode() met a scan that started inside an End-Of-Band run (also when it raised)."""
+    return bool(lib().zo_last_eob_carry())
 
 
 def decode(data: bytes, tap: bool = False):

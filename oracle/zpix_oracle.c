@@ -86,6 +86,7 @@ typedef struct {
     int jfif, adobe_transform_valid;
     int adobe_transform; /* 0 unknown, 1 y_cb_cr, 2 y_cb_cr_k */
     uint16_t eob_run;
+    int eob_carry; /* test aid: a scan started with eob_run != 0 (left open by the previous scan) */
 
     component comp[MAX_COMPONENTS];
     int32_t (*prog_coef[MAX_COMPONENTS])[BLOCK_SIZE];
@@ -903,6 +904,9 @@ static int process_sos(decoder *d, int32_t n) {
     int32_t dc[MAX_COMPONENTS] = {0, 0, 0, 0};
     int32_t b[BLOCK_SIZE];
 
+    /* eob_run is a decoder field that only RSTn resets (decoder.zig:144, :1451): a run left open by the
+     * previous scan is still counted down here.  Recorded for the tests (the GPU path refuses such files). */
+    if (d->eob_run != 0) d->eob_carry = 1;
     for (int32_t my = 0; my < myy; my++) {
         for (int32_t mx = 0; mx < mxx; mx++) {
             for (int k = 0; k < n_comp; k++) {
@@ -1225,6 +1229,10 @@ static void free_decoder(decoder *d) {
     free(d);
 }
 
+/* test aid (not thread-safe): eob_carry of the latest zo_decode / zo_decode_tap, also when it failed */
+static int g_last_eob_carry = 0;
+int zo_last_eob_carry(void) { return g_last_eob_carry; }
+
 int zo_decode_tap(const uint8_t *data, size_t len, zo_image *out, zo_tap *tap) {
     decoder *d = new_decoder(data, len);
     if (!d) return ZO_OutOfMemory;
@@ -1233,6 +1241,8 @@ int zo_decode_tap(const uint8_t *data, size_t len, zo_image *out, zo_tap *tap) {
     memset(out, 0, sizeof(*out));
     int e = decode_inner(d, 0, out);
     if (e != ZO_OK) memset(out, 0, sizeof(*out));
+    else out->eob_carry = d->eob_carry;
+    g_last_eob_carry = d->eob_carry;
     free_decoder(d);
     return e;
 }

@@ -99,7 +99,14 @@ typedef struct zo_image {
     int32_t subsample_ratio; /* ZO_R4xx, only for ZO_YCBCR */
     int32_t ycck_intent;     /* 1 if produced by the YCbCrK branch whose reference code is broken
                                 (SURVEY.md B2): output follows Go's image/jpeg, parity unpinned */
+    int32_t eob_carry;       /* 1 if some scan started inside an End-Of-Band run the previous scan left open
+                                (corrupt streams only; the GPU path answers UnsupportedStream for them) */
+    int32_t pad0;
 } zo_image;
+
+/* eob_carry of the latest zo_decode / zo_decode_tap in this process, also when that call failed
+ * (test aid, not thread-safe) */
+int zo_last_eob_carry(void);
 
 /* Optional coefficient tap, used by the tests of the entropy kernels.
  * Sequential frames: one record per coded block, in the order processSos

@@ -45,9 +45,14 @@ def _read(d, name):
 
 def _oracle_rgba(data):
     try:
-        return O.decode(data).rgbaPixels(), "ok"
+        img = O.decode(data)
     except O.OracleError as e:
-        return None, e.name
+        return None, ("UnsupportedStream" if O.last_eob_carry() else e.name)
+    if img.eob_carry:
+        # corrupt stream whose End-Of-Band run crosses a scan boundary: the reference decodes garbage from
+        # there on, the GPU path refuses the image (deviations)
+        return None, "UnsupportedStream"
+    return img.rgbaPixels(), "ok"
 
 
 def _gpu_batch(jpeg, ctx, datas):

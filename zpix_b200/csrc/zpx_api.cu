@@ -461,6 +461,8 @@ void build_plan(zpx_batch* b, int di) {
                 d.n_mcu = iv.n_mcu;
                 d.ordinal = ord++;
                 d.flags = iv.eof_limit ? 1u : 0u;
+                // bit 1: last interval of a scan that another scan follows (End-Of-Band run carry check)
+                if (&iv == &s.intervals.back() && &s != &p.scans.back()) d.flags |= 2u;
                 if (s.ncomp > 1) {
                     d.first_block = iv.first_mcu * (uint32_t)nb;
                     d.n_blocks = iv.n_mcu * (uint32_t)nb;

@@ -112,6 +112,7 @@ struct ZpxIntervalDev {
     uint32_t n_mcu;      // MCU iterations in this interval
     uint32_t ordinal;    // interval index inside the scan (error ordering)
     uint32_t flags;      // bit0: limit is the end of the file (UnexpectedEof instead of MissingFF00)
+                         // bit1: last interval of a scan that is not the image's last scan
     uint32_t first_block;  // ordinal (inside the scan) of the interval's first coded block
     uint32_t n_blocks;     // coded blocks in this interval
     // self-synchronising mode: the interval is cut into nsub sub-sequences of sub_bytes raw bytes,

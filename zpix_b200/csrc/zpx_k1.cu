@@ -355,6 +355,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 if (br.overrun()) err = (iv.flags & 1) ? ZPX_E_UnexpectedEof : ZPX_E_MissingFF00;
                 report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + (iv.n_blocks - left), err);
                 left = 0;
+                eob_run = 0;
             } else {
                 // hand the block to HBM: slot s of the 128-byte line holds row s ^ key
                 uint32_t bx;
@@ -402,6 +403,11 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
             }
         }
     }
+    // The reference keeps its End-Of-Band run across scans (decoder.zig:144, reset only at RSTn :1451); here
+    // every scan starts from zero, so a run that is still open when a scan ends (corrupt streams only) would
+    // make the next scan differ: refuse the image instead.
+    if (live && (iv.flags & 2u) && eob_run != 0)
+        report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + iv.n_blocks, ZPX_E_UNSUPPORTED_STREAM);
 }
 
 // LPW = lanes of each warp that carry an interval.  The kernel is bound by the latency of a warp's

@@ -590,6 +590,11 @@ __global__ void __launch_bounds__(K3_NT) k3_progressive(const K1Params P, const 
     }
     if (acref && !err && bn) store_batch();
     if (err && lane == 0) report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + j, err);
+    // The reference keeps its End-Of-Band run across scans (decoder.zig:144, reset only at RSTn :1451); here
+    // every scan starts from zero (scans of one level run side by side), so a run that is still open when a
+    // scan ends (corrupt streams only) would make the next scan differ: refuse the image instead.
+    if (!err && lane == 0 && (iv.flags & 2u) && eob_run != 0)
+        report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + iv.n_blocks, ZPX_E_UNSUPPORTED_STREAM);
 }
 
 cudaError_t k3_launch_progressive(const K1Params& P, const uint32_t* list, int n_list, cudaStream_t s) {
