@@ -146,6 +146,7 @@ struct zpx_ctx {
     std::string last_cuda_str;
     std::atomic<uint64_t> launches{0};
     int64_t opt_entropy_mode = 0, opt_force_generic = 0, opt_subseq = 0, opt_pipeline_chunk = 0, opt_lanes_per_warp = 0;
+    int64_t opt_pipeline_ramp = 1;
     bool busy = false;
     const zpx_batch* resident = nullptr;  // the batch whose data currently occupies the device buffers
     zpx_ctx* shadow = nullptr;  // second set of device buffers/streams for the chunk pipeline of zpx_decode_batch_rgba
@@ -849,6 +850,7 @@ int32_t zpx_ctx_set_option(zpx_ctx* c, int32_t option, int64_t value) {
         case ZPX_OPT_FORCE_GENERIC: c->opt_force_generic = value; return ZPX_OK;
         case ZPX_OPT_SUBSEQ_BYTES: c->opt_subseq = value; return ZPX_OK;
         case ZPX_OPT_PIPELINE_CHUNK: c->opt_pipeline_chunk = value; return ZPX_OK;
+        case ZPX_OPT_PIPELINE_RAMP: c->opt_pipeline_ramp = value; return ZPX_OK;
         case ZPX_OPT_LANES_PER_WARP: c->opt_lanes_per_warp = value; return ZPX_OK;
     }
     return ZPX_E_INVALID_ARG;
@@ -1228,7 +1230,18 @@ int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const si
     ctx->shadow->opt_force_generic = ctx->opt_force_generic;
     ctx->shadow->opt_subseq = ctx->opt_subseq;
     ctx->shadow->opt_lanes_per_warp = ctx->opt_lanes_per_warp;
-    const int32_t n_chunks = (n + chunk - 1) / chunk;
+    // chunk list: the first two chunks are a quarter and a half of the regular size, so that the first
+    // device->host copy starts early (the pipeline is bound by that copy; its fill time is pure loss)
+    std::vector<std::pair<int32_t, int32_t>> chunks;
+    for (int32_t i0 = 0; i0 < n;) {
+        int32_t cnt = chunk;
+        if (ctx->opt_pipeline_ramp && chunks.size() == 0) cnt = std::max(1, chunk / 4);
+        else if (ctx->opt_pipeline_ramp && chunks.size() == 1) cnt = std::max(1, chunk / 2);
+        cnt = std::min(cnt, n - i0);
+        chunks.push_back({i0, cnt});
+        i0 += cnt;
+    }
+    const int32_t n_chunks = (int32_t)chunks.size();
     std::atomic<int32_t> next(0);
     int32_t rc[2] = {0, 0};
     std::vector<int32_t> st(status ? 0 : n);
@@ -1238,7 +1251,7 @@ int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const si
         for (;;) {
             const int32_t k = next.fetch_add(1);
             if (k >= n_chunks) break;
-            const int32_t i0 = k * chunk, cnt = std::min(chunk, n - i0);
+            const int32_t i0 = chunks[k].first, cnt = chunks[k].second;
             const int e = decode_range_rgba(c, bufs + i0, lens + i0, cnt, out + i0, out_stride ? out_stride + i0 : nullptr, stp + i0);
             if (e) {
                 rc[w] = e;

@@ -1,5 +1,5 @@
-// zpx_entropy.cuh -- device code shared by the entropy kernels (zpx_k1.cu, zpx_k1s.cu):
-// stuffed-stream bit reader, Huffman symbol decode, RECEIVE/EXTEND, per-lane block buffer.
+// zpx_entropy.cuh -- device code shared by the entropy kernels (zpx_k1.cu, zpx_k1s.cu, zpx_k3.cu):
+// stuffed-stream bit reader with position tracking, Huffman symbol decode, RECEIVE/EXTEND, error report.
 // Reference semantics: src/jpeg/decoder.zig:712-749 (readByteStuffedByte), :909-1022
 // (decodeHuffman, ensureNBits, decodeBit(s)), :1115-1134 (receiveExtend).
 #pragma once
@@ -210,135 +210,5 @@ __device__ __forceinline__ void report(unsigned long long* status, uint32_t img_
         ((unsigned long long)(uint32_t)scan_index << 48) | ((ordinal & 0xffffffffffull) << 8) | (unsigned)code;
     atomicMin(&status[img_slot], key);
 }
-
-// ---------------------------------------------------------------------------
-// One Huffman symbol of a sequential scan, DC or AC alike (decoder.zig:1363-1411): the table, the
-// run/size split and the destination index are selects, so lanes that sit at different symbols of
-// different blocks share one instruction stream.
-//   k        in/out: 0 = the next symbol is the block's DC, 1..63 = next AC zig-zag index
-//   kk       out: zig-zag index the value goes to (valid when store)
-//   SPEC     speculative decode (self-synchronising passes): an invalid code advances one bit and
-//            nothing is an error; DC sums accumulate in dc0..dc3 exactly like the predictors
-// Returns an error code (0 = none); the caller checks br.overrun() to tell MissingFF00 apart.
-// ---------------------------------------------------------------------------
-struct SymOut {
-    int kk, v;
-    bool store, done;
-};
-
-template <bool SPEC>
-__device__ __forceinline__ int symbol_step(BitReader& br, const ZpxHuffDev* __restrict__ tdc,
-                                           const ZpxHuffDev* __restrict__ tac, uint32_t flags, int comp, int& k,
-                                           uint32_t& eob_run, int& dc0, int& dc1, int& dc2, int& dc3, SymOut& o) {
-    int err = 0;
-    br.fill();
-    const uint32_t hi = br.peek32();
-    const bool isdc = k == 0;
-    const ZpxHuffDev* __restrict__ tab = isdc ? tdc : tac;
-    const uint32_t e = __ldg(&tab->lut[hi >> (32 - ZPX_LUT_BITS)]);
-    int len = (int)(e & 0xffu);
-    uint32_t sym = e >> 8;
-    if (len == 0) {  // code longer than the first-level table (about 1 % of the symbols)
-        const uint32_t v16 = hi >> 16;
-#pragma unroll 1
-        for (int l = ZPX_LUT_BITS + 1; l <= 16 && len == 0; l++) {
-            if (v16 < __ldg(&tab->limit[l])) {
-                sym = __ldg(&tab->vals[(__ldg(&tab->valoff[l]) + (int)(v16 >> (16 - l))) & 0xff]);
-                len = l;
-            }
-        }
-        if (len == 0) {
-            if (SPEC) {  // stay in the same state, one bit further
-                br.consume(1);
-                o.store = false;
-                o.done = false;
-                o.kk = 0;
-                o.v = 0;
-                return 0;
-            }
-            len = 16;  // the reference reads 16 bits, then BadHuffmanCode (decoder.zig:947-969)
-            sym = 0;
-            err = ZPX_E_BadHuffmanCode;
-        }
-    }
-    if (!SPEC && (flags & (isdc ? 0x10000u : 0x20000u))) err = ZPX_E_UninitializedHuffmanTable;
-    int size = isdc ? (int)sym : (int)(sym & 15u);
-    const int run = isdc ? 0 : (int)(sym >> 4);
-    if (size > 16) {  // DC category > 16 (decoder.zig:1370)
-        size = 0;
-        if (!SPEC && !err) err = ZPX_E_ExcessiveDCComponent;
-    }
-    int v = receive_extend(br.buf, len, size);
-    int tot = len + size;
-    bool done = false, store = true;
-    int kk = k + run;
-    if (isdc) {
-        // decoder.zig:1366-1376
-        int dc = comp == 0 ? dc0 : comp == 1 ? dc1 : comp == 2 ? dc2 : dc3;
-        dc += v;
-        if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
-        v = dc;
-        kk = 0;
-        k = 1;
-        if (!SPEC && (dc < -32768 || dc > 32767) && !err) err = ZPX_E_COEF_RANGE;
-        if (!SPEC && eob_run > 0) {  // decoder.zig:1379-1380 (End-Of-Band run)
-            eob_run--;
-            done = true;
-        }
-    } else if (size == 0) {
-        store = false;
-        if (run == 15) {  // ZRL
-            k += 16;
-            done = k > 63;
-        } else {          // EOB / EOB run (decoder.zig:1399-1407)
-            eob_run = 1u << run;
-            if (run != 0) eob_run |= (uint32_t)((br.buf << len) >> (64 - run));
-            eob_run = (eob_run - 1) & 0xffffu;
-            tot = len + run;
-            done = true;
-        }
-    } else if (kk > 63) {  // decoder.zig:1393-1395: the value bits stay unread
-        tot = len;
-        store = false;
-        done = true;
-    } else {
-        k = kk + 1;
-        done = k > 63;
-    }
-    br.consume(tot);
-    o.kk = kk;
-    o.v = v;
-    o.store = store;
-    o.done = done;
-    return err;
-}
-
-// ---------------------------------------------------------------------------
-// per-lane block buffer in shared memory: [8 rows][NT lanes] x 16 bytes, so a warp's
-// row loads/stores are contiguous and the scattered int16 stores spread over banks
-// ---------------------------------------------------------------------------
-template <int NT>
-struct LaneBlock {
-    uint4* base;  // this lane's row 0
-    __device__ __forceinline__ void put(int nat, int v) {
-        // natural index -> row (nat>>3), element (nat&7)
-        short* p = reinterpret_cast<short*>(base + (nat >> 3) * NT) + (nat & 7);
-        *p = (short)v;
-    }
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int r = 0; r < 8; r++) base[r * NT] = make_uint4(0, 0, 0, 0);
-    }
-    // write the block to HBM with its rows XOR-swizzled by key, and clear it
-    __device__ __forceinline__ void flush(uint4* dst, int key) {
-#pragma unroll
-        for (int slot = 0; slot < 8; slot++) {  // slot s of the block holds row s ^ key
-            uint4* src = base + (slot ^ key) * NT;
-            dst[slot] = *src;
-            *src = make_uint4(0, 0, 0, 0);
-        }
-    }
-};
-
 
 }  // namespace zpx

@@ -86,6 +86,27 @@ struct FastReader {
         skip = 0;
         feed_slow();  // the first word may start before `first`
     }
+    // start at raw bit position `bitpos`, counted from (start & ~3) like the positions of zpx_k1s.cu; it lies in a
+    // data byte (never in the 0x00 of an FF 00 pair) or at / past the limit (everything reads as padding)
+    __device__ __forceinline__ void init_bits(const uint8_t* blob, uint64_t start, uint32_t len, uint32_t bitpos) {
+        const uint64_t a = start & ~(uint64_t)3;
+        const uint32_t lim = (uint32_t)(start - a) + len;
+        const uint32_t byte = min(bitpos >> 3, lim);
+        const uint32_t wofs = byte & ~3u;
+        base = reinterpret_cast<const uint32_t*>(blob + a + wofs);
+        first = byte - wofs;
+        end = lim - wofs;
+        off = 0;
+        nw = __ldg(base);
+        buf = 0;
+        cnt = 0;
+        pad = 0;
+        skip = 0;
+        feed_slow();
+        const int b = (bitpos >> 3) < lim ? (int)(bitpos & 7u) : 0;
+        buf <<= b;
+        cnt -= b;
+    }
     __device__ __forceinline__ bool overrun() const { return cnt < pad; }
 
     // make sure more than 32 bits are buffered
@@ -246,15 +267,34 @@ __device__ __forceinline__ uint32_t k1_rare(const K1Params& P, const FastReader&
 // Lanes of a warp sit at the same block phase of the MCU (all on luma or all on chroma), so the number
 // of AC iterations is close to the lanes' own symbol counts, and the block-end code runs once per
 // block for all lanes instead of once per symbol for a few.
-template <int NT, bool SMEM>
-__device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxIntervalDev& iv, const bool live, const uint32_t sb,
+// Where a lane starts inside its interval.  One lane per interval: the interval's first bit, block 0, all of its
+// blocks.  Self-synchronising mode (SUB, zpx_k1s.cu): the true decoder state at the start of the lane's
+// sub-sequence -- possibly inside a block, whose tail the lane skips because it belongs to the previous lane --
+// and the number of blocks that start inside the sub-sequence, both known from the synchronisation passes.
+struct K1Start {
+    uint32_t bitpos;  // raw bit position, counted from (iv.start & ~3)
+    int k;            // 0: at a block start; 1..63: inside a block, next zig-zag index k
+    int dc0, dc1, dc2, dc3;  // DC predictors at that point
+    uint32_t j0;      // ordinal (inside the interval) of the first block this lane writes
+    uint32_t count;   // blocks this lane writes
+};
+
+template <int NT, bool SMEM, bool SUB>
+__device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxIntervalDev& iv, const K1Start& st, const uint32_t sb,
                                              const uint32_t su, const uint32_t sdesc /* smem: this lane's scan's blk table */,
                                              const uint32_t slut /* smem: LUT slots base */) {
     const ZpxScanDev* __restrict__ sc = &P.scans[iv.scan];
     const ZpxImageDev* __restrict__ im = &P.imgs[sc->img];
 
     FastReader br;
-    br.init(P.blob, iv.start, iv.len);
+    if (st.count != 0) {
+        br.init_bits(P.blob, iv.start, iv.len, st.bitpos);
+    } else {  // idle lane: never reads
+        br.base = reinterpret_cast<const uint32_t*>(P.blob);
+        br.off = br.first = br.end = br.nw = br.skip = 0;
+        br.buf = 0;
+        br.cnt = br.pad = 0;
+    }
 
     const bool interleaved = sc->interleaved != 0;
     const int nblk = interleaved ? sc->nblk : 1;
@@ -265,29 +305,42 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     const uint64_t coef_base = im->coef_base;
     const uint32_t bpm = (uint32_t)im->bpm;
 
+    // position of block j0
     uint32_t mcu = iv.first_mcu, mx = 0, my = 0, bxn = 0, byn = 0;
+    int c = 0;
     if (interleaved) {
+        if (SUB) {
+            mcu += st.j0 / (uint32_t)nblk;
+            c = (int)(st.j0 % (uint32_t)nblk);
+        }
         mx = mcu % mxx;
         my = mcu / mxx;
     } else {  // n-th coded block of the component, row-major over the blocks that intersect the image
-        byn = iv.first_block / cw;
-        bxn = iv.first_block - byn * cw;
+        const uint32_t o = iv.first_block + (SUB ? st.j0 : 0u);
+        byn = o / cw;
+        bxn = o - byn * cw;
     }
-    int c = 0;
+    // SUB: a lane that starts inside a block first runs that block's remaining AC symbols without storing
+    // anything (phase: the one before block j0's)
+    bool tail = SUB && st.k != 0 && st.count != 0;
+    const int c_first = c;
+    if (tail) c = c == 0 ? nblk - 1 : c - 1;
     // bi: x = DC table (SMEM: shared address of its LUT slot; else table index), y = AC likewise,
     //     z = comp | hx << 8 | vy << 16 | slot << 24, w = h | v << 8 | undefined-table flags
-    uint4 bi = SMEM ? lds_u128(sdesc) : bpack[0];
+    uint4 bi = SMEM ? lds_u128(sdesc + c * 16) : bpack[c];
     const uint32_t* __restrict__ gdc = SMEM ? nullptr : P.huff[bi.x].fast;
     const uint32_t* __restrict__ gac = SMEM ? nullptr : P.huff[bi.y].fast;
 
-    int dc0 = 0, dc1 = 0, dc2 = 0, dc3 = 0;
+    int dc0 = st.dc0, dc1 = st.dc1, dc2 = st.dc2, dc3 = st.dc3;
     uint32_t eob_run = 0;
-    uint32_t left = live ? iv.n_blocks : 0;  // blocks still to decode (including the current one)
+    uint32_t left = st.count;  // blocks still to decode (including the current one)
 
     while (__any_sync(0xffffffffu, left != 0)) {
         int k = 64;  // > 63: no block in flight on this lane
         int err = 0;
-        if (left != 0) {
+        if (SUB && tail) {
+            k = st.k;
+        } else if (left != 0) {
             // ---- DC (decoder.zig:1366-1376) ----
             br.feed();
             const uint32_t hi = (uint32_t)(br.buf >> 32);
@@ -327,7 +380,15 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 uint32_t e;
                 if (SMEM) e = lds_u32(bi.y + ((hi >> (32 - K1_SLB)) << 2));
                 else e = __ldg(gac + (hi >> (32 - ZPX_LUT_BITS)));
-                if ((int)e <= 0) e = k1_rare<SMEM>(P, br, hi, false, e, bi.y, gac, slut, eob_run, err);
+                if ((int)e <= 0) {
+                    e = k1_rare<SMEM>(P, br, hi, false, e, bi.y, gac, slut, eob_run, err);
+                    // End-Of-Band RUN inside a sequential scan: the synchronisation passes do not
+                    // model that state
+                    if (SUB && eob_run != 0) {
+                        eob_run = 0;
+                        if (!err) err = ZPX_E_UNSUPPORTED_STREAM;
+                    }
+                }
                 const int len = (int)((e >> 8) & 31u), size = (int)((e >> 13) & 31u);
                 int tot = (int)(e & 63u);
                 const int adv = (int)((e >> 18) & 127u);
@@ -335,7 +396,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 int v = (int)((t >> 1) >> (31 - size));
                 v += (~((int)t >> 31)) & (1 - (1 << size));  // first bit 0 -> negative
                 const int kk = k + adv - 1;                    // zig-zag index the value goes to
-                bool store = size != 0;
+                bool store = size != 0 && !(SUB && tail);
                 if (kk > 63) {  // decoder.zig:1393-1395: run past the block end, the value bits stay unread
                     tot = len;
                     store = false;
@@ -348,12 +409,23 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
             }
         }
         // ---- block end ----
-        if (left != 0) {
+        if (SUB && tail) {
+            // end of the skipped tail (its errors are the previous lane's to report): block j0 comes next
+            tail = false;
+            c = c_first;
+            if (SMEM) {
+                bi = lds_u128(sdesc + c * 16);
+            } else {
+                bi = bpack[c];
+                gdc = P.huff[bi.x].fast;
+                gac = P.huff[bi.y].fast;
+            }
+        } else if (left != 0) {
             if (err || br.overrun()) {
                 // a symbol that needed bits past the limit is the reference's MissingFF00 / UnexpectedEof,
                 // whatever the garbage decoded to
                 if (br.overrun()) err = (iv.flags & 1) ? ZPX_E_UnexpectedEof : ZPX_E_MissingFF00;
-                report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + (iv.n_blocks - left), err);
+                report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + st.j0 + (st.count - left), err);
                 left = 0;
                 eob_run = 0;
             } else {
@@ -406,15 +478,15 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     // The reference keeps its End-Of-Band run across scans (decoder.zig:144, reset only at RSTn :1451); here
     // every scan starts from zero, so a run that is still open when a scan ends (corrupt streams only) would
     // make the next scan differ: refuse the image instead.
-    if (live && (iv.flags & 2u) && eob_run != 0)
+    if (!SUB && st.count != 0 && (iv.flags & 2u) && eob_run != 0)
         report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + iv.n_blocks, ZPX_E_UNSUPPORTED_STREAM);
 }
 
-// LPW = lanes of each warp that carry an interval.  The kernel is bound by the latency of a warp's
-// serial step, not by issue slots; with LPW = 16 a warp has half the divergent work per step (fewer
-// block ends, refills and cache misses to wait for) and twice as many warps fill the idle issue slots.
-template <int NT, int LPW>
-__global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
+// One CTA: NT lanes, each with an interval and a start inside it (K1Start).  Collects the distinct scans and
+// Huffman tables of the CTA's lanes, stages their first-level LUTs and block descriptors in shared memory and
+// runs the block-synchronous loop.
+template <int NT, bool SUB>
+__device__ __forceinline__ void k1_cta_run(const K1Params& P, const ZpxIntervalDev& iv, const K1Start& st) {
     __shared__ uint4 sblk[8 * NT];   // per-lane block: [8 rows][NT lanes] x 16 bytes
     // zig-zag index -> byte offset of that coefficient inside the lane's block (row * NT*16 + column * 2);
     // lane-divergent index: shared, not constant, memory (padded: k + run <= 78)
@@ -426,15 +498,11 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
     __shared__ int s_nscan, s_ntab, s_ok;
 
     const int tid = threadIdx.x;
-    const int gid = (blockIdx.x * (NT / 32) + (tid >> 5)) * LPW + (tid & 31);
     for (int r = 0; r < 8; r++) sblk[r * NT + tid] = make_uint4(0, 0, 0, 0);
     if (tid < 80) {
         const int nat = tid < 64 ? c_unzig[tid] : 63;
         s_unzig[tid] = (uint16_t)((nat >> 3) * (NT * 16) + (nat & 7) * 2);
     }
-    // lanes past the end of the interval list (or beyond LPW) idle through the loop (its head is a warp vote)
-    const bool live = gid < P.n_iv && (tid & 31) < LPW;
-    const ZpxIntervalDev iv = P.ivs[live ? gid : P.n_iv - 1];
     s_lane_scan[tid] = iv.scan;
     __syncthreads();
 
@@ -500,8 +568,58 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
     asm volatile("mov.u32 %0, %0;" : "+r"(sb));
     asm volatile("mov.u32 %0, %0;" : "+r"(su));
     asm volatile("mov.u32 %0, %0;" : "+r"(slut));
-    if (cached) k1_lane_loop<NT, true>(P, iv, live, sb, su, sdesc, slut);
-    else k1_lane_loop<NT, false>(P, iv, live, sb, su, 0, 0);
+    if (cached) k1_lane_loop<NT, true, SUB>(P, iv, st, sb, su, sdesc, slut);
+    else k1_lane_loop<NT, false, SUB>(P, iv, st, sb, su, 0, 0);
+}
+
+// K1a: one lane per restart interval.
+// LPW = lanes of each warp that carry an interval.  The kernel is bound by the latency of a warp's
+// serial step, not by issue slots; with LPW = 16 a warp has half the divergent work per step (fewer
+// block ends, refills and cache misses to wait for) and twice as many warps fill the idle issue slots.
+template <int NT, int LPW>
+__global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
+    const int tid = threadIdx.x;
+    const int gid = (blockIdx.x * (NT / 32) + (tid >> 5)) * LPW + (tid & 31);
+    // lanes past the end of the interval list (or beyond LPW) idle through the loop (its head is a warp vote)
+    const bool live = gid < P.n_iv && (tid & 31) < LPW;
+    const ZpxIntervalDev iv = P.ivs[live ? gid : P.n_iv - 1];
+    K1Start st;
+    st.bitpos = ((uint32_t)iv.start & 3u) * 8u;
+    st.k = 0;
+    st.dc0 = st.dc1 = st.dc2 = st.dc3 = 0;
+    st.j0 = 0;
+    st.count = live ? iv.n_blocks : 0;
+    k1_cta_run<NT, false>(P, iv, st);
+}
+
+// K1b, last pass (zpx_k1s.cu): one lane per sub-sequence, 32 consecutive sub-sequences of one segment per warp.
+// Every lane starts from its true state (found by k1s_sync), skips the tail of a block begun in the previous
+// sub-sequence and writes the blocks that START inside its own (their number and the DC predictors at that
+// point come from k1s_scan), running past its boundary to finish the last one.
+template <int NT>
+__global__ void __launch_bounds__(NT) k1s_write(const K1SParams P) {
+    const int wid = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const bool wv = wid < P.n_warps;
+    const ZpxWarpDev w = P.warps[wv ? wid : P.n_warps - 1];
+    const ZpxIntervalDev iv = P.k1.ivs[w.iv];
+    const uint32_t li = w.first + lane;
+    const bool valid = wv && li < iv.nsub;
+    const uint32_t t = iv.sub_first + (valid ? li : 0);
+    const unsigned long long in = P.s_in[t];
+    const uint32_t excl = min((uint32_t)max(P.s_n[t], 0), iv.n_blocks);
+    const uint32_t next = (valid && li + 1 < iv.nsub) ? min((uint32_t)max(P.s_n[t + 1], 0), iv.n_blocks) : iv.n_blocks;
+    const int4 dc = P.s_dc[t];
+    K1Start st;
+    st.bitpos = (uint32_t)in;
+    st.k = (int)((in >> 40) & 0xff);
+    st.dc0 = dc.x;
+    st.dc1 = dc.y;
+    st.dc2 = dc.z;
+    st.dc3 = dc.w;
+    st.j0 = excl;
+    st.count = valid && next > excl ? next - excl : 0;
+    k1_cta_run<NT, true>(P.k1, iv, st);
 }
 
 cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s) {
@@ -513,6 +631,14 @@ cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s) {
     } else {
         k1_lane_per_interval<NT, 32><<<(P.n_iv + NT - 1) / NT, NT, 0, s>>>(P);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t k1s_launch_write(const K1SParams& P, cudaStream_t s) {
+    if (P.n_warps <= 0) return cudaSuccess;
+    constexpr int NT = 128;
+    const int wpc = NT / 32;
+    k1s_write<NT><<<(P.n_warps + wpc - 1) / wpc, NT, 0, s>>>(P);
     return cudaGetLastError();
 }
 

@@ -17,8 +17,8 @@
 //              few symbols, so this takes 2-3 rounds in practice but is exact for any input.
 //   k1s_scan   exclusive prefix sums, per domain, of the block counts and DC sums (wrapping int32
 //              adds: identical to the sequential accumulation of decoder.zig:1374).
-//   k1s_write  every lane decodes again from its true start state and writes the blocks that START
-//              inside its sub-sequence (it skips the tail of a block begun earlier and runs past
+//   k1s_write  (zpx_k1.cu) every lane decodes again from its true start state and writes the blocks that
+//              START inside its sub-sequence (it skips the tail of a block begun earlier and runs past
 //              its boundary to finish its last block), absolute DC included.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -280,147 +280,8 @@ __global__ void __launch_bounds__(K1S_NT) k1s_scan(const K1SParams P) {
     }
 }
 
-// ---------------------------------------------------------------------------
-// write kernel
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(K1S_NT) k1s_write(const K1SParams P) {
-    __shared__ uint4 sblk[8 * K1S_NT];
-    __shared__ uint8_t s_unzig[80];
-    LaneBlock<K1S_NT> lb;
-    lb.base = sblk + threadIdx.x;
-    lb.clear();
-    if (threadIdx.x < 80) s_unzig[threadIdx.x] = threadIdx.x < 64 ? c_unzig[threadIdx.x] : 63;
-    __syncthreads();
-    const int wid = blockIdx.x * (K1S_NT / 32) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (wid >= P.n_warps) return;  // whole warp
-    const ZpxWarpDev w = P.warps[wid];
-    LaneCtx L;
-    lane_setup(P.k1, w, lane, L);
-    const ZpxIntervalDev* __restrict__ iv = L.iv;
-    const ZpxScanDev* __restrict__ sc = L.sc;
-    const ZpxImageDev* __restrict__ im = L.im;
-    const bool valid = L.li < iv->nsub;
-    const uint32_t t = iv->sub_first + (valid ? L.li : 0);
-    const unsigned long long in = P.s_in[t];
-    const int excl_n = P.s_n[t];
-    const int4 excl_dc = P.s_dc[t];
-    const int err_eof = (iv->flags & 1) ? ZPX_E_UnexpectedEof : ZPX_E_MissingFF00;
-
-    BitReader br;
-    br.init_at(L.words, (uint32_t)in, L.end, L.bnd);
-    int c = (int)((in >> 32) & 0xff), k = (int)((in >> 40) & 0xff);
-    const bool interleaved = sc->interleaved != 0;
-    const int nblk = interleaved ? sc->nblk : 1;
-    const bool planar = im->layout == ZPX_LAYOUT_PLANAR || !interleaved;
-    const uint4* __restrict__ bpack = reinterpret_cast<const uint4*>(sc->blk_pack);
-    if (sc->rotate) {
-        // the phase was left out of the state: block excl_n of the segment has phase excl_n % nblk; a block in
-        // flight at the start is the one before it
-        const int j0 = excl_n;
-        c = k != 0 ? (j0 + nblk - 1) % nblk : j0 % nblk;
-    }
-    uint4 bi = bpack[c];
-    const ZpxHuffDev* __restrict__ tdc = &P.k1.huff[bi.x];
-    const ZpxHuffDev* __restrict__ tac = &P.k1.huff[bi.y];
-
-    // a lane whose start state is inside a block first skips that block's tail (it belongs to the
-    // lane in whose sub-sequence the block started); `skipping` ends at the first block start
-    bool skipping = k != 0;
-    int dc0 = excl_dc.x, dc1 = excl_dc.y, dc2 = excl_dc.z, dc3 = excl_dc.w;
-    uint32_t eob_run = 0;
-    uint32_t j = (uint32_t)excl_n;  // index (inside the domain) of the next block this lane starts
-    const uint32_t mxx = (uint32_t)im->mxx;
-    const uint32_t cw = (uint32_t)sc->cw;
-    uint32_t mcu = 0, mx = 0, my = 0, bxn = 0, byn = 0;
-    // the block that follows a skipped tail has phase c+1; j % nblk says the same for true states
-    {
-        const uint32_t jj = j;
-        if (interleaved) {
-            mcu = iv->first_mcu + jj / (uint32_t)nblk;
-            mx = mcu % mxx;
-            my = mcu / mxx;
-        } else {
-            const uint32_t o = iv->first_block + jj;
-            byn = o / cw;
-            bxn = o - byn * cw;
-        }
-    }
-    bool go = valid && j < iv->n_blocks;
-    while (__any_sync(0xffffffffu, go)) {
-        if (go) {
-            // a block (or a skipped tail's successor) may only START before the boundary
-            const uint32_t u = br.used();
-            if (k == 0 && !skipping && br.bpassed && u >= br.B) {
-                go = false;
-            } else if (skipping && ((br.bpassed && u >= br.B) || (br.pad && u >= br.fed))) {
-                go = false;  // no block starts inside this sub-sequence
-            } else {
-                SymOut so;
-                int err;
-                if (skipping) {
-                    int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-                    uint32_t er = 0;
-                    err = symbol_step<true>(br, tdc, tac, bi.w, 0, k, er, s0, s1, s2, s3, so);
-                    if (so.done) {
-                        skipping = false;
-                        k = 0;
-                        c = c + 1 == nblk ? 0 : c + 1;
-                        bi = bpack[c];
-                        tdc = &P.k1.huff[bi.x];
-                        tac = &P.k1.huff[bi.y];
-                    }
-                } else {
-                    err = symbol_step<false>(br, tdc, tac, bi.w, (int)(bi.z & 0xff), k, eob_run, dc0, dc1, dc2, dc3, so);
-                    if (so.store) lb.put(s_unzig[so.kk], so.v);
-                    // End-Of-Band RUN inside a sequential scan: the reference blanks the next
-                    // blocks; the speculative passes do not model that state
-                    if (!err && eob_run != 0) err = ZPX_E_UNSUPPORTED_STREAM;
-                    if (err) {
-                        if (br.overrun()) err = err_eof;
-                        report(P.k1.status, im->status_slot, sc->scan_index, (uint64_t)iv->first_block + j, err);
-                        go = false;
-                    } else if (so.done) {
-                        if (br.overrun()) {
-                            report(P.k1.status, im->status_slot, sc->scan_index, (uint64_t)iv->first_block + j, err_eof);
-                            go = false;
-                        } else {
-                            const int comp = (int)(bi.z & 0xff);
-                            int bx, by;
-                            if (interleaved) {
-                                bx = (int)(bi.w & 0xff) * (int)mx + (int)((bi.z >> 8) & 0xff);
-                                by = (int)((bi.w >> 8) & 0xff) * (int)my + (int)((bi.z >> 16) & 0xff);
-                            } else {
-                                bx = (int)bxn;
-                                by = (int)byn;
-                            }
-                            uint64_t blk;
-                            if (planar) blk = im->comp_base[comp] + (uint64_t)by * im->comp_bw[comp] + bx;
-                            else blk = im->coef_base + (uint64_t)mcu * im->bpm + (bi.z >> 24);
-                            lb.flush(P.k1.coef + blk * 8, bx & 7);
-                            k = 0;
-                            j++;
-                            if (j >= iv->n_blocks) go = false;
-                            if (interleaved) {
-                                if (++c == nblk) {
-                                    c = 0;
-                                    mcu++;
-                                    if (++mx == mxx) { mx = 0; my++; }
-                                }
-                                bi = bpack[c];
-                                tdc = &P.k1.huff[bi.x];
-                                tac = &P.k1.huff[bi.y];
-                            } else if (++bxn == cw) {
-                                bxn = 0;
-                                byn++;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    }
-}
+// the write pass (k1s_write) lives in zpx_k1.cu: it is the block-synchronous loop of the lane-per-interval
+// kernel, started from each sub-sequence's true state
 
 cudaError_t k1s_launch_sync(const K1SParams& P, int sweep, cudaStream_t s) {
     if (P.n_warps <= 0) return cudaSuccess;
@@ -434,11 +295,4 @@ cudaError_t k1s_launch_scan(const K1SParams& P, cudaStream_t s) {
     k1s_scan<<<(P.n_iv + wpc - 1) / wpc, K1S_NT, 0, s>>>(P);
     return cudaGetLastError();
 }
-cudaError_t k1s_launch_write(const K1SParams& P, cudaStream_t s) {
-    if (P.n_warps <= 0) return cudaSuccess;
-    const int wpc = K1S_NT / 32;
-    k1s_write<<<(P.n_warps + wpc - 1) / wpc, K1S_NT, 0, s>>>(P);
-    return cudaGetLastError();
-}
-
 }  // namespace zpx
