@@ -146,10 +146,10 @@ struct zpx_ctx {
     std::string last_cuda_str;
     std::atomic<uint64_t> launches{0};
     int64_t opt_entropy_mode = 0, opt_force_generic = 0, opt_subseq = 0, opt_pipeline_chunk = 0, opt_lanes_per_warp = 0;
-    int64_t opt_pipeline_ramp = 1;
+    int64_t opt_pipeline_ramp = 1, opt_pipeline_workers = 3;
     bool busy = false;
     const zpx_batch* resident = nullptr;  // the batch whose data currently occupies the device buffers
-    zpx_ctx* shadow = nullptr;  // second set of device buffers/streams for the chunk pipeline of zpx_decode_batch_rgba
+    std::vector<zpx_ctx*> shadows;  // further sets of device buffers/streams for the chunk pipeline of zpx_decode_batch_rgba
 };
 
 struct zpx_batch {
@@ -598,6 +598,13 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         bool multi = false;
         for (size_t k = 0; k < pl.n_seq; k++) multi = multi || pl.ivs[k].nsub > 32;
         for (int sweep = 1; multi; sweep++) {
+            // warp boundaries first (cheap); a full sweep only if one of them moved
+            CU(ctx, cudaMemsetAsync(ks.changed, 0, sizeof(int), st));
+            CU(ctx, k1s_launch_fix(ks, st));
+            k1_launches++;
+            CU(ctx, cudaMemcpyAsync(hflag, ks.changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(ctx, cudaStreamSynchronize(st));
+            if (*hflag == 0) break;
             CU(ctx, cudaMemsetAsync(ks.changed, 0, sizeof(int), st));
             CU(ctx, k1s_launch_sync(ks, sweep, st));
             k1_launches++;
@@ -815,7 +822,7 @@ int32_t zpx_ctx_create(const int32_t* device_ids, int32_t n_devices, zpx_ctx** o
 
 void zpx_ctx_destroy(zpx_ctx* c) {
     if (!c) return;
-    if (c->shadow) zpx_ctx_destroy(c->shadow);
+    for (zpx_ctx* sh : c->shadows) zpx_ctx_destroy(sh);
     for (DeviceCtx& d : c->devs) {
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
@@ -851,6 +858,10 @@ int32_t zpx_ctx_set_option(zpx_ctx* c, int32_t option, int64_t value) {
         case ZPX_OPT_SUBSEQ_BYTES: c->opt_subseq = value; return ZPX_OK;
         case ZPX_OPT_PIPELINE_CHUNK: c->opt_pipeline_chunk = value; return ZPX_OK;
         case ZPX_OPT_PIPELINE_RAMP: c->opt_pipeline_ramp = value; return ZPX_OK;
+        case ZPX_OPT_PIPELINE_WORKERS:
+            if (value < 1 || value > 8) return ZPX_E_INVALID_ARG;
+            c->opt_pipeline_workers = value;
+            return ZPX_OK;
         case ZPX_OPT_LANES_PER_WARP: c->opt_lanes_per_warp = value; return ZPX_OK;
     }
     return ZPX_E_INVALID_ARG;
@@ -1212,24 +1223,38 @@ static int32_t decode_range_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const
 }
 
 // Large batches are cut into chunks that flow through two sets of device buffers and streams
-// (context + shadow context, one host thread each): while one chunk's RGBA travels back over PCIe,
+// (context + shadow contexts, one host thread each): while one chunk's RGBA travels back over PCIe,
 // the next chunk is parsed, uploaded and decoded.  Images are independent, so chunking changes
 // nothing in the results.
 int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* lens, int32_t n,
                               uint8_t* const* out, const size_t* out_stride, int32_t* status) {
     if (!ctx || n < 0 || (n > 0 && (!bufs || !lens || !out))) return ZPX_E_INVALID_ARG;
-    int32_t chunk = ctx->opt_pipeline_chunk > 0 ? (int32_t)ctx->opt_pipeline_chunk : 128;
+    int32_t chunk = (int32_t)ctx->opt_pipeline_chunk;
+    if (chunk == 0) {
+        // auto: about 28 MB of compressed input per chunk (64 images of cfg2; roughly 0.5 GB of RGBA), which keeps
+        // the device->host copy of one chunk around 10 ms -- long enough to amortise launches, short enough
+        // for the pipeline to fill quickly
+        uint64_t total = 0;
+        for (int32_t i = 0; i < n; i++) total += lens[i];
+        const uint64_t avg = std::max<uint64_t>(1, total / (uint64_t)std::max(n, 1));
+        chunk = (int32_t)std::min<uint64_t>(2048, std::max<uint64_t>(16, (28u << 20) / avg));
+    }
     if (ctx->opt_pipeline_chunk < 0 || n < 2 * chunk) return decode_range_rgba(ctx, bufs, lens, n, out, out_stride, status);
-    if (!ctx->shadow) {
+    const int n_workers = (int)std::min<int64_t>(ctx->opt_pipeline_workers, (n + chunk - 1) / chunk);
+    while ((int)ctx->shadows.size() < n_workers - 1) {
         std::vector<int32_t> ids;
         for (const DeviceCtx& d : ctx->devs) ids.push_back(d.dev);
-        int e = zpx_ctx_create(ids.data(), (int32_t)ids.size(), &ctx->shadow);
+        zpx_ctx* sh = nullptr;
+        int e = zpx_ctx_create(ids.data(), (int32_t)ids.size(), &sh);
         if (e) return e;
+        ctx->shadows.push_back(sh);
     }
-    ctx->shadow->opt_entropy_mode = ctx->opt_entropy_mode;
-    ctx->shadow->opt_force_generic = ctx->opt_force_generic;
-    ctx->shadow->opt_subseq = ctx->opt_subseq;
-    ctx->shadow->opt_lanes_per_warp = ctx->opt_lanes_per_warp;
+    for (zpx_ctx* sh : ctx->shadows) {
+        sh->opt_entropy_mode = ctx->opt_entropy_mode;
+        sh->opt_force_generic = ctx->opt_force_generic;
+        sh->opt_subseq = ctx->opt_subseq;
+        sh->opt_lanes_per_warp = ctx->opt_lanes_per_warp;
+    }
     // chunk list: the first two chunks are a quarter and a half of the regular size, so that the first
     // device->host copy starts early (the pipeline is bound by that copy; its fill time is pure loss)
     std::vector<std::pair<int32_t, int32_t>> chunks;
@@ -1243,31 +1268,37 @@ int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const si
     }
     const int32_t n_chunks = (int32_t)chunks.size();
     std::atomic<int32_t> next(0);
-    int32_t rc[2] = {0, 0};
+    std::vector<int32_t> rc((size_t)n_workers, 0);
     std::vector<int32_t> st(status ? 0 : n);
     int32_t* stp = status ? status : st.data();
     auto worker = [&](int w) {
-        zpx_ctx* c = w == 0 ? ctx : ctx->shadow;
+        zpx_ctx* c = w == 0 ? ctx : ctx->shadows[(size_t)w - 1];
         for (;;) {
             const int32_t k = next.fetch_add(1);
             if (k >= n_chunks) break;
             const int32_t i0 = chunks[k].first, cnt = chunks[k].second;
             const int e = decode_range_rgba(c, bufs + i0, lens + i0, cnt, out + i0, out_stride ? out_stride + i0 : nullptr, stp + i0);
             if (e) {
-                rc[w] = e;
-                if (w == 1) {  // surface the CUDA error text on the caller's context
-                    ctx->last_cuda = c->last_cuda;
-                    ctx->last_cuda_str = c->last_cuda_str;
-                }
+                rc[(size_t)w] = e;
                 break;
             }
         }
     };
-    std::thread t1(worker, 1);
+    std::vector<std::thread> threads;
+    for (int w = 1; w < n_workers; w++) threads.emplace_back(worker, w);
     worker(0);
-    t1.join();
-    ctx->launches += ctx->shadow->launches.exchange(0);
-    return rc[0] ? rc[0] : rc[1];
+    for (std::thread& t : threads) t.join();
+    int32_t ret = rc[0];
+    for (int w = 1; w < n_workers; w++) {
+        zpx_ctx* c = ctx->shadows[(size_t)w - 1];
+        ctx->launches += c->launches.exchange(0);
+        if (!ret && rc[(size_t)w]) {  // surface the CUDA error text on the caller's context
+            ret = rc[(size_t)w];
+            ctx->last_cuda = c->last_cuda;
+            ctx->last_cuda_str = c->last_cuda_str;
+        }
+    }
+    return ret;
 }
 
 }  // extern "C"

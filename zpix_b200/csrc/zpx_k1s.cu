@@ -11,7 +11,9 @@
 //              started and the sum of the DC differences it decoded, per component.  Sub-sequence 0
 //              starts in the true state, the others from a guess (boundary byte, block 0, DC).  Lanes
 //              hand their end state to the next lane (shuffle inside the warp, global memory across
-//              warps, one kernel launch per sweep) and re-decode while their start state changes.
+//              warps) and re-decode while their start state changes.  After sweep 0 only the first
+//              sub-sequence of each warp can be stale: k1s_fix repairs those, one lane per warp boundary,
+//              and another full sweep runs only if a repaired sub-sequence ends in a new state.
 //              Fixed point => every start state is the true one, by induction from sub-sequence 0
 //              (F_i(true start of i) = true start of i+1); Huffman streams re-synchronise after a
 //              few symbols, so this takes 2-3 rounds in practice but is exact for any input.
@@ -183,6 +185,12 @@ __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int 
                 }
             }
         }
+        // a lane whose predecessor's end state is not its start state (k1s_fix may have changed lane 0's)
+        const unsigned long long po0 = __shfl_up_sync(0xffffffffu, out, 1);
+        if (lane > 0 && active && po0 != in) {
+            in = po0;
+            dirty = true;
+        }
         if (!__any_sync(0xffffffffu, dirty)) return;
     }
     bool touched = false;
@@ -207,6 +215,43 @@ __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int 
         P.s_dc[t] = dc;
     }
     if (last_active && more_warps && (sweep == 0 || out != old_out)) atomicExch(P.changed, 1);
+}
+
+// ---------------------------------------------------------------------------
+// boundary kernel: after a sweep only the FIRST sub-sequence of every warp can still have a stale start
+// state (it comes from the previous warp).  One lane per warp boundary re-decodes that sub-sequence from
+// the previous warp's end state; the lanes of a warp here are 32 different boundaries, so this costs
+// 1/32 of the warp instructions of another full sweep.  If such a re-decode ends in a new state, the rest
+// of that warp is stale: `changed` asks the host for another k1s_sync sweep.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(K1S_NT) k1s_fix(const K1SParams P) {
+    const int g = blockIdx.x * K1S_NT + threadIdx.x;
+    const bool valid = g < P.n_warps;
+    const ZpxWarpDev w = P.warps[valid ? g : 0];
+    LaneCtx L;
+    lane_setup(P.k1, w, 0, L);
+    bool dirty = valid && w.first > 0;
+    const uint32_t t = L.iv->sub_first + L.li;
+    unsigned long long in = 0, old_out = 0;
+    if (dirty) {
+        const unsigned long long ni = P.s_out[t - 1];
+        in = P.s_in[t];
+        old_out = P.s_out[t];
+        dirty = ni != in;
+        in = ni;
+    }
+    const unsigned dm = __ballot_sync(0xffffffffu, dirty);
+    if (dm == 0) return;
+    if (dirty) {
+        int n = 0;
+        int4 dc = make_int4(0, 0, 0, 0);
+        const unsigned long long out = sync_decode(P.k1, L, in, dm, n, dc);
+        P.s_in[t] = in;
+        P.s_out[t] = out;
+        P.s_n[t] = n;
+        P.s_dc[t] = dc;
+        if (out != old_out && L.li + 1 < L.iv->nsub) atomicExch(P.changed, 1);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -287,6 +332,11 @@ cudaError_t k1s_launch_sync(const K1SParams& P, int sweep, cudaStream_t s) {
     if (P.n_warps <= 0) return cudaSuccess;
     const int wpc = K1S_NT / 32;
     k1s_sync<<<(P.n_warps + wpc - 1) / wpc, K1S_NT, 0, s>>>(P, sweep);
+    return cudaGetLastError();
+}
+cudaError_t k1s_launch_fix(const K1SParams& P, cudaStream_t s) {
+    if (P.n_warps <= 0) return cudaSuccess;
+    k1s_fix<<<(P.n_warps + K1S_NT - 1) / K1S_NT, K1S_NT, 0, s>>>(P);
     return cudaGetLastError();
 }
 cudaError_t k1s_launch_scan(const K1SParams& P, cudaStream_t s) {

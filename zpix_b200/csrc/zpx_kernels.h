@@ -34,6 +34,7 @@ struct K1SParams {
     int* changed;               // device flag: an end state crossing a warp boundary changed in this sweep
 };
 cudaError_t k1s_launch_sync(const K1SParams& P, int sweep, cudaStream_t s);
+cudaError_t k1s_launch_fix(const K1SParams& P, cudaStream_t s);
 cudaError_t k1s_launch_scan(const K1SParams& P, cudaStream_t s);
 cudaError_t k1s_launch_write(const K1SParams& P, cudaStream_t s);
 
