@@ -66,12 +66,42 @@ __device__ __forceinline__ void lane_setup(const K1Params& P, const ZpxWarpDev w
 // to accumulate the per-component sums of DC differences.  Invalid codes advance one bit (any
 // deterministic rule works: true states of a well-formed stream never meet one; errors are reported
 // by k1s_write).  Called by the lanes in `mask` together; the vote keeps them in lock step.
+//
+// Checkpoints (CK): a re-decode from a corrected start state joins the trajectory of the lane's previous
+// decode after a few dozen symbols (that is what self-synchronisation means), and from there on repeats
+// it.  Each decode therefore records its state at the first symbol boundary at or after 1/4, 1/2 and 3/4
+// of the sub-sequence -- (bits past that raw byte offset, block phase, zig-zag index), which does not
+// depend on where the decode started -- together with the counts so far; a later decode that reaches a
+// checkpoint in the same state stops there and completes its counts from the previous decode's
+// (exact: equal state at equal raw position means identical continuation).  n_out / dc_out / old_out
+// carry the previous decode's results in.
+struct CkStore {          // this lane's slots in shared memory, [3] strided by K1S_NT
+    uint32_t* st;         // rel | c << 16 | k << 24 ; 0xffffffff = none
+    int* n;
+    int4* dc;
+};
+
+template <bool CK>
 __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, const LaneCtx& L, unsigned long long in,
-                                                          unsigned mask, int& n_out, int4& dc_out) {
-    BitReader br;
-    br.init_at(L.words, (uint32_t)in, L.end, L.bnd);
-    int c = (int)((in >> 32) & 0xff), k = (int)((in >> 40) & 0xff);
+                                                          unsigned mask, int& n_out, int4& dc_out,
+                                                          unsigned long long old_out = 0, CkStore ck = CkStore{nullptr, nullptr, nullptr}) {
     const ZpxScanDev* __restrict__ sc = L.sc;
+    // thresholds T_m = bnd - (3 - m) * step, m = 0..2, then the sub-sequence boundary itself (m == 3)
+    const uint32_t step = (L.iv->sub_bytes >> 2) & ~3u;
+    const bool use_ck = CK && sc->rotate == 0 && step >= 32;
+    uint32_t m = 3;
+    if (use_ck) {
+        // arm the first threshold that lies safely after the start position (the reader buffers ahead)
+        const uint32_t sbyte = (uint32_t)in >> 3;
+        m = 0;
+        while (m < 3 && L.bnd - (3 - m) * step <= sbyte + 16) {
+            ck.st[m * K1S_NT] = 0xffffffffu;
+            m++;
+        }
+    }
+    BitReader br;
+    br.init_at(L.words, (uint32_t)in, L.end, L.bnd - (3 - m) * step);
+    int c = (int)((in >> 32) & 0xff), k = (int)((in >> 40) & 0xff);
     const int nblk = sc->interleaved ? sc->nblk : 1;
     const uint4* __restrict__ bpack = reinterpret_cast<const uint4*>(sc->blk_pack);
     // rotate mode: the phase is not part of the state; c counts blocks relative to this sub-sequence and
@@ -82,12 +112,45 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
     uint4 bi = bpack[c];
     const uint32_t* __restrict__ fdc = P.huff[bi.x].fast;
     const uint32_t* __restrict__ fac = P.huff[bi.y].fast;
-    bool go = true;
+    bool go = true, merged = false;
     while (__any_sync(mask, go)) {
         if (go) {
             const uint32_t u = br.used();
-            if ((br.bpassed && u >= br.B) || (br.pad && u >= br.fed)) {
+            if (br.pad && u >= br.fed) {
                 go = false;
+            } else if (br.bpassed && u >= br.B) {
+                if (!CK || m >= 3) {
+                    go = false;  // first symbol boundary at or after the end of the sub-sequence
+                } else {
+                    const uint32_t cur = (u - br.B) | (uint32_t)c << 16 | (uint32_t)k << 24;
+                    const int4 odc = ck.dc[m * K1S_NT];
+                    const int on = ck.n[m * K1S_NT];
+                    if (ck.st[m * K1S_NT] == cur) {
+                        // joined the previous trajectory: the rest is known
+                        const int dn = n - on;
+                        const int e0 = d0 - odc.x, e1 = d1 - odc.y, e2 = d2 - odc.z, e3 = d3 - odc.w;
+                        for (uint32_t q = m; q < 3; q++) {  // re-base the stored counts on this decode's start
+                            ck.n[q * K1S_NT] += dn;
+                            int4 t = ck.dc[q * K1S_NT];
+                            t.x += e0; t.y += e1; t.z += e2; t.w += e3;
+                            ck.dc[q * K1S_NT] = t;
+                        }
+                        n = n_out + dn;
+                        d0 = dc_out.x + e0;
+                        d1 = dc_out.y + e1;
+                        d2 = dc_out.z + e2;
+                        d3 = dc_out.w + e3;
+                        merged = true;
+                        go = false;
+                    } else {
+                        ck.st[m * K1S_NT] = cur;
+                        ck.n[m * K1S_NT] = n;
+                        ck.dc[m * K1S_NT] = make_int4(d0, d1, d2, d3);
+                        m++;
+                        br.bnd = L.bnd - (3 - m) * step;
+                        br.bpassed = 0;
+                    }
+                }
             } else {
                 br.fill();
                 const uint32_t hi = br.peek32();
@@ -141,6 +204,9 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
     }
     n_out = n;
     dc_out = make_int4(d0, d1, d2, d3);
+    if (CK && merged) return old_out;
+    if (CK && use_ck)  // checkpoints this decode did not reach (data ran out) must not match later
+        for (uint32_t q = m; q < 3; q++) ck.st[q * K1S_NT] = 0xffffffffu;
     // a DC symbol decoded in rotate mode belongs to relative phase c *before* the block ends; when the
     // sub-sequence ends inside a block, that block's phase is (c) and was counted -- nothing to fix
     return pack_state(br.rawpos(), rotate ? 0 : c, k);
@@ -150,6 +216,11 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
 // sweep kernel
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int sweep) {
+    __shared__ uint32_t s_ck[3 * K1S_NT];
+    __shared__ int s_cn[3 * K1S_NT];
+    __shared__ int4 s_cdc[3 * K1S_NT];
+    const CkStore ck{s_ck + threadIdx.x, s_cn + threadIdx.x, s_cdc + threadIdx.x};
+    for (int q = 0; q < 3; q++) s_ck[q * K1S_NT + threadIdx.x] = 0xffffffffu;
     const int wid = blockIdx.x * (K1S_NT / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (wid >= P.n_warps) return;
@@ -197,7 +268,7 @@ __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int 
     do {
         const unsigned dm = __ballot_sync(0xffffffffu, dirty);
         if (dirty) {
-            out = sync_decode(P.k1, L, in, dm, n, dc);
+            out = sync_decode<true>(P.k1, L, in, dm, n, dc, out, ck);
             touched = true;
         }
         const unsigned long long po = __shfl_up_sync(0xffffffffu, out, 1);
@@ -245,7 +316,7 @@ __global__ void __launch_bounds__(K1S_NT) k1s_fix(const K1SParams P) {
     if (dirty) {
         int n = 0;
         int4 dc = make_int4(0, 0, 0, 0);
-        const unsigned long long out = sync_decode(P.k1, L, in, dm, n, dc);
+        const unsigned long long out = sync_decode<false>(P.k1, L, in, dm, n, dc);
         P.s_in[t] = in;
         P.s_out[t] = out;
         P.s_n[t] = n;
