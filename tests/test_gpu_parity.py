@@ -345,6 +345,46 @@ def test_native_cmyk_variant(jpeg, fixtures_dir):
         assert c.toRGBA()[0] >> 8 == int(ref.rgbaPixels()[5, 3, 0])
 
 
+def test_dispatcher_routes_jpegs_to_the_batch_path(jpeg, fixtures_dir):
+    """zpix.fromBuffer / fromBuffers (src/root.zig:24-40): probe, JPEG -> GPU path, anything else UnknownImageFormat."""
+    import zpix_b200 as zpix
+    a = _read(fixtures_dir, "video-001.q50.420.jpeg")
+    b = _read(fixtures_dir, "video-005.gray.jpeg")
+    png = b"\x89PNG\r\n\x1a\n" + bytes(32)
+    res = zpix.fromBuffers([a, png, b, b""])
+    assert isinstance(res[1], ValueError) and isinstance(res[3], ValueError)
+    assert np.array_equal(res[0].rgbaPixels().reshape(-1), O.decode(a).rgbaPixels().reshape(-1))
+    assert np.array_equal(res[2].rgbaPixels().reshape(-1), O.decode(b).rgbaPixels().reshape(-1))
+    one = zpix.fromBuffer(a)
+    assert one.tag == "YCbCr" and np.array_equal(one.rgbaPixels().reshape(-1), res[0].rgbaPixels().reshape(-1))
+    with pytest.raises(ValueError):
+        zpix.fromBuffer(png)
+
+
+def test_all_devices_of_the_box_in_one_context(jpeg, fixtures_dir):
+    """the host scheduler splits a batch over the GPUs of one box (contiguous ranges balanced by
+    entropy-coded bytes, one host thread per device), no collective.  Runs on however many GPUs are visible."""
+    import torch
+    nd = torch.cuda.device_count()
+    if nd < 2:
+        pytest.skip("one GPU visible")
+    names = BASELINE_FIXTURES + PROGRESSIVE_FIXTURES
+    datas = [_read(fixtures_dir, n) for n in names] * 3
+    datas += S.make_batch(2, 6, 1920, 1080, subsampling="4:2:0", restart_rows=1)
+    datas += [S.encode(52001 + i, 640, 480, subsampling="4:4:4") for i in range(5)]
+    ctx = jpeg.Context(list(range(nd)))
+    assert ctx.num_devices == nd
+    for mode in (0, 2):
+        ctx.set_option(1, mode)
+        _assert_same(jpeg, ctx, datas)
+    with jpeg.Batch(ctx, datas) as b:
+        b.upload()
+        b.decode()
+        used = [di for di in range(nd) if b.timing(di)["images"] > 0]
+    assert len(used) >= 2
+    ctx.close()
+
+
 def test_one_call_chunk_pipeline(jpeg, fixtures_dir):
     """zpx_decode_batch_rgba cuts large batches into chunks that alternate between two sets of device
     buffers; results and per-image status must not depend on the chunking."""

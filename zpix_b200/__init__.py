@@ -22,3 +22,12 @@ def fromFilePath(path: str):
     if jpeg.probePath(path):
         return jpeg.load(path)
     raise ValueError("error.UnknownImageFormat")
+
+
+def fromBuffers(buffers, ctx=None):
+    """Batch form of fromBuffer: probe every buffer, send the JPEGs to the GPU batch path in one
+    call and answer `error.UnknownImageFormat` for the rest (PNG / QOI / BMP stay with the reference's CPU
+    decoders, which are out of scope here).  Returns one Image or one exception instance per input."""
+    is_jpeg = [jpeg.probeBuffer(b) for b in buffers]
+    decoded = iter(jpeg.decodeBatch([b for b, j in zip(buffers, is_jpeg) if j], ctx))
+    return [next(decoded) if j else ValueError("error.UnknownImageFormat") for j in is_jpeg]

@@ -1014,9 +1014,19 @@ int32_t zpx_batch_decode(zpx_batch* b, void* stream) {
     for (int di = 0; di < nd; di++)
         if (!b->plans[di].images.empty() && !b->plans[di].uploaded) return ZPX_E_BAD_STATE;
     b->status_ready = false;
-    for (int di = 0; di < nd; di++) {
-        int e = decode_on_device(b, di, (cudaStream_t)stream);
+    if (nd == 1) {
+        int e = decode_on_device(b, 0, (cudaStream_t)stream);
         if (e) return e;
+    } else {
+        // one host thread per device: the self-synchronising decoder reads a flag back between sweeps, which
+        // would otherwise serialise the devices
+        std::vector<int> rc((size_t)nd, 0);
+        std::vector<std::thread> th;
+        for (int di = 1; di < nd; di++) th.emplace_back([&, di] { rc[(size_t)di] = decode_on_device(b, di, nullptr); });
+        rc[0] = decode_on_device(b, 0, nullptr);
+        for (std::thread& t : th) t.join();
+        for (int di = 0; di < nd; di++)
+            if (rc[(size_t)di]) return rc[(size_t)di];
     }
     if (stream) return ZPX_OK;  // caller synchronises its own stream
     for (int di = 0; di < nd; di++) {
