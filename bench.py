@@ -191,7 +191,6 @@ def main():
         import torch.distributed as dist_mod
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (no "NCCL version" banner)
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
 
@@ -345,4 +344,13 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL's version banner, torchrun
+    # notices): point fd 1 at stderr for the whole run and hand the real stdout only to the final print.
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
+    try:
+        main()
+    finally:
+        _real_stdout.flush()

@@ -109,28 +109,25 @@ struct FastReader {
     }
     __device__ __forceinline__ bool overrun() const { return cnt < pad; }
 
-    // make sure more than 32 bits are buffered
+    // make sure more than 32 bits are buffered.  One divergent region, entered every fifth symbol or so; the
+    // common refill (32 data bits, no 0xFF, inside the range) is straight-line code that ends by loading the
+    // NEXT word straight into nw's register (inline asm: no move waits for it), so nothing stalls on that load
+    // until the next refill.
     __device__ __forceinline__ void feed() {
-        const bool need = cnt <= 32;
-        const uint32_t raw = nw;
-        const uint32_t nff = ~raw;
-        const uint32_t hasff = (nff - 0x01010101u) & raw & 0x80808080u;
-        const bool fast = need && (hasff | skip) == 0 && off + 4 <= end;  // off >= first after init
-        if (fast) {
-            buf |= ((uint64_t)__byte_perm(raw, 0, 0x0123) << 32) >> cnt;
-            cnt += 32;
-            off += 4;
-            // L1 allocates 32-byte sectors: ask for the sector four ahead when entering a new one
-            if ((off & 31u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(base) + off + 128));
+        if (cnt <= 32) {
+            const uint32_t raw = nw;
+            const uint32_t hasff = (~raw - 0x01010101u) & raw & 0x80808080u;
+            if ((hasff | skip) == 0 && off + 4 <= end) {  // off >= first after init
+                buf |= ((uint64_t)__byte_perm(raw, 0, 0x0123) << 32) >> cnt;
+                cnt += 32;
+                off += 4;
+                // L1 allocates 32-byte sectors: ask for the sector four ahead when entering a new one
+                if ((off & 31u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(base) + off + 128));
+                asm volatile("ld.global.nc.u32 %0, [%1];" : "+r"(nw) : "l"(base + (off >> 2)));
+            } else {
+                feed_slow();
+            }
         }
-        {
-            const uint32_t* p = base + (off >> 2);
-            asm volatile(
-                "{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p ld.global.nc.u32 %0, [%1];\n}\n"
-                : "+r"(nw)
-                : "l"(p), "r"((uint32_t)fast));
-        }
-        if (need && !fast) feed_slow();
     }
 
     // byte by byte: range edges, FF 00 pairs, zero padding past the limit; until cnt > 32
