@@ -22,10 +22,17 @@
 // code or invalid.  Longer codes: smallest l with v16 < limit[l] (v16 = next 16 bits, left aligned),
 // symbol = vals[valoff[l] + (v16 >> (16 - l))]  -- the canonical decode the reference does bit by
 // bit at decoder.zig:946-969; identical results for every code of the table.
-// fast[]: everything the per-symbol step needs in one 32-bit load:
-//   bits 0-5 tot (bits to consume: len+size), 8-12 len, 13-17 size (value bits), 18-24 adv (how far the
-//   zig-zag index moves: DC 1, AC run+1, ZRL 16, EOB 64), bit 31 special (EOB run, DC category > 16);
+// fast[]: everything the per-symbol step needs in one 32-bit load --
+// ZpxHuffDev::fast entry, one per ZPX_LUT_BITS-bit prefix (byte-aligned fields: one PRMT each on the device):
+//   byte 0  total bits of the symbol (code + value bits)
+//   byte 1  code length
+//   byte 2  value bits (size); for a special entry: the run r of an End-Of-Band run
+//   byte 3  zig-zag advance (DC: 1; AC: run + 1, ZRL 16, EOB 64) | special << 7
+//   special: AC (r, 0) with 0 < r < 15 (End-Of-Band run) or a DC category > 16
 //   0 = code longer than ZPX_LUT_BITS or invalid -> canonical search.
+#define ZPX_FE(tot, len, size, adv, special) \
+    ((uint32_t)(tot) | (uint32_t)(len) << 8 | (uint32_t)(size) << 16 | (uint32_t)(adv) << 24 | (uint32_t)(special) << 31)
+
 struct ZpxHuffDev {
     uint32_t fast[ZPX_LUT_SIZE];
     uint16_t lut[ZPX_LUT_SIZE];

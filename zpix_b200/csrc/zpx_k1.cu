@@ -167,13 +167,13 @@ struct FastReader {
 };
 
 // rare path of the symbol step: code longer than the first-level table, or a special entry.
-// Returns the fast-entry fields for the symbol in the low word (bit 31 kept for an AC End-Of-Band
-// run, with its r in bits 25-28) and an error code in the high word.
+// Returns the fast-entry fields for the symbol in the low word (ZPX_FE; bit 31 kept for an AC End-Of-Band
+// run, with its r in byte 2) and an error code in the high word.
 __device__ __noinline__ unsigned long long k1_slow_symbol(const ZpxHuffDev* __restrict__ tab, uint32_t hi, bool isdc,
                                                           uint32_t e) {
     int err = 0;
     uint32_t sym = 0;
-    int len = (int)((e >> 8) & 31u);
+    int len = (int)((e >> 8) & 0xffu);
     if (e == 0) {
         const uint32_t v16 = hi >> 16;
         len = 0;
@@ -184,7 +184,7 @@ __device__ __noinline__ unsigned long long k1_slow_symbol(const ZpxHuffDev* __re
             }
         }
         if (len == 0)  // the reference reads 16 bits, then BadHuffmanCode (decoder.zig:947-969)
-            return (unsigned long long)(16u | 16u << 8 | 64u << 18) | ((unsigned long long)ZPX_E_BadHuffmanCode << 32);
+            return (unsigned long long)ZPX_FE(16, 16, 0, 64, 0) | ((unsigned long long)ZPX_E_BadHuffmanCode << 32);
     } else {
         // special first-level entry: recover the symbol from the 16-bit table
         sym = (uint32_t)tab->lut[hi >> (32 - ZPX_LUT_BITS)] >> 8;
@@ -205,7 +205,7 @@ __device__ __noinline__ unsigned long long k1_slow_symbol(const ZpxHuffDev* __re
         else if (r == 0) { size = 0; adv = 64; }
         else { size = 0; adv = 64; special = 1; rr = r; }
     }
-    e = ((uint32_t)len + size) | (uint32_t)len << 8 | size << 13 | adv << 18 | rr << 25 | special << 31;
+    e = ZPX_FE((uint32_t)len + size, len, special ? rr : size, adv, special);
     return (unsigned long long)e | ((unsigned long long)(uint32_t)err << 32);
 }
 
@@ -233,6 +233,19 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
     return v;
 }
 
+// fields of a ZpxHuffDev::fast entry (ZPX_FE): one PRMT / SHF each
+__device__ __forceinline__ int fe_tot(uint32_t e) { return (int)__byte_perm(e, 0, 0x4440); }
+__device__ __forceinline__ int fe_len(uint32_t e) { return (int)__byte_perm(e, 0, 0x4441); }
+__device__ __forceinline__ int fe_size(uint32_t e) { return (int)__byte_perm(e, 0, 0x4442); }
+__device__ __forceinline__ int fe_adv(uint32_t e) { return (int)(e >> 24); }  // special bit is clear on this path
+// RECEIVE + EXTEND (decoder.zig:1115-1134) on the `size` bits at the top of t (size 0 -> 0): PTX shr clamps a
+// shift by 32 to zero
+__device__ __forceinline__ int fe_extend(uint32_t t, int size) {
+    uint32_t v;
+    asm("shr.u32 %0, %1, %2;" : "=r"(v) : "r"(t), "r"(32 - size));
+    return (int)v + (((int)t >= 0) ? 1 - (1 << size) : 0);
+}
+
 // slow-path wrapper shared by the DC and AC steps: returns the entry fields, sets err / eob_run
 template <bool SMEM>
 __device__ __forceinline__ uint32_t k1_rare(const K1Params& P, const FastReader& br, uint32_t hi, bool isdc, uint32_t e,
@@ -250,11 +263,13 @@ __device__ __forceinline__ uint32_t k1_rare(const K1Params& P, const FastReader&
     err = (int)(r >> 32);
     if (e >> 31) {
         // (r, 0) with 0 < r < 15 (decoder.zig:1399-1407): eob_run = (1 << r | next r bits) - 1
-        const int len = (int)((e >> 8) & 31u), rr = (int)((e >> 25) & 15u);
+        const int len = (int)((e >> 8) & 0xffu), rr = (int)((e >> 16) & 0xffu);
         eob_run = (1u << rr) | (uint32_t)((br.buf << len) >> (64 - rr));
         eob_run = (eob_run - 1) & 0xffffu;
-        e = (e & 0x01ffffc0u) | (uint32_t)(len + rr);  // consume code + run bits, adv stays 64
+        e = ZPX_FE(len + rr, len, 0, 64, 0);  // consume code + run bits, end of block
     }
+    // an error ends the block: advance past index 63 (the caller's err stays set for the block-end code)
+    if (err) e = (e & 0x00ffffffu) | 64u << 24;
     return e;
 }
 
@@ -346,17 +361,15 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
             else e = __ldg(gdc + (hi >> (32 - ZPX_LUT_BITS)));
             if ((int)e <= 0) e = k1_rare<SMEM>(P, br, hi, true, e, bi.x, gdc, slut, eob_run, err);
             if (bi.w & 0x10000u) err = ZPX_E_UninitializedHuffmanTable;
-            const int len = (int)((e >> 8) & 31u), size = (int)((e >> 13) & 31u);
-            const uint32_t t = (uint32_t)((br.buf << len) >> 32);
-            int v = (int)((t >> 1) >> (31 - size));
-            v += (~((int)t >> 31)) & (1 - (1 << size));
+            const int len = fe_len(e), size = fe_size(e);
+            const int v = fe_extend(__funnelshift_l((uint32_t)br.buf, (uint32_t)(br.buf >> 32), len), size);
             const int comp = (int)(bi.z & 0xff);
             int dc = comp == 0 ? dc0 : comp == 1 ? dc1 : comp == 2 ? dc2 : dc3;
             dc += v;
             if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
             if ((dc < -32768 || dc > 32767) && !err) err = ZPX_E_COEF_RANGE;
-            br.buf <<= (len + size);
-            br.cnt -= (len + size);
+            br.buf <<= fe_tot(e);
+            br.cnt -= fe_tot(e);
             sts_u16(sb, dc);
             k = 1;
             if (eob_run > 0) {  // decoder.zig:1379-1380 (End-Of-Band run)
@@ -386,12 +399,10 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                         if (!err) err = ZPX_E_UNSUPPORTED_STREAM;
                     }
                 }
-                const int len = (int)((e >> 8) & 31u), size = (int)((e >> 13) & 31u);
-                int tot = (int)(e & 63u);
-                const int adv = (int)((e >> 18) & 127u);
-                const uint32_t t = (uint32_t)((br.buf << len) >> 32);
-                int v = (int)((t >> 1) >> (31 - size));
-                v += (~((int)t >> 31)) & (1 - (1 << size));  // first bit 0 -> negative
+                const int len = fe_len(e), size = fe_size(e);
+                int tot = fe_tot(e);
+                const int adv = fe_adv(e);  // 64 after an error: the block ends here
+                const int v = fe_extend(__funnelshift_l((uint32_t)br.buf, (uint32_t)(br.buf >> 32), len), size);
                 const int kk = k + adv - 1;                    // zig-zag index the value goes to
                 bool store = size != 0 && !(SUB && tail);
                 if (kk > 63) {  // decoder.zig:1393-1395: run past the block end, the value bits stay unread
@@ -402,7 +413,6 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 br.buf <<= tot;
                 br.cnt -= tot;
                 if (store) sts_u16(sb + lds_u16(su + 2 * kk), v);
-                if (err) k = 64;
             }
         }
         // ---- block end ----
@@ -551,7 +561,7 @@ __device__ __forceinline__ void k1_cta_run(const K1Params& P, const ZpxIntervalD
         for (int i = tid; i < (nt << K1_SLB); i += NT) {
             const int slot = i >> K1_SLB, ix = i & ((1 << K1_SLB) - 1);
             uint32_t e = __ldg(&P.huff[tab_ids[slot]].fast[ix << (ZPX_LUT_BITS - K1_SLB)]);
-            if (((e >> 8) & 31u) > (uint32_t)K1_SLB) e = 0;
+            if (((e >> 8) & 0xffu) > (uint32_t)K1_SLB) e = 0;
             s_lut[i] = e;
         }
         for (int i = 0; i < s_nscan; i++)

@@ -165,7 +165,7 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
                         e = 1u;  // invalid: one bit further, same state (tot = 1, adv = 0)
                     } else if (isdc) {
                         const uint32_t size = hs.sym > 16 ? 0u : hs.sym;
-                        e = ((uint32_t)hs.len + size) | (uint32_t)hs.len << 8 | size << 13 | 1u << 18;
+                        e = ZPX_FE((uint32_t)hs.len + size, hs.len, size, 1, 0);
                     } else {
                         const uint32_t r = hs.sym >> 4, s2 = hs.sym & 15;
                         uint32_t size = s2, adv = r + 1, extra = 0;
@@ -174,12 +174,12 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
                             adv = r == 15 ? 16 : 64;
                             extra = (r != 15) ? r : 0;  // EOB run: r more bits belong to the symbol
                         }
-                        e = ((uint32_t)hs.len + size + extra) | (uint32_t)hs.len << 8 | size << 13 | adv << 18;
+                        e = ZPX_FE((uint32_t)hs.len + size + extra, hs.len, size, adv, 0);
                     }
                 }
-                const int len = (int)((e >> 8) & 31u), size = (int)((e >> 13) & 31u);
-                int tot = (int)(e & 63u);
-                const int adv = (int)((e >> 18) & 127u);
+                const int len = (int)__byte_perm(e, 0, 0x4441), size = (int)__byte_perm(e, 0, 0x4442);
+                int tot = (int)__byte_perm(e, 0, 0x4440);
+                const int adv = (int)(e >> 24);
                 if (isdc && adv) {
                     const uint32_t t = (uint32_t)((br.buf << len) >> 32);
                     int v = (int)((t >> 1) >> (31 - size));

@@ -517,13 +517,13 @@ uint32_t zpx_fast_entry(bool is_ac, int len, int sym) {
         adv = 1;
         if (sym > 16) { special = 1; size = 0; }
     } else {
-        const int r = sym >> 4, s2 = sym & 15;
-        if (s2 != 0) { size = (uint32_t)s2; adv = (uint32_t)r + 1; }
+        const uint32_t r = (uint32_t)sym >> 4, s2 = (uint32_t)sym & 15;
+        if (s2 != 0) { size = s2; adv = r + 1; }
         else if (r == 15) { size = 0; adv = 16; }
         else if (r == 0) { size = 0; adv = 64; }
         else { size = 0; adv = 64; special = 1; }
     }
-    return ((uint32_t)len + size) | (uint32_t)len << 8 | size << 13 | adv << 18 | special << 31;
+    return ZPX_FE((uint32_t)len + size, len, size, adv, special);
 }
 
 void zpx_build_huff_dev(const ZpxHuffHost& h, bool is_ac, ZpxHuffDev* o, int* malformed) {
