@@ -18,6 +18,7 @@
 // first error in the reference's decode order wins.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "zpx_entropy.cuh"
 #include "zpx_internal.h"
@@ -629,9 +630,25 @@ __global__ void __launch_bounds__(NT) k1s_write(const K1SParams P) {
     k1_cta_run<NT, true>(P.k1, iv, st);
 }
 
+// The kernel keeps 44 KB of shared memory per CTA; at the register-limited 5 CTAs per SM the driver carves
+// 228 KB out of the 256 KB unified array and leaves the 640 per-lane streams of an SM some 28 KB of L1.
+// Measured on cfg2 (544 CTAs): carve-out 100 / 86 % 5.81 ms, 72 % (164 KB, 3 CTAs per SM, 92 KB of L1) 5.64 ms,
+// 57 % 8.43 ms.  ZPX_K1_CARVEOUT overrides the percentage (-1: leave it to the driver).
+template <typename K>
+static void k1_prefer_l1(K kernel) {
+    static bool done = false;
+    if (!done) {
+        const char* e = getenv("ZPX_K1_CARVEOUT");
+        const int pct = e ? atoi(e) : 72;
+        if (pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        done = true;
+    }
+}
+
 cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s) {
     if (P.n_iv <= 0) return cudaSuccess;
     constexpr int NT = 128;
+    k1_prefer_l1(k1_lane_per_interval<NT, 32>);
     if (P.lanes_per_warp == 16) {
         constexpr int per_cta = (NT / 32) * 16;
         k1_lane_per_interval<NT, 16><<<(P.n_iv + per_cta - 1) / per_cta, NT, 0, s>>>(P);
