@@ -39,6 +39,27 @@ CACHE = os.environ.get("ZPX_SYNTH_CACHE", "/tmp/zpx_synth")
 WORKLOAD = "cfg2: 1024 x 1920x1080 baseline 4:2:0 YCbCr JPEG, DRI = 1 MCU row (120 MCUs), quality 85, per GPU"
 
 
+def bind_to_gpu_numa(device_index: int) -> str:
+    """Pin this rank (and the pinned buffers it is about to allocate: first touch) to the CPUs next to its GPU.
+    With 8 ranks on a two-socket box half of them would otherwise push their 8.5 GB of RGBA per step through the
+    socket interconnect.  Returns a note for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = [i for i in range(n) if (mask[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"rank bound to {len(allowed)} CPUs near its GPU"
+    except Exception as e:  # no NVML, no permission: run unbound
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 def reduce_max(value: float, dist, device) -> float:
     """max over ranks of a per-rank device time (ms); identity when not distributed"""
     if dist is None:
@@ -187,12 +208,14 @@ def main():
 
     torch.cuda.set_device(local)
     dist = None
+    numa_note = "single rank, unbound"
     if world > 1:
         import torch.distributed as dist_mod
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
+        numa_note = bind_to_gpu_numa(local)
 
     def barrier():
         if dist:
@@ -327,7 +350,7 @@ def main():
                    "entropy_mode": "one lane per restart interval (69632 intervals per GPU)"},
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(tm["entropy_bytes_in"]), "d2h_bytes_per_step": int(tm["rgba_bytes"]),
-                "note": "zpx_decode_batch_rgba: host header parse + pinned staging + H2D + kernels + D2H into pinned host memory"},
+                "note": "zpx_decode_batch_rgba: host header parse + pinned staging + H2D + kernels + D2H into pinned host memory; " + numa_note},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k2_fused<2,2,3>", "achieved": achieved, "peak": peak, "unit": "GB/s",
