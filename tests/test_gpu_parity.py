@@ -69,6 +69,8 @@ def _assert_same(jpeg, ctx, datas, names=None):
     for i, d in enumerate(datas):
         want, err = _oracle_rgba(d)
         tag = names[i] if names else i
+        if err == "ReferencePanics":
+            continue  # the Zig code hits a panic / out-of-bounds index on this input: nothing defined to match
         if want is None:
             assert st[i] != 0, f"{tag}: oracle fails with {err}, GPU path succeeded"
             assert jpeg.lib.zpx_error_name(st[i]).decode() == err, f"{tag}: {err} vs {st[i]}"
@@ -292,6 +294,19 @@ def test_damaged_progressive_streams_match_oracle(jpeg, ctx, fixtures_dir):
                        ("video-001.separate.dc.progression.progressive.jpeg", 3)]:
         datas += _damaged(_read(fixtures_dir, name), seed, 12, 40)
     datas += _damaged(S.encode(50021, 160, 120, subsampling="4:2:0", progressive=True, restart_rows=1), 4, 6, 20)
+    _assert_same(jpeg, ctx, datas)
+
+
+def test_header_fuzz_decodes_like_oracle(jpeg, ctx, fixtures_dir):
+    """Seeded damage in the marker segments: odd-but-legal sampling factors, table assignments, scan scripts,
+    restart intervals ... must decode to the oracle's pixels, everything else must fail with its error."""
+    from _damage import header_damage
+    rng = np.random.default_rng(77)
+    datas = []
+    for fname in ["video-001.jpeg", "video-001.q50.420.progressive.jpeg", "video-001.cmyk.jpeg", "video-001.restart2.jpeg",
+                  "video-005.gray.q50.2x2.jpeg", "video-001.separate.dc.progression.jpeg", "video-001.rgb.jpeg",
+                  "video-001.q50.411.jpeg"]:
+        datas += header_damage(_read(fixtures_dir, fname), rng, 60)
     _assert_same(jpeg, ctx, datas)
 
 

@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
+from _damage import header_damage
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -149,6 +150,38 @@ def test_parser_error_kinds_match_oracle(zlib, fixtures_dir, golden_dir):
             # only the entropy decode (GPU) can fail these
             assert want in ("ok", "MissingFF00", "BadHuffmanCode", "ExcessiveDCComponent", "UninitializedHuffmanTable",
                             "UnsupportedColorModel"), want
+
+
+ENTROPY_ERRORS = ("MissingFF00", "BadHuffmanCode", "ExcessiveDCComponent", "UninitializedHuffmanTable",
+                  "UnexpectedHuffmanCode", "TooManyCoefficients")
+
+
+def test_parser_header_fuzz_matches_oracle(zlib, fixtures_dir):
+    """Seeded byte damage in the marker segments (SOF / DHT / DQT / DRI / SOS headers / APPn) of several fixtures:
+    whenever the host parser rejects a file its error is the oracle's; when it accepts one, the oracle either
+    decodes it or fails later, inside entropy data (the device's job) or with the error the parser queued."""
+    rng = np.random.default_rng(20241018)
+    name = lambda c: zlib.lib.zpx_error_name(c).decode()
+    n_cases = n_rejected = 0
+    for fname in ["video-001.jpeg", "video-001.q50.420.progressive.jpeg", "video-001.cmyk.jpeg", "video-001.restart2.jpeg",
+                  "video-005.gray.q50.2x2.jpeg", "video-001.separate.dc.progression.jpeg", "video-001.rgb.jpeg"]:
+        for d in header_damage(_read(fixtures_dir, fname), rng, 120):
+            try:
+                O.decode(d)
+                want = "ok"
+            except O.OracleError as e:
+                want = e.name
+            inf, rep = _report(zlib, d)
+            n_cases += 1
+            if rep.status:
+                n_rejected += 1
+                assert name(rep.status) == want, (fname, want, name(rep.status))
+            elif rep.pending_err or rep.trailing_err:
+                assert want != "ok", fname
+                assert want in (name(rep.pending_err or rep.trailing_err),) + ENTROPY_ERRORS, (fname, want)
+            else:
+                assert want in ("ok", "UnsupportedColorModel") + ENTROPY_ERRORS or O.last_eob_carry(), (fname, want)
+    assert n_cases == 840 and n_rejected > 100
 
 
 def test_probe_is_decode_config(zlib, fixtures_dir):
