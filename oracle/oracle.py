@@ -85,6 +85,8 @@ def lib():
         L.zo_rgba_pixels.restype = None
         L.zo_last_eob_carry.argtypes = []
         L.zo_last_eob_carry.restype = C.c_int
+        L.zo_last_coef_overflow.argtypes = []
+        L.zo_last_coef_overflow.restype = C.c_int
         L.zo_free.argtypes = [C.POINTER(_ZoImage)]
         L.zo_free.restype = None
         L.zo_error_name.argtypes = [C.c_int]
@@ -152,6 +154,11 @@ class Image:
 def last_eob_carry() -> bool:
     """True if the latest decode() met a scan that started inside an End-Of-Band run (also when it raised)."""
     return bool(lib().zo_last_eob_carry())
+
+
+def last_coef_overflow() -> bool:
+    """True if a coefficient left the int16 range during the latest decode() (also when it raised)."""
+    return bool(lib().zo_last_coef_overflow())
 
 
 def decode(data: bytes, tap: bool = False):

@@ -87,6 +87,7 @@ typedef struct {
     int adobe_transform; /* 0 unknown, 1 y_cb_cr, 2 y_cb_cr_k */
     uint16_t eob_run;
     int eob_carry; /* test aid: a scan started with eob_run != 0 (left open by the previous scan) */
+    int coef_overflow; /* test aid: a coefficient left the int16 range (the GPU path stores int16) */
 
     component comp[MAX_COMPONENTS];
     int32_t (*prog_coef[MAX_COMPONENTS])[BLOCK_SIZE];
@@ -761,6 +762,7 @@ static int refine_non_zeroes(decoder *d, int32_t *b, int32_t zig, int32_t zig_en
         if (!bit) continue;
         if (b[index] >= 0) b[index] = wadd(b[index], delta);
         else b[index] = wsub(b[index], delta);
+        if (b[index] < -32768 || b[index] > 32767) d->coef_overflow = 1;
     }
     *out_zig = zig;
     return ZO_OK;
@@ -943,6 +945,7 @@ static int process_sos(decoder *d, int32_t n) {
                             TRY(receive_extend(d, value, &dc_delta));
                             dc[ci] = wadd(dc[ci], dc_delta);
                             b[0] = wshl(dc[ci], (int)al);
+                            if (b[0] < -32768 || b[0] > 32767) d->coef_overflow = 1;
                         }
                         if (zig <= zig_end && d->eob_run > 0) {
                             d->eob_run -= 1;
@@ -958,6 +961,7 @@ static int process_sos(decoder *d, int32_t n) {
                                     int32_t ac;
                                     TRY(receive_extend(d, val1, &ac));
                                     b[unzig[zig]] = wshl(ac, (int)al);
+                                    if (b[unzig[zig]] < -32768 || b[unzig[zig]] > 32767) d->coef_overflow = 1;
                                 } else {
                                     if (val0 != 0x0f) {
                                         d->eob_run = (uint16_t)(1u << val0);
@@ -1230,8 +1234,9 @@ static void free_decoder(decoder *d) {
 }
 
 /* test aid (not thread-safe): eob_carry of the latest zo_decode / zo_decode_tap, also when it failed */
-static int g_last_eob_carry = 0;
+static int g_last_eob_carry = 0, g_last_coef_overflow = 0;
 int zo_last_eob_carry(void) { return g_last_eob_carry; }
+int zo_last_coef_overflow(void) { return g_last_coef_overflow; }
 
 int zo_decode_tap(const uint8_t *data, size_t len, zo_image *out, zo_tap *tap) {
     decoder *d = new_decoder(data, len);
@@ -1243,6 +1248,7 @@ int zo_decode_tap(const uint8_t *data, size_t len, zo_image *out, zo_tap *tap) {
     if (e != ZO_OK) memset(out, 0, sizeof(*out));
     else out->eob_carry = d->eob_carry;
     g_last_eob_carry = d->eob_carry;
+    g_last_coef_overflow = d->coef_overflow;
     free_decoder(d);
     return e;
 }

@@ -107,6 +107,9 @@ typedef struct zo_image {
 /* eob_carry of the latest zo_decode / zo_decode_tap in this process, also when that call failed
  * (test aid, not thread-safe) */
 int zo_last_eob_carry(void);
+/* likewise: 1 if a coefficient left the int16 range during that decode (non-conforming streams; the GPU path
+ * stores int16 coefficients and answers CoefficientOutOfRange) */
+int zo_last_coef_overflow(void);
 
 /* Optional coefficient tap, used by the tests of the entropy kernels.
  * Sequential frames: one record per coded block, in the order processSos

@@ -68,9 +68,15 @@ def _assert_same(jpeg, ctx, datas, names=None):
     outs, st, _ = _gpu_batch(jpeg, ctx, datas)
     for i, d in enumerate(datas):
         want, err = _oracle_rgba(d)
+        overflow = O.last_coef_overflow()
         tag = names[i] if names else i
         if err == "ReferencePanics":
             continue  # the Zig code hits a panic / out-of-bounds index on this input: nothing defined to match
+        if st[i] == 104:
+            # documented deviation: coefficients are int16 in HBM; a (non-conforming) stream whose coefficients leave
+            # that range is refused with CoefficientOutOfRange where the reference, keeping int32, decodes on
+            assert overflow, f"{tag}: CoefficientOutOfRange but the oracle's coefficients fit int16"
+            continue
         if want is None:
             assert st[i] != 0, f"{tag}: oracle fails with {err}, GPU path succeeded"
             assert jpeg.lib.zpx_error_name(st[i]).decode() == err, f"{tag}: {err} vs {st[i]}"
@@ -307,6 +313,41 @@ def test_header_fuzz_decodes_like_oracle(jpeg, ctx, fixtures_dir):
                   "video-005.gray.q50.2x2.jpeg", "video-001.separate.dc.progression.jpeg", "video-001.rgb.jpeg",
                   "video-001.q50.411.jpeg"]:
         datas += header_damage(_read(fixtures_dir, fname), rng, 60)
+    _assert_same(jpeg, ctx, datas)
+
+
+def _with_eob_run_symbols(data: bytes, swaps):
+    """Rewrite symbols of the AC Huffman tables (class 1 DHT segments) so that ordinary run/size symbols become
+    End-Of-Band-run symbols (r, 0), 0 < r < 15 -- legal only in progressive scans, honoured by the reference in
+    sequential ones too."""
+    d = bytearray(data)
+    i = 2
+    while i + 4 <= len(d) and not (d[i] == 0xFF and d[i + 1] == 0xDA):
+        seglen = (d[i + 2] << 8) | d[i + 3]
+        if d[i + 1] == 0xC4:
+            j = i + 4
+            while j < i + 2 + seglen:
+                tc, n = d[j] >> 4, sum(d[j + 1:j + 17])
+                if tc == 1:
+                    for k in range(j + 17, j + 17 + n):
+                        if d[k] in swaps:
+                            d[k] = swaps[d[k]]
+                j += 17 + n
+        i += 2 + seglen
+    return bytes(d)
+
+
+def test_eob_runs_in_sequential_scans(jpeg, ctx, fixtures_dir):
+    """the reference counts End-Of-Band runs down in baseline scans as well (decoder.zig:1379-1407),
+    resetting them only at RSTn.  Such scans always take the lane-per-interval kernel, which models the run."""
+    datas = []
+    for name in ["video-001.restart2.jpeg", "video-001.jpeg", "video-005.gray.jpeg", "video-001.q50.420.jpeg",
+                 "video-001.cmyk.jpeg"]:
+        base = _read(fixtures_dir, name)
+        for swaps in ({0x04: 0x30}, {0x03: 0x10, 0x12: 0x20}, {0x05: 0xE0}, {0x02: 0x10}, {0x11: 0x40, 0x21: 0x50}):
+            datas.append(_with_eob_run_symbols(base, swaps))
+    oks = sum(1 for d in datas if _oracle_rgba(d)[0] is not None)
+    assert oks >= 5, oks  # enough of them decode (garbage, but the same garbage) rather than fail
     _assert_same(jpeg, ctx, datas)
 
 

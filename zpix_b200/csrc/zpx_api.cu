@@ -5,6 +5,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include <map>
 #include <string>
@@ -120,6 +122,9 @@ struct DevicePlan {
     std::vector<size_t> prog_off;                    // byte offsets of those lists in the descriptor buffer
     std::vector<std::pair<uint64_t, uint64_t>> prog_zero;  // (first block, blocks) of progressive images: zeroed before the scans
     size_t n_seq = 0;                                // sequential intervals = ivs[0, n_seq)
+    size_t n_sub_iv = 0;                             // self-synchronising mode: ivs[0, n_sub_iv) take it, the rest
+                                                     // of the sequential ones one lane per interval
+    std::vector<uint8_t> iv_lane_only;               // per sequential interval (build time only)
     std::vector<ZpxWarpDev> warps;  // self-synchronising mode: one entry per warp
     size_t n_subs = 0;
     bool sub_mode = false;
@@ -444,6 +449,16 @@ void build_plan(zpx_batch* b, int di) {
                 sd.cw = std::min(im.comp_bw[c], (p.width + 7) / 8);
                 sd.ch = std::min(im.comp_bh[c], (p.height + 7) / 8);
             }
+            // An AC table that holds a symbol (r, 0) with 0 < r < 15 can start an End-Of-Band run inside a
+            // sequential scan; the self-synchronising decoder does not model that state, so such
+            // scans always take one lane per interval.
+            bool eob_capable = false;
+            if (!p.progressive)
+                for (int i = 0; i < s.ncomp; i++)
+                    for (int v = 0; v < s.ac[i].num_codes; v++) {
+                        const int sym = s.ac[i].vals[v];
+                        eob_capable = eob_capable || ((sym & 15) == 0 && (sym >> 4) >= 1 && (sym >> 4) <= 14);
+                    }
             const uint32_t scan_ix = (uint32_t)pl.scans.size();
             pl.scans.push_back(sd);
             if (s.intervals.empty()) continue;
@@ -481,6 +496,7 @@ void build_plan(zpx_batch* b, int di) {
                     d.n_blocks = (uint32_t)(coded_before(x1) - coded_before(x0));
                 }
                 d.sub_first = d.nsub = d.sub_bytes = d.pad0 = 0;
+                if (!p.progressive) pl.iv_lane_only.push_back(eob_capable ? 1 : 0);
                 if (p.progressive) {
                     const size_t lv = (size_t)level[sd.scan_index];
                     if (pl.prog_lists.size() <= lv) pl.prog_lists.resize(lv + 1);
@@ -506,9 +522,16 @@ void build_plan(zpx_batch* b, int di) {
     // once, serially; otherwise the self-synchronising decoder parallelises inside the intervals
     const int64_t mode = b->ctx->opt_entropy_mode;
     pl.sub_mode = mode == 2 || (mode == 0 && pl.n_seq < 16384);
+    pl.n_sub_iv = 0;
     if (pl.sub_mode) {
+        // lane-only intervals (End-Of-Band-run capable tables) to the back of the sequential range
+        std::vector<ZpxIntervalDev> keep, lane;
+        for (size_t k = 0; k < pl.n_seq; k++) (pl.iv_lane_only[k] ? lane : keep).push_back(pl.ivs[k]);
+        pl.n_sub_iv = keep.size();
+        std::copy(keep.begin(), keep.end(), pl.ivs.begin());
+        std::copy(lane.begin(), lane.end(), pl.ivs.begin() + (ptrdiff_t)keep.size());
         const uint32_t submax = b->ctx->opt_subseq > 0 ? (uint32_t)align_up((size_t)b->ctx->opt_subseq, 4) : 256u;
-        for (size_t k = 0; k < pl.n_seq; k++) {
+        for (size_t k = 0; k < pl.n_sub_iv; k++) {
             ZpxIntervalDev& d = pl.ivs[k];
             const uint32_t span = (uint32_t)(d.start & 3) + d.len;
             uint32_t sub = (uint32_t)align_up((span + 31) / 32, 4);
@@ -578,6 +601,16 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         CU(ctx, k1_launch_lane_per_interval(k1, st));
         k1_launches++;
     } else if (k1.n_iv > 0) {
+        if (pl.n_sub_iv < pl.n_seq) {  // scans the self-synchronising decoder does not take
+            K1Params kl = k1;
+            kl.ivs = k1.ivs + pl.n_sub_iv;
+            kl.n_iv = (int)(pl.n_seq - pl.n_sub_iv);
+            CU(ctx, k1_launch_lane_per_interval(kl, st));
+            k1_launches++;
+        }
+        k1.n_iv = (int)pl.n_sub_iv;
+    }
+    if (k1.n_iv > 0 && pl.sub_mode) {
         K1SParams ks;
         ks.k1 = k1;
         ks.warps = (const ZpxWarpDev*)(desc + pl.off_warps);
@@ -596,7 +629,7 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         CU(ctx, k1s_launch_sync(ks, 0, st));
         k1_launches++;
         bool multi = false;
-        for (size_t k = 0; k < pl.n_seq; k++) multi = multi || pl.ivs[k].nsub > 32;
+        for (size_t k = 0; k < pl.n_sub_iv; k++) multi = multi || pl.ivs[k].nsub > 32;
         for (int sweep = 1; multi; sweep++) {
             // warp boundaries first (cheap); a full sweep only if one of them moved
             CU(ctx, cudaMemsetAsync(ks.changed, 0, sizeof(int), st));
@@ -704,11 +737,20 @@ int finalize_status(zpx_batch* b) {
             const ZpxParsed& p = b->parsed[bi];
             int st = 0;
             if (hs[k] != ZPX_STATUS_NONE) st = (int)(hs[k] & 0xff);
-            if (st == 0) {
+            if (hs[k] != ZPX_STATUS_NONE && getenv("ZPX_DEBUG_STATUS"))
+                fprintf(stderr, "zpx: image %d device status: scan %llu block %llu code %d\n", bi, hs[k] >> 48,
+                        (hs[k] >> 8) & 0xffffffffffull, st);
+            // errors the host queued (found after the entropy data they follow) come after every real device error;
+            // ZPX_E_COEF_RANGE is not an error of the reference, which would go on and return the queued one
+            // (only the sequential kernels' deferred report, scan field 0x7fff; after a wrapped coefficient in a
+            // progressive frame nothing later can be trusted and ZPX_E_COEF_RANGE stands)
+            if (st == 0 || (st == ZPX_E_COEF_RANGE && (hs[k] >> 48) == 0x7fffull)) {
+                int host = 0;
                 for (const ZpxScanHost& s : p.scans)
-                    if (s.pending_err) { st = s.pending_err; break; }
+                    if (s.pending_err) { host = s.pending_err; break; }
+                if (host == 0) host = p.trailing_err;
+                if (host) st = host;
             }
-            if (st == 0) st = p.trailing_err;
             b->status[bi] = st;
             if (st) failed++;
         }

@@ -211,4 +211,12 @@ __device__ __forceinline__ void report(unsigned long long* status, uint32_t img_
     atomicMin(&status[img_slot], key);
 }
 
+// A coefficient left the int16 range the HBM layout stores (non-conforming stream; the reference keeps int32).
+// The image cannot be reproduced, but decoding goes on with the wrapped value: if the reference meets a real
+// error further on (MissingFF00, BadHuffmanCode ...), that one is what it returns, so this code sorts after
+// every real error key.
+__device__ __forceinline__ void report_coef_range(unsigned long long* status, uint32_t img_slot) {
+    atomicMin(&status[img_slot], (0x7fffull << 48) | (unsigned)ZPX_E_COEF_RANGE);
+}
+
 }  // namespace zpx

@@ -368,7 +368,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
             int dc = comp == 0 ? dc0 : comp == 1 ? dc1 : comp == 2 ? dc2 : dc3;
             dc += v;
             if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
-            if ((dc < -32768 || dc > 32767) && !err) err = ZPX_E_COEF_RANGE;
+            if (dc < -32768 || dc > 32767) report_coef_range(P.status, im->status_slot);
             br.buf <<= fe_tot(e);
             br.cnt -= fe_tot(e);
             sts_u16(sb, dc);
@@ -407,7 +407,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 const int kk = k + adv - 1;                    // zig-zag index the value goes to
                 bool store = size != 0 && !(SUB && tail);
                 if (kk > 63) {  // decoder.zig:1393-1395: run past the block end, the value bits stay unread
-                    tot = len;
+                    if (size != 0) tot = len;  // (an End-Of-Band run keeps its r run bits: size == 0 there)
                     store = false;
                 }
                 k += adv;

@@ -482,6 +482,8 @@ __global__ void __launch_bounds__(K3_NT) k3_progressive(const K1Params P, const 
                                     if (comp == 0) dc0 = d; else if (comp == 1) dc1 = d; else if (comp == 2) dc2 = d; else dc3 = d;
                                     rd.skip(len + t);
                                     const int v = (int)((uint32_t)d << al);
+                                    // hard error here, unlike the sequential kernels: later scans parse according to
+                                    // which coefficients are non-zero, so nothing after a wrapped value can be trusted
                                     if (v < -32768 || v > 32767) { err = ZPX_E_COEF_RANGE; stop = true; }
                                     else gblk[cslot(key, 0)] = (short)v;
                                 }
@@ -509,7 +511,7 @@ __global__ void __launch_bounds__(K3_NT) k3_progressive(const K1Params P, const 
                                     const int r = (int)(hs >> 4) & 15, s = (int)hs & 15;
                                     if (s != 0) {
                                         zig += r;
-                                        if (zig > se) { rd.pos += len; break; }
+                                        if (zig > se) { rd.skip(len); break; }  // decoding goes on: keep the reader's words in step
                                         const int v = (int)((uint32_t)extend32(hi, len, s) << al);
                                         rd.skip(len + s);
                                         if (v < -32768 || v > 32767) { err = ZPX_E_COEF_RANGE; break; }
@@ -572,15 +574,17 @@ __global__ void __launch_bounds__(K3_NT) k3_progressive(const K1Params P, const 
                 if (nlo >> lane & 1u) {
                     const uint32_t bp = p0 + c0 + (uint32_t)__popc(nlo & lt);
                     if ((W.ring[(bp >> 5) & (K3_RW - 1)] << (bp & 31)) >> 31) {
-                        const int v = W.zz[k][lane];
-                        W.zz[k][lane] = (short)(v >= 0 ? v + delta : v - delta);
+                        const int v = W.zz[k][lane], nv = v >= 0 ? v + delta : v - delta;
+                        if (nv < -32768 || nv > 32767) report_coef_range(P.status, im->status_slot);
+                        W.zz[k][lane] = (short)nv;
                     }
                 }
                 if (nhi >> lane & 1u) {
                     const uint32_t bp = p0 + c1 + (uint32_t)(__popc(nlo) + __popc(nhi & lt));
                     if ((W.ring[(bp >> 5) & (K3_RW - 1)] << (bp & 31)) >> 31) {
-                        const int v = W.zz[k][lane + 32];
-                        W.zz[k][lane + 32] = (short)(v >= 0 ? v + delta : v - delta);
+                        const int v = W.zz[k][lane + 32], nv = v >= 0 ? v + delta : v - delta;
+                        if (nv < -32768 || nv > 32767) report_coef_range(P.status, im->status_slot);
+                        W.zz[k][lane + 32] = (short)nv;
                     }
                 }
             }
