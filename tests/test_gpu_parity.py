@@ -11,6 +11,7 @@ pytestmark = pytest.mark.gpu
 
 from oracle import oracle as O  # noqa: E402
 from tools import synth_jpeg as S  # noqa: E402
+from _damage import header_damage  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -306,7 +307,6 @@ def test_damaged_progressive_streams_match_oracle(jpeg, ctx, fixtures_dir):
 def test_header_fuzz_decodes_like_oracle(jpeg, ctx, fixtures_dir):
     """Seeded damage in the marker segments: odd-but-legal sampling factors, table assignments, scan scripts,
     restart intervals ... must decode to the oracle's pixels, everything else must fail with its error."""
-    from _damage import header_damage
     rng = np.random.default_rng(77)
     datas = []
     for fname in ["video-001.jpeg", "video-001.q50.420.progressive.jpeg", "video-001.cmyk.jpeg", "video-001.restart2.jpeg",
@@ -349,6 +349,33 @@ def test_eob_runs_in_sequential_scans(jpeg, ctx, fixtures_dir):
     oks = sum(1 for d in datas if _oracle_rgba(d)[0] is not None)
     assert oks >= 5, oks  # enough of them decode (garbage, but the same garbage) rather than fail
     _assert_same(jpeg, ctx, datas)
+
+
+def test_files_found_by_fuzzing(jpeg, ctx, golden_dir):
+    """Regression files from tools/fuzz_hunt.py: garbage streams the reference still decodes.
+    idct_dc_row_wrap_*: first-column values beyond 2^20, where the reference's all-AC-zero row shortcut (s0 << 3,
+    idct.zig:84-97) and the general row formula part ways; prog_run_past_band_end: a run/size symbol whose run
+    leaves the band (value bits stay unread, decoding goes on); eob_run_in_baseline_dri: SURVEY B6."""
+    d = os.path.join(golden_dir, "fuzz_found")
+    names = sorted(os.listdir(d))
+    assert len(names) >= 5
+    _assert_same(jpeg, ctx, [open(os.path.join(d, n), "rb").read() for n in names], names)
+
+
+def test_fuzz_every_fixture(jpeg, fixtures_dir):
+    """A wider net than the tests above, default entropy mode only: every fixture of the reference, damaged in its
+    marker segments, in its entropy-coded data and by truncation (~1000 files in one batch)."""
+    rng = np.random.default_rng(4242)
+    datas = []
+    for k, name in enumerate(sorted(os.listdir(fixtures_dir))):
+        if name == "iceberg.jpg":
+            continue
+        base = _read(fixtures_dir, name)
+        datas += header_damage(base, rng, 24)
+        datas += _damaged(base, 1000 + k, 4, 14)
+    c = jpeg.Context()
+    _assert_same(jpeg, c, datas)
+    c.close()
 
 
 def test_damaged_baseline_streams_match_oracle(jpeg, ctx, fixtures_dir):

@@ -1,0 +1,73 @@
+"""Bug hunt, not a test: many seeds of header / entropy damage over the reference's fixtures, GPU result against the
+oracle under the same rules as tests/test_gpu_parity.py::_assert_same.  Prints every disagreement and saves the file.
+
+  python tools/fuzz_hunt.py [--seeds 20] [--out gpurun_out/fuzz]
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from _damage import header_damage  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from zpix_b200 import jpeg  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--seeds", type=int, default=20)
+ap.add_argument("--first", type=int, default=0)
+ap.add_argument("--out", default="gpurun_out/fuzz")
+ap.add_argument("--mode", type=int, default=0)
+a = ap.parse_args()
+os.makedirs(a.out, exist_ok=True)
+FX = os.path.join(ROOT, "tests", "golden", "ref_fixtures")
+
+
+def entropy_damage(data, rng, n_trunc, n_flip):
+    first_sos = data.index(b"\xff\xda")
+    out = [data[: int(k)] for k in rng.integers(first_sos + 14, len(data) - 2, n_trunc)]
+    for k in rng.integers(first_sos + 14, len(data) - 2, n_flip):
+        d = bytearray(data)
+        d[int(k)] = int(rng.integers(0, 256))
+        out.append(bytes(d))
+    return out
+
+
+ctx = jpeg.Context([0])
+ctx.set_option(1, a.mode)
+bad = total = 0
+for seed in range(a.first, a.first + a.seeds):
+    rng = np.random.default_rng(900000 + seed)
+    datas = []
+    for name in sorted(os.listdir(FX)):
+        if name == "iceberg.jpg":
+            continue
+        base = open(os.path.join(FX, name), "rb").read()
+        datas += header_damage(base, rng, 20) + entropy_damage(base, rng, 4, 16)
+    with jpeg.Batch(ctx, datas) as b:
+        b.upload()
+        b.decode()
+        outs, st = b.fetch_rgba()
+    for i, d in enumerate(datas):
+        total += 1
+        try:
+            img = O.decode(d)
+            want, err = img.rgbaPixels(), "ok"
+            if img.eob_carry:
+                want, err = None, "UnsupportedStream"
+        except O.OracleError as e:
+            want, err = None, ("UnsupportedStream" if O.last_eob_carry() else e.name)
+        ovf = O.last_coef_overflow()
+        got = jpeg.lib.zpx_error_name(st[i]).decode() if st[i] else "ok"
+        if err == "ReferencePanics" or (st[i] == 104 and ovf):
+            continue
+        ok = (got == err) if want is None else (st[i] == 0 and np.array_equal(outs[i], want))
+        if not ok:
+            bad += 1
+            p = os.path.join(a.out, f"seed{seed}_case{i}.jpg")
+            open(p, "wb").write(d)
+            print(f"MISMATCH seed {seed} case {i}: oracle {err} gpu {got} overflow {ovf} -> {p}", flush=True)
+print(f"{total} cases, {bad} mismatches")

@@ -266,6 +266,14 @@ void build_plan(zpx_batch* b, int di) {
         im.hmax = p.h[0];
         im.vmax = p.v[0];
         im.status_slot = (uint32_t)k;
+        // components some scan covers.  Progressive frames allocate their coefficient arrays by looping the FRAME's
+        // component count over the scan's component list (entries past the scan's own count read as
+        // component 0), and only allocated components are reconstructed (decoder.zig:1272-1279, :1644).
+        im.recon_mask = 0;
+        for (const ZpxScanHost& sc : p.scans) {
+            for (int i = 0; i < sc.ncomp; i++) im.recon_mask |= 1u << sc.comp[i];
+            if (p.progressive && sc.ncomp < p.ncomp) im.recon_mask |= 1u;
+        }
         int bpm = 0;
         for (int c = 0; c < p.ncomp; c++) {
             im.h[c] = (uint8_t)p.h[c];
@@ -583,6 +591,8 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
 
     CU(ctx, cudaEventRecord(dc.ev[0], st));
     CU(ctx, cudaMemsetAsync(dc.status.p, 0xff, pl.imgs.size() * sizeof(unsigned long long), st));
+    uint32_t* img_flags = (uint32_t*)((uint8_t*)dc.status.p + align_up(pl.imgs.size() * sizeof(unsigned long long), 256));
+    CU(ctx, cudaMemsetAsync(img_flags, 0, pl.imgs.size() * sizeof(uint32_t), st));
     if (pl.plane_bytes) CU(ctx, cudaMemsetAsync(dc.planes.p, 0, pl.plane_bytes, st));
 
     int k1_launches = 0, k2_launches = 0;
@@ -596,6 +606,7 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
     k1.huff = (const ZpxHuffDev*)(desc + pl.off_huff);
     k1.coef = (uint4*)dc.coef.p;
     k1.status = (unsigned long long*)dc.status.p;
+    k1.img_flags = img_flags;
     k1.lanes_per_warp = ctx->opt_lanes_per_warp == 16 ? 16 : 32;
     if (k1.n_iv > 0 && !pl.sub_mode) {
         CU(ctx, k1_launch_lane_per_interval(k1, st));
@@ -667,6 +678,7 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         k2.imgs = k1.imgs;
         k2.tiles = (const ZpxTileDev*)(desc + g.tiles_off);
         k2.quant = (const ZpxQuantDev*)(desc + pl.off_quant);
+        k2.img_flags = img_flags;
         k2.ntiles = (int)g.tiles.size();
         k2.tmax = g.tmax;
         const int grid = std::min<int>(k2.ntiles, dc.sm_count * 2);
@@ -1002,7 +1014,8 @@ int32_t zpx_batch_upload(zpx_batch* b) {
         CU(ctx, dc.out.ensure(pl.out_bytes + 256));
         if (pl.plane_bytes) CU(ctx, dc.planes.ensure(pl.plane_bytes + 256));
         CU(ctx, dc.desc.ensure(pl.desc_bytes + 256));
-        CU(ctx, dc.status.ensure(pl.imgs.size() * sizeof(unsigned long long) + 256));
+        // per image: error key (u64), then flags (u32)
+        CU(ctx, dc.status.ensure(align_up(pl.imgs.size() * sizeof(unsigned long long), 256) + pl.imgs.size() * sizeof(uint32_t) + 256));
         CU(ctx, dc.stage.ensure(pl.blob_bytes + 64));
         CU(ctx, dc.hdesc.ensure(pl.desc_bytes + 256));
         // descriptors

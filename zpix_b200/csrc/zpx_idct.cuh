@@ -1,8 +1,12 @@
 // zpx_idct.cuh -- exact fixed-point 8x8 IDCT of the reference (src/jpeg/idct.zig:77-201),
 // one thread per block, everything in registers.  Every shift of the reference is a rounding point
 // and stays where it is; only value-neutral rewrites are used:
-//   * the row pass' "all AC zero" shortcut (idct.zig:84-97) is dropped: the general formulas give the
-//     same values (((s0<<11)+128)>>8 == s0<<3) -- SURVEY B3;
+//   * the row pass' "all AC zero" shortcut (idct.zig:84-97: every output = s0 << 3) is not taken: the
+//     general formulas give the same values, ((s0<<11)+128)>>8 == s0<<3, as long as s0 << 11 does not
+//     wrap, i.e. |s0| < 2^20 -- true for every conforming stream (|DC-column value| <= 2047 *
+//     255).  Images that may break that bound (a coefficient outside [-4096, 4095] with 8-bit quantisers:
+//     only garbage streams have them; the entropy kernels flag them, one max per symbol) take
+//     idct_block_q8_exact, which does such rows the reference's way; the unfused path always does;
 //   * dequantisation (decoder.zig:1564-1567) is fused into the row-pass loads; the <<11 prescale of
 //     columns 0 and 4 is folded into the quantiser ((c*q)<<11 == c*(q<<11) in wrapping 32-bit);
 //   * level shift + clamp (decoder.zig:1622-1628: v<-128 -> 0, v>127 -> 255, else v+128) is a
@@ -133,6 +137,8 @@ __device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b) {
 // Same as dequant_idct_block below for quantisers that fit 8 bits: `qp` holds, per row, four words
 // q[2j] | q[2j+1] << 24.  The <<11 prescale of columns 0 and 4 (idct.zig:100-101) is applied after
 // the product ((c*q)<<11, wrapping).
+// Exact for blocks whose first-column coefficients lie in [-4096, 4095] (see the header comment); images that
+// have wider ones are flagged by the entropy kernels and take idct_block_q8_exact instead.
 template <typename LoadRow>
 __device__ __forceinline__ void dequant_idct_block_q8(LoadRow ld, const uint32_t* __restrict__ qp, uint32_t (&px)[16]) {
     int b[64];
@@ -155,6 +161,37 @@ __device__ __forceinline__ void dequant_idct_block_q8(LoadRow ld, const uint32_t
     }
 }
 
+// The same block the reference's way where it matters: a row whose dequantised AC are all zero yields s0 << 3
+// in every column (idct.zig:84-97), which differs from the general row once s0 << 11 wraps (|s0| >= 2^20; only
+// garbage streams).  Out of line and self-contained (reads the block from shared memory again, stores the 8x8
+// pixels itself), so that it costs the hot path nothing but the test that calls it.
+__device__ __noinline__ void idct_block_q8_exact(const uint4* blk, int key, const uint32_t* __restrict__ qp, uint8_t* dst, int pitch) {
+    int b[64];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint4 c = blk[r ^ key];
+        const uint4 q = *reinterpret_cast<const uint4*>(qp + r * 4);
+        const int u0 = dp2a_lo_su(c.x, q.x), s1 = dp2a_hi_su(c.x, q.x);
+        const int s2 = dp2a_lo_su(c.y, q.y), s3 = dp2a_hi_su(c.y, q.y);
+        const int u4 = dp2a_lo_su(c.z, q.z), s5 = dp2a_hi_su(c.z, q.z);
+        const int s6 = dp2a_lo_su(c.w, q.w), s7 = dp2a_hi_su(c.w, q.w);
+        if ((s1 | s2 | s3 | u4 | s5 | s6 | s7) == 0) {
+            const int dc = (int)((uint32_t)u0 << 3);
+#pragma unroll
+            for (int k = 0; k < 8; k++) b[r * 8 + k] = dc;
+        } else {
+            idct_row((int)((uint32_t)u0 << 11), s1, s2, s3, (int)((uint32_t)u4 << 11), s5, s6, s7, &b[r * 8]);
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < 8; x++) idct_col(&b[x]);
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+        *reinterpret_cast<uint2*>(dst + r * pitch) =
+            make_uint2(pack4_level_shift(b[r * 8 + 0], b[r * 8 + 1], b[r * 8 + 2], b[r * 8 + 3]),
+                       pack4_level_shift(b[r * 8 + 4], b[r * 8 + 5], b[r * 8 + 6], b[r * 8 + 7]));
+}
+
 // Dequantise + IDCT one block.  `ld(r)` returns row r of the block as a uint4 of 8 int16 (natural
 // order); `q` points at the block's quantiser in natural order with columns 0 and 4 pre-multiplied
 // by 2048 (int32[64], warp-uniform address).  Result: 8 rows x 2 words of level-shifted pixels.
@@ -170,6 +207,14 @@ __device__ __forceinline__ void dequant_idct_block(LoadRow ld, const int* __rest
         const int s4 = lo16(c.z) * qb.x, s5 = hi16(c.z) * qb.y, s6 = lo16(c.w) * qb.z, s7 = hi16(c.w) * qb.w;
         // idct_row(x0=s0', x4=s1, x3=s2, x7=s3, x1=s4', x6=s5, x2=s6, x5=s7)
         idct_row(s0, s1, s2, s3, s4, s5, s6, s7, &b[r * 8]);
+        // (this unfused path is not the hot one: the reference's all-AC-zero row, idct.zig:84-97, is taken literally;
+        // qa.x carries the << 11 prescale of column 0, so the plain product is s0 >> 11 exactly when it did not wrap,
+        // and is recomputed from the coefficient otherwise)
+        if ((s1 | s2 | s3 | (lo16(c.z) * (qb.x >> 11)) | s5 | s6 | s7) == 0) {
+            const int dc = (int)((uint32_t)(lo16(c.x) * (qa.x >> 11)) << 3);
+#pragma unroll
+            for (int k = 0; k < 8; k++) b[r * 8 + k] = dc;
+        }
     }
 #pragma unroll
     for (int x = 0; x < 8; x++) idct_col(&b[x]);

@@ -346,6 +346,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
 
     int dc0 = st.dc0, dc1 = st.dc1, dc2 = st.dc2, dc3 = st.dc3;
     uint32_t eob_run = 0;
+    int wide = 0;  // max over the lane's symbols of (AC value bits, DC magnitude >> 8): >= 13 / >= 16 flags the image
     uint32_t left = st.count;  // blocks still to decode (including the current one)
 
     while (__any_sync(0xffffffffu, left != 0)) {
@@ -369,6 +370,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
             dc += v;
             if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
             if (dc < -32768 || dc > 32767) report_coef_range(P.status, im->status_slot);
+            wide = max(wide, ((dc ^ (dc >> 31)) >> 12) ? 13 : 0);
             br.buf <<= fe_tot(e);
             br.cnt -= fe_tot(e);
             sts_u16(sb, dc);
@@ -403,6 +405,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 const int len = fe_len(e), size = fe_size(e);
                 int tot = fe_tot(e);
                 const int adv = fe_adv(e);  // 64 after an error: the block ends here
+                wide = max(wide, size);
                 const int v = fe_extend(__funnelshift_l((uint32_t)br.buf, (uint32_t)(br.buf >> 32), len), size);
                 const int kk = k + adv - 1;                    // zig-zag index the value goes to
                 bool store = size != 0 && !(SUB && tail);
@@ -486,6 +489,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     // The reference keeps its End-Of-Band run across scans (decoder.zig:144, reset only at RSTn :1451); here
     // every scan starts from zero, so a run that is still open when a scan ends (corrupt streams only) would
     // make the next scan differ: refuse the image instead.
+    if (wide >= 13) atomicOr(&P.img_flags[im->status_slot], 1u);  // a coefficient outside [-4096, 4095]
     if (!SUB && st.count != 0 && (iv.flags & 2u) && eob_run != 0)
         report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + iv.n_blocks, ZPX_E_UNSUPPORTED_STREAM);
 }

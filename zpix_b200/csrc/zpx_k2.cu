@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
         int32_t width, height;
         uint64_t out_off;
         uint32_t nr, wt;  // gray: the tile is nr whole MCU rows of wt MCUs (n = nr * wt); else nr = 1, wt = n
+        uint32_t wide;    // the image has coefficients outside [-4096, 4095]: exact all-AC-zero rows (zpx_idct.cuh)
     };
     __shared__ TileCtx ctx[NS];
     __shared__ __align__(16) uint32_t qsm[NS][3 * 32];  // per row four words q[2j] | q[2j+1] << 24 (dp2a operands)
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
             c.out_off = imn->out_off;
             c.nr = tn.pad & 0xffu ? tn.pad & 0xffu : 1u;
             c.wt = tn.pad >> 16 ? tn.pad >> 16 : tn.n;
+            c.wide = P.img_flags[imn->status_slot] & 1u;
             ctx[stg] = c;
         }
         if (tid < 32 * NC) {
@@ -189,11 +191,9 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
         const uint4* st = reinterpret_cast<const uint4*>(stage0 + (size_t)stage * stage_bytes);
         const int nY = (NC == 1) ? n : n * H * V;
         const int nblk = n * BPM;
-        for (int i = tid; i < nblk; i += 256) {
-            int slot, bxa;        // block index inside the stage; absolute component-x of the block
-            uint8_t* dst;
-            int pitch;
-            const uint32_t* q;
+        // block i of the tile: its slot in the stage, absolute component-x (swizzle key), destination in the
+        // plane tile and quantiser
+        auto locate = [&](int i, int& slot, int& bxa, uint8_t*& dst, int& pitch, const uint32_t*& q) {
             if (NC == 1) {
                 // gray: blocks of nr whole MCU rows, row-major
                 const int wt = (int)t.wt;
@@ -223,13 +223,31 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
                 pitch = PC;
                 q = qs_t + 32 * (1 + c);
             }
-            const uint4* blk = st + slot * 8;
-            const int key = bxa & 7;
-            uint32_t px[16];
-            dequant_idct_block_q8([&](int r) { return blk[r ^ key]; }, q, px);
+        };
+        if (!t.wide) {
+            for (int i = tid; i < nblk; i += 256) {
+                int slot, bxa, pitch;
+                uint8_t* dst;
+                const uint32_t* q;
+                locate(i, slot, bxa, dst, pitch, q);
+                const uint4* blk = st + slot * 8;
+                const int key = bxa & 7;
+                uint32_t px[16];
+                dequant_idct_block_q8([&](int r) { return blk[r ^ key]; }, q, px);
 #pragma unroll
-            for (int r = 0; r < 8; r++)
-                *reinterpret_cast<uint2*>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+                for (int r = 0; r < 8; r++)
+                    *reinterpret_cast<uint2*>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+            }
+        } else {
+            // the image has coefficients outside [-4096, 4095] (garbage streams only): rows whose AC are all zero the
+            // reference's way (zpx_idct.cuh)
+            for (int i = tid; i < nblk; i += 256) {
+                int slot, bxa, pitch;
+                uint8_t* dst;
+                const uint32_t* q;
+                locate(i, slot, bxa, dst, pitch, q);
+                idct_block_q8_exact(st + slot * 8, bxa & 7, q, dst, pitch);
+            }
         }
         __syncthreads();
 
@@ -391,7 +409,13 @@ __global__ void __launch_bounds__(128) k2g_idct_planes(const K2GParams P) {
     const uint4* __restrict__ src = reinterpret_cast<const uint4*>(P.coef) + blk * 8;
     const int key = bx & 7;
     uint32_t px[16];
-    dequant_idct_block([&](int r) { return __ldg(src + (r ^ key)); }, qsm[c], px);
+    if (im->recon_mask >> c & 1u) {
+        dequant_idct_block([&](int r) { return __ldg(src + (r ^ key)); }, qsm[c], px);
+    } else {
+        // no scan covers this component: the reference never reconstructs it and its plane keeps makeImg's zeros
+#pragma unroll
+        for (int k = 0; k < 16; k++) px[k] = 0;
+    }
     uint8_t* dst = P.planes + im->plane_off[c] + ((size_t)by * 8) * im->plane_stride[c] + (size_t)bx * 8;
 #pragma unroll
     for (int r = 0; r < 8; r++)

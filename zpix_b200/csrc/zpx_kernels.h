@@ -17,6 +17,9 @@ struct K1Params {
     const ZpxHuffDev* huff;
     uint4* coef;                  // 8 x uint4 per block
     unsigned long long* status;   // per image: smallest error key, ZPX_STATUS_NONE if none
+    uint32_t* img_flags;          // per image (status slot), zeroed before the decode: bit 0 = some coefficient of a
+                                  // sequential scan lies outside [-4096, 4095] (the fused IDCT then takes the
+                                  // reference's all-AC-zero row literally, zpx_idct.cuh)
     int lanes_per_warp;           // lane-per-interval kernel: 32 or 16 intervals per warp
 };
 cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s);
@@ -48,6 +51,7 @@ struct K2Params {
     const ZpxImageDev* imgs;
     const ZpxTileDev* tiles;
     const ZpxQuantDev* quant;
+    const uint32_t* img_flags;  // K1Params::img_flags
     int ntiles;
     int tmax;  // largest tile (MCUs): fixes the shared-memory layout
 };

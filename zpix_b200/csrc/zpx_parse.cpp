@@ -403,8 +403,13 @@ struct Parser {
                 case 0xc0:
                 case 0xc1:
                 case 0xc2:
-                    o.baseline = marker == 0xc0;
-                    o.progressive = marker == 0xc2;
+                    // (the reference sets these before processSof, decoder.zig:303-305; a second SOF then fails with
+                    // MultipleSofMarkers and nothing reads them again -- here the scans accepted so far are still
+                    // to be decoded, so a rejected SOF must not change how)
+                    if (o.ncomp == 0) {
+                        o.baseline = marker == 0xc0;
+                        o.progressive = marker == 0xc2;
+                    }
                     if (!process_sof(n)) return false;
                     if (config_only && o.jfif) return fail(ZPX_E_ConfigOnly);
                     break;
