@@ -21,6 +21,7 @@ ap.add_argument("--seeds", type=int, default=20)
 ap.add_argument("--first", type=int, default=0)
 ap.add_argument("--out", default="gpurun_out/fuzz")
 ap.add_argument("--mode", type=int, default=0)
+ap.add_argument("--synth", type=int, default=0, help="1: synthetic base files (other shapes, DRI, CMYK, YCbCrK) instead of the fixtures")
 a = ap.parse_args()
 os.makedirs(a.out, exist_ok=True)
 FX = os.path.join(ROOT, "tests", "golden", "ref_fixtures")
@@ -36,16 +37,29 @@ def entropy_damage(data, rng, n_trunc, n_flip):
     return out
 
 
+def bases():
+    if not a.synth:
+        return [open(os.path.join(FX, n), "rb").read() for n in sorted(os.listdir(FX)) if n != "iceberg.jpg"]
+    from tools import synth_jpeg as S
+    kw = [dict(subsampling="4:2:0"), dict(subsampling="4:2:0", restart_rows=1), dict(subsampling="4:2:0", restart_blocks=3),
+          dict(subsampling="4:2:2"), dict(subsampling="4:2:2", restart_blocks=5), dict(subsampling="4:4:4"),
+          dict(subsampling="4:4:4", restart_rows=1), dict(mode="L"), dict(mode="L", restart_blocks=4), dict(mode="CMYK"),
+          dict(mode="CMYK", ycck=True), dict(mode="CMYK", restart_rows=1), dict(subsampling="4:2:0", progressive=True),
+          dict(subsampling="4:2:0", progressive=True, restart_rows=1), dict(subsampling="4:4:4", progressive=True),
+          dict(mode="L", progressive=True), dict(mode="CMYK", progressive=True), dict(subsampling="4:2:0", quality=30),
+          dict(subsampling="4:2:0", quality=98), dict(subsampling="4:2:2", progressive=True, restart_blocks=7)]
+    sizes = [(211, 157), (97, 64), (320, 96), (33, 250)]
+    return [S.encode(70000 + i, *sizes[i % 4], **k) for i, k in enumerate(kw)]
+
+
+BASES = bases()
 ctx = jpeg.Context([0])
 ctx.set_option(1, a.mode)
 bad = total = 0
 for seed in range(a.first, a.first + a.seeds):
     rng = np.random.default_rng(900000 + seed)
     datas = []
-    for name in sorted(os.listdir(FX)):
-        if name == "iceberg.jpg":
-            continue
-        base = open(os.path.join(FX, name), "rb").read()
+    for base in BASES:
         datas += header_damage(base, rng, 20) + entropy_damage(base, rng, 4, 16)
     with jpeg.Batch(ctx, datas) as b:
         b.upload()

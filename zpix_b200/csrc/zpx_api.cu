@@ -633,7 +633,8 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         ks.s_in = (unsigned long long*)(sb + S * 16);
         ks.s_out = (unsigned long long*)(sb + S * 24);
         ks.s_n = (int*)(sb + S * 32);
-        ks.changed = (int*)(sb + S * 36);
+        ks.s_bad = (int*)(sb + S * 36);
+        ks.changed = (int*)(sb + S * 40);
         int* hflag = (int*)dc.hflag.p;
         // sweep 0 decodes every sub-sequence from its guess and settles each warp; later sweeps carry
         // end states across warp boundaries until nothing changes (exact fixed point)
@@ -1030,7 +1031,7 @@ int32_t zpx_batch_upload(zpx_batch* b) {
         for (size_t k = 0; k < pl.prog_lists.size(); k++)
             memcpy(hd + pl.prog_off[k], pl.prog_lists[k].data(), pl.prog_lists[k].size() * sizeof(uint32_t));
         if (pl.sub_mode) {
-            CU(ctx, dc.subs.ensure(align_up(pl.n_subs, 64) * 36 + 256));
+            CU(ctx, dc.subs.ensure(align_up(pl.n_subs, 64) * 40 + 256));
             CU(ctx, dc.hflag.ensure(64));
         }
         for (const FusedGroup& g : pl.groups) memcpy(hd + g.tiles_off, g.tiles.data(), g.tiles.size() * sizeof(ZpxTileDev));

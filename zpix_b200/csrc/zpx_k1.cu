@@ -290,6 +290,12 @@ struct K1Start {
     int dc0, dc1, dc2, dc3;  // DC predictors at that point
     uint32_t j0;      // ordinal (inside the interval) of the first block this lane writes
     uint32_t count;   // blocks this lane writes
+    // SUB: after its last block the lane also decodes the next DC symbol, writing nothing, and reports the error
+    // if there is one.  The synchronisation pass steps over invalid codes bit by bit; when that happens at a block
+    // start, the block it finally finds may start in a later sub-sequence, and no lane would ever decode the
+    // invalid code itself.  The lane that owns the preceding block does, here (reference: BadHuffmanCode at the
+    // block that follows, decoder.zig:947-969).
+    bool probe;
 };
 
 template <int NT, bool SMEM, bool SUB>
@@ -300,7 +306,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     const ZpxImageDev* __restrict__ im = &P.imgs[sc->img];
 
     FastReader br;
-    if (st.count != 0) {
+    if (st.count != 0 || (SUB && st.probe)) {
         br.init_bits(P.blob, iv.start, iv.len, st.bitpos);
     } else {  // idle lane: never reads
         br.base = reinterpret_cast<const uint32_t*>(P.blob);
@@ -335,7 +341,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     }
     // SUB: a lane that starts inside a block first runs that block's remaining AC symbols without storing
     // anything (phase: the one before block j0's)
-    bool tail = SUB && st.k != 0 && st.count != 0;
+    bool tail = SUB && st.k != 0 && (st.count != 0 || st.probe);
     const int c_first = c;
     if (tail) c = c == 0 ? nblk - 1 : c - 1;
     // bi: x = DC table (SMEM: shared address of its LUT slot; else table index), y = AC likewise,
@@ -347,7 +353,9 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     int dc0 = st.dc0, dc1 = st.dc1, dc2 = st.dc2, dc3 = st.dc3;
     uint32_t eob_run = 0;
     int wide = 0;  // max over the lane's symbols of (AC value bits, DC magnitude >> 8): >= 13 / >= 16 flags the image
-    uint32_t left = st.count;  // blocks still to decode (including the current one)
+    const bool probe = SUB && st.probe;
+    const uint32_t total = st.count + (probe ? 1u : 0u);
+    uint32_t left = total;  // blocks still to decode (including the current one and the probe)
 
     while (__any_sync(0xffffffffu, left != 0)) {
         int k = 64;  // > 63: no block in flight on this lane
@@ -383,6 +391,14 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
             else if (k == 1 && (bi.w & 0x20000u)) {
                 err = ZPX_E_UninitializedHuffmanTable;
                 k = 64;
+            }
+            if (SUB && probe && left == 1) {
+                // probe block: only the DC symbol counts, and only if it is an error (a valid one belongs to the
+                // next lane's block); nothing is stored
+                k = 64;
+                sts_u16(sb, 0);
+                if (err == ZPX_E_UninitializedHuffmanTable && !(bi.w & 0x10000u)) err = 0;
+                if (!err && !br.overrun()) left = 0;
             }
         }
         // ---- AC (decoder.zig:1383-1411): one symbol per lane per vote ----
@@ -436,7 +452,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 // a symbol that needed bits past the limit is the reference's MissingFF00 / UnexpectedEof,
                 // whatever the garbage decoded to
                 if (br.overrun()) err = (iv.flags & 1) ? ZPX_E_UnexpectedEof : ZPX_E_MissingFF00;
-                report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + st.j0 + (st.count - left), err);
+                report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + st.j0 + (total - left), err);
                 left = 0;
                 eob_run = 0;
             } else {
@@ -601,6 +617,7 @@ __global__ void __launch_bounds__(NT) k1_lane_per_interval(const K1Params P) {
     st.dc0 = st.dc1 = st.dc2 = st.dc3 = 0;
     st.j0 = 0;
     st.count = live ? iv.n_blocks : 0;
+    st.probe = false;
     k1_cta_run<NT, false>(P, iv, st);
 }
 
@@ -631,6 +648,8 @@ __global__ void __launch_bounds__(NT) k1s_write(const K1SParams P) {
     st.dc3 = dc.w;
     st.j0 = excl;
     st.count = valid && next > excl ? next - excl : 0;
+    // probe the symbol after the lane's last block if the lane skipped an invalid code and a block follows
+    st.probe = valid && P.s_bad[t] != 0 && st.j0 + st.count < iv.n_blocks;
     k1_cta_run<NT, true>(P.k1, iv, st);
 }
 

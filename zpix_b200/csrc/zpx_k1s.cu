@@ -83,7 +83,7 @@ struct CkStore {          // this lane's slots in shared memory, [3] strided by 
 
 template <bool CK>
 __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, const LaneCtx& L, unsigned long long in,
-                                                          unsigned mask, int& n_out, int4& dc_out,
+                                                          unsigned mask, int& n_out, int4& dc_out, int& bad_out,
                                                           unsigned long long old_out = 0, CkStore ck = CkStore{nullptr, nullptr, nullptr}) {
     const ZpxScanDev* __restrict__ sc = L.sc;
     // thresholds T_m = bnd - (3 - m) * step, m = 0..2, then the sub-sequence boundary itself (m == 3)
@@ -113,6 +113,9 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
     const uint32_t* __restrict__ fdc = P.huff[bi.x].fast;
     const uint32_t* __restrict__ fac = P.huff[bi.y].fast;
     bool go = true, merged = false;
+    int bad = 0;  // an invalid code was skipped (one bit further).  If this decode started in the true state, the
+                  // reference fails there; a skipped code at a block start is seen by no write-pass lane unless the
+                  // lane that owns the preceding block probes the symbol after it (k1s_write)
     while (__any_sync(mask, go)) {
         if (go) {
             const uint32_t u = br.used();
@@ -162,6 +165,7 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
                     const ZpxHuffDev* __restrict__ tab = reinterpret_cast<const ZpxHuffDev*>(ftab);
                     const HuffSym hs = huff_decode(tab, hi);
                     if (hs.len == 0) {
+                        bad = 1;
                         e = 1u;  // invalid: one bit further, same state (tot = 1, adv = 0)
                     } else if (isdc) {
                         const uint32_t size = hs.sym > 16 ? 0u : hs.sym;
@@ -204,6 +208,7 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
     }
     n_out = n;
     dc_out = make_int4(d0, d1, d2, d3);
+    bad_out = (CK && merged) ? (bad_out | bad) : bad;  // merged: the rest of the previous decode still counts
     if (CK && merged) return old_out;
     if (CK && use_ck)  // checkpoints this decode did not reach (data ran out) must not match later
         for (uint32_t q = m; q < 3; q++) ck.st[q * K1S_NT] = 0xffffffffu;
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int 
     const bool more_warps = w.first + 32 < L.iv->nsub;
 
     unsigned long long in = 0, out = 0, old_out = 0;
-    int n = 0;
+    int n = 0, bad = 0;
     int4 dc = make_int4(0, 0, 0, 0);
     bool dirty = false;
     if (sweep == 0) {
@@ -248,6 +253,7 @@ __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int 
             old_out = out;
             n = P.s_n[t];
             dc = P.s_dc[t];
+            bad = P.s_bad[t];
             if (lane == 0 && w.first > 0) {
                 const unsigned long long ni = P.s_out[t - 1];
                 if (ni != in) {
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int 
     do {
         const unsigned dm = __ballot_sync(0xffffffffu, dirty);
         if (dirty) {
-            out = sync_decode<true>(P.k1, L, in, dm, n, dc, out, ck);
+            out = sync_decode<true>(P.k1, L, in, dm, n, dc, bad, out, ck);
             touched = true;
         }
         const unsigned long long po = __shfl_up_sync(0xffffffffu, out, 1);
@@ -284,6 +290,7 @@ __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int 
         P.s_out[t] = out;
         P.s_n[t] = n;
         P.s_dc[t] = dc;
+        P.s_bad[t] = bad;
     }
     if (last_active && more_warps && (sweep == 0 || out != old_out)) atomicExch(P.changed, 1);
 }
@@ -314,13 +321,14 @@ __global__ void __launch_bounds__(K1S_NT) k1s_fix(const K1SParams P) {
     const unsigned dm = __ballot_sync(0xffffffffu, dirty);
     if (dm == 0) return;
     if (dirty) {
-        int n = 0;
+        int n = 0, bad = 0;
         int4 dc = make_int4(0, 0, 0, 0);
-        const unsigned long long out = sync_decode<false>(P.k1, L, in, dm, n, dc);
+        const unsigned long long out = sync_decode<false>(P.k1, L, in, dm, n, dc, bad);
         P.s_in[t] = in;
         P.s_out[t] = out;
         P.s_n[t] = n;
         P.s_dc[t] = dc;
+        P.s_bad[t] = bad;
         if (out != old_out && L.li + 1 < L.iv->nsub) atomicExch(P.changed, 1);
     }
 }

@@ -34,6 +34,8 @@ struct K1SParams {
     unsigned long long* s_out;  //                   state at its end boundary
     int* s_n;                   //                   blocks started inside it (then: exclusive prefix)
     int4* s_dc;                 //                   DC difference sums per component (then: exclusive prefix)
+    int* s_bad;                 //                   1: that decode skipped an invalid code (the write pass then probes
+                                //                   the symbol after the lane's last block, see k1s_write)
     int* changed;               // device flag: an end state crossing a warp boundary changed in this sweep
 };
 cudaError_t k1s_launch_sync(const K1SParams& P, int sweep, cudaStream_t s);
