@@ -130,7 +130,7 @@ __device__ __forceinline__ int extend32(uint32_t hi, int len, int size) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(K3_NT) k3_progressive(const K1Params P, const uint32_t* __restrict__ list, const int n_list) {
+__global__ void __launch_bounds__(K3_NT, 5) k3_progressive(const K1Params P, const uint32_t* __restrict__ list, const int n_list) {
     __shared__ __align__(16) WarpSm s_w[K3_WARPS];
     __shared__ uint8_t s_unzig[64];
     if (threadIdx.x < 64) s_unzig[threadIdx.x] = c_unzig[threadIdx.x];
