@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include <sched.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -23,11 +25,29 @@ using namespace zpx;
 // ---------------------------------------------------------------------------
 namespace {
 
+// CPUs this thread may run on (a rank bound to its GPU's NUMA node sees only those), and a per-thread cap for
+// code that already runs several such loops side by side (the chunk pipeline's workers)
+static size_t usable_cpus() {
+    // ZPX_HOST_THREADS: a budget set by whoever knows how many processes share the box (bench.py under torchrun)
+    if (const char* e = getenv("ZPX_HOST_THREADS")) {
+        const long v = atol(e);
+        if (v > 0) return (size_t)v;
+    }
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+        const int n = CPU_COUNT(&set);
+        if (n > 0) return (size_t)n;
+    }
+    const size_t hw = std::thread::hardware_concurrency();
+    return hw ? hw : 4;
+}
+static thread_local size_t t_par_limit = 0;  // 0 = no extra cap
+
 template <typename F>
 void parallel_for(size_t n, size_t min_chunk, F fn) {
-    size_t hw = std::thread::hardware_concurrency();
-    if (hw == 0) hw = 4;
+    size_t hw = usable_cpus();
     if (hw > 64) hw = 64;
+    if (t_par_limit && hw > t_par_limit) hw = t_par_limit;
     size_t nt = std::min(hw, (n + min_chunk - 1) / std::max<size_t>(min_chunk, 1));
     if (nt <= 1) {
         for (size_t i = 0; i < n; i++) fn(i);
@@ -1337,8 +1357,10 @@ int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const si
     std::vector<int32_t> rc((size_t)n_workers, 0);
     std::vector<int32_t> st(status ? 0 : n);
     int32_t* stp = status ? status : st.data();
+    const size_t par_each = std::max<size_t>(1, usable_cpus() / (size_t)n_workers);
     auto worker = [&](int w) {
         zpx_ctx* c = w == 0 ? ctx : ctx->shadows[(size_t)w - 1];
+        t_par_limit = par_each;  // the workers' parse / staging loops share the host cores
         for (;;) {
             const int32_t k = next.fetch_add(1);
             if (k >= n_chunks) break;
@@ -1353,6 +1375,7 @@ int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const si
     std::vector<std::thread> threads;
     for (int w = 1; w < n_workers; w++) threads.emplace_back(worker, w);
     worker(0);
+    t_par_limit = 0;
     for (std::thread& t : threads) t.join();
     int32_t ret = rc[0];
     for (int w = 1; w < n_workers; w++) {
