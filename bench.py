@@ -213,8 +213,6 @@ def main():
     dist = None
     numa_note = bind_to_gpu_numa(local)
     if world > 1:
-        # the ranks share the host cores: give each library instance its share for header parsing and staging
-        os.environ.setdefault("ZPX_HOST_THREADS", str(max(3, len(os.sched_getaffinity(0)) // world)))
         import torch.distributed as dist_mod
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
