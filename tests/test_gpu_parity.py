@@ -351,6 +351,28 @@ def test_eob_runs_in_sequential_scans(jpeg, ctx, fixtures_dir):
     _assert_same(jpeg, ctx, datas)
 
 
+def _multiscan_cases():
+    from tools.multiscan import recode
+    out = []
+    for seed, (w, h), kw in [(60000, (97, 75), dict(subsampling="4:2:0")), (60002, (130, 50), dict(subsampling="4:2:2")),
+                             (60004, (64, 64), dict(subsampling="4:4:4")), (60006, (83, 41), dict(mode="CMYK")),
+                             (60008, (640, 360), dict(subsampling="4:2:0"))]:
+        base = S.encode(seed, w, h, **kw)  # even seed: Annex K tables, complete
+        nc = 4 if kw.get("mode") == "CMYK" else 3
+        scripts = [([[c] for c in range(nc)], 0), ([[0], list(range(1, nc))], 0), ([[nc - 1], [0], *[[c] for c in range(1, nc - 1)]], 3),
+                   ([[0, 1], *[[c] for c in range(2, nc)]], 5), ([[c] for c in range(nc)], 1)]
+        out += [recode(base, sc, ri) for sc, ri in scripts]
+    return out
+
+
+def test_multi_scan_sequential_frames(jpeg, ctx):
+    """Sequential frames whose components arrive in separate scans (non-interleaved block order, restart
+    intervals counted in the scan's own MCU iterations; decoder.zig:1294-1336).  Pillow cannot write
+    them: tools/multiscan.py re-codes single-scan files.  These take the planar coefficient layout and the
+    unfused reconstruction kernels."""
+    _assert_same(jpeg, ctx, _multiscan_cases())
+
+
 def test_files_found_by_fuzzing(jpeg, ctx, golden_dir):
     """Regression files from tools/fuzz_hunt.py: garbage streams the reference still decodes.
     idct_dc_row_wrap_*: first-column values beyond 2^20, where the reference's all-AC-zero row shortcut (s0 << 3,

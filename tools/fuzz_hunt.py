@@ -49,7 +49,14 @@ def bases():
           dict(mode="L", progressive=True), dict(mode="CMYK", progressive=True), dict(subsampling="4:2:0", quality=30),
           dict(subsampling="4:2:0", quality=98), dict(subsampling="4:2:2", progressive=True, restart_blocks=7)]
     sizes = [(211, 157), (97, 64), (320, 96), (33, 250)]
-    return [S.encode(70000 + i, *sizes[i % 4], **k) for i, k in enumerate(kw)]
+    out = [S.encode(70000 + i, *sizes[i % 4], **k) for i, k in enumerate(kw)]
+    # sequential frames re-coded into several scans (tools/multiscan.py)
+    from tools.multiscan import recode
+    b420, b444 = S.encode(70100, 97, 75, subsampling="4:2:0"), S.encode(70102, 64, 48, subsampling="4:4:4")
+    bcmyk = S.encode(70104, 83, 41, mode="CMYK")
+    out += [recode(b420, [[0], [1], [2]], 0), recode(b420, [[0], [1, 2]], 4), recode(b444, [[2], [0], [1]], 3),
+            recode(b420, [[0, 1], [2]], 5), recode(bcmyk, [[0], [1], [2], [3]], 0), recode(bcmyk, [[0, 1], [2, 3]], 2)]
+    return out
 
 
 BASES = bases()
