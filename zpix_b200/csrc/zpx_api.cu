@@ -223,6 +223,7 @@ int unsupported_reason(const ZpxParsed& p) {
 
 bool fused_eligible(const ZpxParsed& p) {
     if (p.progressive || p.scans.size() != 1) return false;
+    if ((uint64_t)p.width * (uint64_t)p.height >= (1ull << 30)) return false;  // the fused kernel keeps 32-bit pixel offsets
     const ZpxScanHost& s = p.scans[0];
     if (p.ncomp == 1) return p.mode == ZPX_MODE_GRAY && s.ncomp == 1;
     if (p.ncomp != 3 || p.mode != ZPX_MODE_YCBCR || s.ncomp != 3) return false;

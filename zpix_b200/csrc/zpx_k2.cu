@@ -294,12 +294,14 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
                     }
 #pragma unroll
                     for (int k = 0; k < NCS; k++)
-                        chroma_terms((cbw[k >> 2] >> (8 * (k & 3))) & 0xff, (crw[k >> 2] >> (8 * (k & 3))) & 0xff, rr[k], gg[k], bb[k]);
+                        chroma_terms((int)__byte_perm(cbw[k >> 2], 0, 0x4440 + (k & 3)), (int)__byte_perm(crw[k >> 2], 0, 0x4440 + (k & 3)),
+                                     rr[k], gg[k], bb[k]);
                 }
 #pragma unroll
                 for (int r = 0; r < RP; r++) {
                     if (y + r >= Hh) break;
-                    uint8_t* o = outp + ((size_t)(y + r) * W + x) * 4;
+                    // 32-bit offset inside the image (fused images are below 2^30 pixels, zpx_api.cu)
+                    uint8_t* o = outp + ((uint32_t)(y + r) * (uint32_t)W + (uint32_t)x) * 4u;
 #pragma unroll
                     for (int g = 0; g < PXW / 4; g++) {
                         if (g > 0 && x + 4 * g >= W) break;
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
                         uint32_t p[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            const uint32_t yv = (yw >> (8 * j)) & 0xffu;
+                            const uint32_t yv = __byte_perm(yw, 0, 0x4440 + j);  // byte j, zero-extended: one PRMT
                             if (NC == 1) {
                                 p[j] = yv * 0x010101u | 0xff000000u;  // .gray: (Y,Y,Y,255), color.zig:122-126
                             } else {
