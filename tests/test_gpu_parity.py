@@ -450,6 +450,40 @@ def test_native_cmyk_variant(jpeg, fixtures_dir):
         assert c.toRGBA()[0] >> 8 == int(ref.rgbaPixels()[5, 3, 0])
 
 
+def test_gpu_resident_hand_off(jpeg, fixtures_dir):
+    """a consumer on the GPU takes the RGBA where the kernels left it (zpx_batch_device_rgba), on the
+    caller's own stream, with no device->host copy in between."""
+    import torch
+
+    class _Dev:  # __cuda_array_interface__ view of library-owned device memory
+        def __init__(self, ptr, h, w):
+            self.__cuda_array_interface__ = {"shape": (h, w, 4), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+    names = ["video-001.q50.420.jpeg", "video-005.gray.jpeg", "video-001.cmyk.jpeg", "video-001.progressive.jpeg"]
+    datas = [_read(fixtures_dir, n) for n in names]
+    c = jpeg.Context([0])
+    stream = torch.cuda.Stream()
+    with jpeg.Batch(c, datas) as b:
+        b.upload()
+        b.decode(stream.cuda_stream)  # asynchronous: the caller's stream orders decode and consumer
+        with torch.cuda.stream(stream):
+            views = []
+            for i in range(len(datas)):
+                inf = b.info(i)
+                ptr = b.device_rgba_ptr(i)
+                assert ptr != 0
+                views.append(torch.as_tensor(_Dev(ptr, inf.height, inf.width), device="cuda"))
+            sums = [int(v.sum(dtype=torch.int64)) for v in views]   # a reduction on the GPU, then 8 bytes per image
+            copies = [v.clone() for v in views]
+        stream.synchronize()
+        assert all(s == 0 for s in b.status())
+    for d, got, total in zip(datas, copies, sums):
+        want = O.decode(d).rgbaPixels()
+        assert np.array_equal(got.cpu().numpy(), want)
+        assert total == int(want.astype(np.int64).sum())
+    c.close()
+
+
 def test_dispatcher_routes_jpegs_to_the_batch_path(jpeg, fixtures_dir):
     """zpix.fromBuffer / fromBuffers (src/root.zig:24-40): probe, JPEG -> GPU path, anything else UnknownImageFormat."""
     import zpix_b200 as zpix
