@@ -450,6 +450,42 @@ def test_native_cmyk_variant(jpeg, fixtures_dir):
         assert c.toRGBA()[0] >> 8 == int(ref.rgbaPixels()[5, 3, 0])
 
 
+def test_batch_shapes_at_the_edges(jpeg, fixtures_dir):
+    """Empty batch, a batch with nothing decodable, thousands of tiny images (planner / tile-table limits), and a
+    context reused across batches of very different sizes."""
+    c = jpeg.Context([0])
+    outs, st = jpeg.decodeBatchOneCall([], c)
+    assert outs == [] and st == []
+    with jpeg.Batch(c, []) as b:
+        b.upload()
+        b.decode()
+        assert b.fetch_rgba() == ([], [])
+    junk = [b"", b"\xff\xd8", b"not a jpeg at all", b"\xff\xd8\xff\xd9"]
+    outs, st = jpeg.decodeBatchOneCall(junk, c)
+    assert all(o is None for o in outs) and all(s != 0 for s in st)
+    for d, s in zip(junk, st):
+        assert jpeg.lib.zpx_error_name(s).decode() == _oracle_rgba(d)[1]
+    tiny = [S.encode(53000 + i, 1 + i % 9, 1 + (i * 7) % 11, subsampling=["4:2:0", "4:4:4", "4:2:2"][i % 3]) for i in range(12)]
+    tiny += [S.encode(53100, 8, 8, mode="L"), S.encode(53101, 3, 17, mode="CMYK")]
+    want = [_oracle_rgba(d)[0] for d in tiny]
+    batch = [tiny[i % len(tiny)] for i in range(6000)]
+    for mode in (0, 1, 2):
+        c.set_option(1, mode)
+        with jpeg.Batch(c, batch) as b:
+            b.upload()
+            b.decode()
+            outs, st = b.fetch_rgba()
+        assert not any(st)
+        for i in range(0, 6000, 37):
+            assert np.array_equal(outs[i], want[i % len(tiny)]), (mode, i)
+    c.set_option(1, 0)
+    outs, st = jpeg.decodeBatchOneCall(batch[:3000], c)   # through the chunk pipeline as well
+    assert not any(st) and all(np.array_equal(outs[i], want[i % len(tiny)]) for i in range(0, 3000, 41))
+    big = _read(fixtures_dir, "iceberg.jpg")
+    _assert_same(jpeg, c, [big, tiny[0], big])
+    c.close()
+
+
 def test_gpu_resident_hand_off(jpeg, fixtures_dir):
     """a consumer on the GPU takes the RGBA where the kernels left it (zpx_batch_device_rgba), on the
     caller's own stream, with no device->host copy in between."""
