@@ -550,7 +550,20 @@ void build_plan(zpx_batch* b, int di) {
     // entropy mode: with enough restart intervals to fill the GPU, one lane per interval decodes each
     // once, serially; otherwise the self-synchronising decoder parallelises inside the intervals
     const int64_t mode = b->ctx->opt_entropy_mode;
-    pl.sub_mode = mode == 2 || (mode == 0 && pl.n_seq < 16384);
+    {
+        // auto: estimated time of either decoder (measured on B200, cfg2-like data).  One lane per interval is bound
+        // by its longest interval while there are few of them (about 2.3 MB/s per lane) and by instruction issue
+        // once the GPU is full (78 GB/s); the self-synchronising decoder parallelises inside intervals but decodes
+        // everything about twice (25-36 GB/s) and has a fixed cost of a few launches.
+        uint64_t total = 0, longest = 0;
+        for (size_t k = 0; k < pl.n_seq; k++) {
+            total += pl.ivs[k].len;
+            longest = std::max<uint64_t>(longest, pl.ivs[k].len);
+        }
+        const double lane_s = std::max((double)longest / 2.3e6, (double)total / 78e9);
+        const double sub_s = 0.3e-3 + (double)total / (total < (200u << 20) ? 25e9 : 36e9);
+        pl.sub_mode = mode == 2 || (mode == 0 && sub_s < lane_s);
+    }
     pl.n_sub_iv = 0;
     if (pl.sub_mode) {
         // lane-only intervals (End-Of-Band-run capable tables) to the back of the sequential range

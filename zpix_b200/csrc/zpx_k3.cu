@@ -565,12 +565,14 @@ __global__ void __launch_bounds__(K3_NT, 5) k3_progressive(const K1Params P, con
                 const uint32_t nlo = W.nzlo[k], nhi = W.nzhi[k], p0 = W.p0[k];
                 // bits of the symbols read before position z was passed = running maximum of cum[0..z]
                 uint32_t c0 = W.cum[k][lane], c1 = W.cum[k][lane + 32];
+                if (__any_sync(0xffffffffu, (c0 | c1) != 0)) {  // (a block inside an End-Of-Band run has no symbols)
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    c0 = max(c0, __shfl_up_sync(0xffffffffu, c0, d));   // lanes below d read themselves: no-op
-                    c1 = max(c1, __shfl_up_sync(0xffffffffu, c1, d));
+                    for (int d = 1; d < 32; d <<= 1) {
+                        c0 = max(c0, __shfl_up_sync(0xffffffffu, c0, d));   // lanes below d read themselves: no-op
+                        c1 = max(c1, __shfl_up_sync(0xffffffffu, c1, d));
+                    }
+                    c1 = max(c1, __shfl_sync(0xffffffffu, c0, 31));
                 }
-                c1 = max(c1, __shfl_sync(0xffffffffu, c0, 31));
                 if (nlo >> lane & 1u) {
                     const uint32_t bp = p0 + c0 + (uint32_t)__popc(nlo & lt);
                     if ((W.ring[(bp >> 5) & (K3_RW - 1)] << (bp & 31)) >> 31) {
