@@ -446,6 +446,14 @@ void build_plan(zpx_batch* b, int di) {
             sd.total_mcu = p.mxx * p.myy;
             sd.restart_interval = s.restart_interval;
             sd.scan_index = scan_index++;
+            // A sequential frame may code a component in more than one scan (only broken files do): the reference
+            // reconstructs every scan as it comes, so the last one wins.  Here all scans of an image decode side by
+            // side: the earlier ones are still decoded (their errors count) but do not store their blocks.
+            bool superseded[ZPX_MAX_COMP] = {false, false, false, false};
+            if (!p.progressive)
+                for (int i = 0; i < s.ncomp; i++)
+                    for (const ZpxScanHost* t = &s + 1; t <= &p.scans.back(); t++)
+                        for (int j = 0; j < t->ncomp; j++) superseded[i] = superseded[i] || t->comp[j] == s.comp[i];
             int nb = 0;
             for (int i = 0; i < s.ncomp; i++) {
                 const int c = s.comp[i];
@@ -462,7 +470,7 @@ void build_plan(zpx_batch* b, int di) {
                     sd.blk_pack[nb][2] = (uint32_t)c | (uint32_t)(j % p.h[c]) << 8 | (uint32_t)(j / p.h[c]) << 16 |
                                          (uint32_t)(im.blk_off[c] + j) << 24;
                     sd.blk_pack[nb][3] = (uint32_t)p.h[c] | (uint32_t)p.v[c] << 8 | (s.dc[i].defined ? 0u : 1u << 16) |
-                                         (s.ac[i].defined ? 0u : 1u << 17);
+                                         (s.ac[i].defined ? 0u : 1u << 17) | (superseded[i] ? 1u << 18 : 0u);
                     nb++;
                 }
             }

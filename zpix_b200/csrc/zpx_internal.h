@@ -107,7 +107,8 @@ struct ZpxScanDev {
     // the same, packed for one 16-byte load per block:
     //   x = DC table index, y = AC table index,
     //   z = comp | hx << 8 | vy << 16 | slot << 24,
-    //   w = h | v << 8 | (DC table undefined) << 16 | (AC table undefined) << 17
+    //   w = h | v << 8 | (DC table undefined) << 16 | (AC table undefined) << 17 |
+    //       (a later scan of the frame codes this component again: decode, do not store) << 18
     alignas(16) uint32_t blk_pack[ZPX_MAX_BLK_PER_MCU][4];
 };
 

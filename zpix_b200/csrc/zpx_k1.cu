@@ -475,10 +475,11 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 }
                 uint4* __restrict__ dst = P.coef + blk * 8;
                 const uint32_t key = bx & 7;
+                const bool keep = !(bi.w & 0x40000u);  // not superseded by a later scan of the same component
 #pragma unroll
                 for (uint32_t slot = 0; slot < 8; slot++) {
                     const uint32_t a = sb + (slot ^ key) * (NT * 16);
-                    dst[slot] = lds_v4(a);
+                    if (keep) dst[slot] = lds_v4(a);
                     sts_zero16(a);
                 }
                 left--;
