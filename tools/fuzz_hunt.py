@@ -21,6 +21,7 @@ ap.add_argument("--seeds", type=int, default=20)
 ap.add_argument("--first", type=int, default=0)
 ap.add_argument("--out", default="gpurun_out/fuzz")
 ap.add_argument("--mode", type=int, default=0)
+ap.add_argument("--structural", type=int, default=0, help="N more files per base with marker-level damage")
 ap.add_argument("--synth", type=int, default=0, help="1: synthetic base files (other shapes, DRI, CMYK, YCbCrK) instead of the fixtures")
 a = ap.parse_args()
 os.makedirs(a.out, exist_ok=True)
@@ -60,6 +61,43 @@ def bases():
 
 
 BASES = bases()
+def structural_damage(data, rng, count):
+    """Marker-level damage: stray / missing / renumbered RSTn, inserted and deleted bytes, a scan played twice,
+    a segment moved, a changed restart interval."""
+    first_sos = data.index(b"\xff\xda")
+    out = []
+    for _ in range(count):
+        d = bytearray(data)
+        op = int(rng.integers(0, 7))
+        k = int(rng.integers(first_sos + 14, max(first_sos + 15, len(d) - 2)))
+        if op == 0:      # stray restart marker
+            d[k:k] = bytes([0xFF, 0xD0 + int(rng.integers(0, 8))])
+        elif op == 1:    # delete a byte
+            del d[k]
+        elif op == 2:    # insert a byte
+            d.insert(k, int(rng.integers(0, 256)))
+        elif op == 3:    # renumber / remove an existing restart marker
+            rst = [i for i in range(first_sos, len(d) - 1) if d[i] == 0xFF and 0xD0 <= d[i + 1] <= 0xD7]
+            if rst:
+                i = rst[int(rng.integers(0, len(rst)))]
+                if rng.integers(0, 2):
+                    d[i + 1] = 0xD0 + int(rng.integers(0, 8))
+                else:
+                    del d[i:i + 2]
+        elif op == 4:    # the tail of the file (from a random scan on) played twice
+            sos = [i for i in range(len(d) - 1) if d[i] == 0xFF and d[i + 1] == 0xDA]
+            i = sos[int(rng.integers(0, len(sos)))]
+            d = d[:-2] + d[i:]
+        elif op == 5:    # junk before a marker
+            mk = [i for i in range(2, len(d) - 1) if d[i] == 0xFF and d[i + 1] in (0xC4, 0xDA, 0xDB, 0xD9)]
+            i = mk[int(rng.integers(0, len(mk)))]
+            d[i:i] = bytes(rng.integers(0, 255, int(rng.integers(1, 4))).astype("uint8"))
+        else:            # a DRI segment before the first scan
+            d[first_sos:first_sos] = bytes([0xFF, 0xDD, 0, 4, 0, int(rng.integers(0, 9))])
+        out.append(bytes(d))
+    return out
+
+
 ctx = jpeg.Context([0])
 ctx.set_option(1, a.mode)
 bad = total = 0
@@ -68,6 +106,8 @@ for seed in range(a.first, a.first + a.seeds):
     datas = []
     for base in BASES:
         datas += header_damage(base, rng, 20) + entropy_damage(base, rng, 4, 16)
+        if a.structural:
+            datas += structural_damage(base, rng, a.structural)
     with jpeg.Batch(ctx, datas) as b:
         b.upload()
         b.decode()
