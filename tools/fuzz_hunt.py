@@ -42,6 +42,13 @@ def bases():
     if not a.synth:
         return [open(os.path.join(FX, n), "rb").read() for n in sorted(os.listdir(FX)) if n != "iceberg.jpg"]
     from tools import synth_jpeg as S
+    if a.synth == 2:
+        # larger files: segments of several hundred sub-sequences (many warps per segment in the self-synchronising
+        # decoder, its boundary kernel and later sweeps), long restart intervals
+        kw2 = [dict(subsampling="4:2:0"), dict(subsampling="4:4:4"), dict(mode="L"), dict(mode="CMYK"),
+               dict(subsampling="4:2:0", restart_rows=8), dict(subsampling="4:2:2", restart_rows=3),
+               dict(subsampling="4:2:0", quality=97), dict(subsampling="4:2:0", progressive=True)]
+        return [S.encode(71000 + i, 640, 480, **k) for i, k in enumerate(kw2)]
     kw = [dict(subsampling="4:2:0"), dict(subsampling="4:2:0", restart_rows=1), dict(subsampling="4:2:0", restart_blocks=3),
           dict(subsampling="4:2:2"), dict(subsampling="4:2:2", restart_blocks=5), dict(subsampling="4:4:4"),
           dict(subsampling="4:4:4", restart_rows=1), dict(mode="L"), dict(mode="L", restart_blocks=4), dict(mode="CMYK"),
