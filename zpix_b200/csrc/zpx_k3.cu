@@ -234,23 +234,37 @@ __global__ void __launch_bounds__(K3_NT, 5) k3_progressive(const K1Params P, con
         key = bx & 7;
         return ((uint64_t)b.base + (uint64_t)by * b.bw + (uint64_t)bx) * 64;
     };
+    // the same for the k-th block after (bx0, by0) of a non-interleaved scan: blocks follow each other along the
+    // component's row (one division per batch instead of one per block)
+    auto block_addr_seq = [&](uint32_t bx0, uint32_t by0, uint32_t k, int& key) -> uint64_t {
+        uint32_t bx = bx0 + k, by = by0;
+        while (bx >= cw) {
+            bx -= cw;
+            by++;
+        }
+        const BlkPos b = W.pos[0];
+        key = (int)(bx & 7u);
+        return ((uint64_t)b.base + (uint64_t)by * b.bw + (uint64_t)bx) * 64;
+    };
     auto prefetch = [&](uint32_t j0) {
         pj0 = j0;
         pn = j0 < iv.n_blocks ? min((uint32_t)K3_BATCH, iv.n_blocks - j0) : 0;
+        const uint32_t q0 = iv.first_block + j0, by0 = interleaved ? 0 : q0 / cw, bx0 = interleaved ? 0 : q0 - by0 * cw;
 #pragma unroll
         for (int k = 0; k < K3_BATCH; k++) {
             if ((uint32_t)k < pn) {
                 int key;
-                const short* g = cbase + block_addr(j0 + k, key);
+                const short* g = cbase + (interleaved ? block_addr(j0 + k, key) : block_addr_seq(bx0, by0, (uint32_t)k, key));
                 pre[2 * k] = inb0 ? g[cslot(key, uz0)] : (short)0;
                 pre[2 * k + 1] = inb1 ? g[cslot(key, uz1)] : (short)0;
             }
         }
     };
     auto store_batch = [&]() {
+        const uint32_t q0 = iv.first_block + bj0, by0 = interleaved ? 0 : q0 / cw, bx0 = interleaved ? 0 : q0 - by0 * cw;
         for (uint32_t k = 0; k < bn; k++) {
             int key;
-            short* g = cbase + block_addr(bj0 + k, key);
+            short* g = cbase + (interleaved ? block_addr(bj0 + k, key) : block_addr_seq(bx0, by0, k, key));
             if (inb0) g[cslot(key, uz0)] = W.zz[k][lane];
             if (inb1) g[cslot(key, uz1)] = W.zz[k][lane + 32];
         }
@@ -329,8 +343,7 @@ __global__ void __launch_bounds__(K3_NT, 5) k3_progressive(const K1Params P, con
                     W.ncnt[k][lane + 32] = (uint8_t)(nzl + __popc(nhi & lt));
                     if (zlo >> lane & 1u) W.zl[k][__popc(zlo & lt)] = (uint8_t)lane;
                     if (zhi >> lane & 1u) W.zl[k][nzero_lo + __popc(zhi & lt)] = (uint8_t)(lane + 32);
-                    for (int i = lane; i < 80; i += 32)
-                        if (i >= nzero) W.zl[k][i] = 0xff;
+                    if (lane < 16) W.zl[k][nzero + lane] = 0xff;  // zl[zi + r] reads at most 15 past the last zero
                     W.cum[k][lane] = 0;
                     W.cum[k][lane + 32] = 0;
                     if (lane == 0) {
