@@ -409,11 +409,17 @@ def test_damaged_baseline_streams_match_oracle(jpeg, ctx, fixtures_dir):
 
 
 def test_native_variant_matches_reference_planes(jpeg, fixtures_dir):
-    """jpeg.load mirror (N2): .YCbCr / .Gray planes with makeImg's exact strides, on every block whose
-    origin is inside bounds (the reference's own `check`, decoder.zig:1803-1836)."""
-    for name in ["video-001.q50.420.jpeg", "video-001.q50.422.jpeg", "video-001.jpeg", "video-005.gray.jpeg",
-                 "video-001.221212.jpeg", "video-001.q50.411.jpeg"]:
-        data = _read(fixtures_dir, name)
+    """jpeg.load mirror (N2): .YCbCr / .Gray planes with makeImg's exact strides, whole planes including the MCU
+    padding (stricter than the reference's own `check`, decoder.zig:1803-1836, which looks at blocks whose origin is
+    inside bounds)."""
+    from tools.multiscan import recode
+    cases = [_read(fixtures_dir, name) for name in
+             ["video-001.q50.420.jpeg", "video-001.q50.422.jpeg", "video-001.jpeg", "video-005.gray.jpeg",
+              "video-001.221212.jpeg", "video-001.q50.411.jpeg", "video-001.q50.420.progressive.jpeg",
+              "video-001.progressive.jpeg", "video-005.gray.q50.progressive.jpeg"]]
+    # component scans of their own: blocks outside the image are never coded, the planes keep makeImg's zeros there
+    cases.append(recode(S.encode(60010, 97, 75, subsampling="4:2:0"), [[0], [1], [2]], 0))
+    for data in cases:
         ref = O.decode(data)
         img = jpeg.loadFromBuffer(data)
         assert img.tag == ref.variant_name
@@ -422,7 +428,7 @@ def test_native_variant_matches_reference_planes(jpeg, fixtures_dir):
         if img.tag == "Gray":
             got = img.Gray.pixels.reshape(-1, img.Gray.stride)
             assert img.Gray.stride == ref.stride
-            assert np.array_equal(got[: ref.height, : ref.width], ref.pix[: ref.height, : ref.width])
+            assert got.shape == ref.pix.shape and np.array_equal(got, ref.pix)  # MCU padding included
         else:
             m = img.YCbCr
             assert (m.y_stride, m.c_stride) == (ref.y_stride, ref.c_stride)

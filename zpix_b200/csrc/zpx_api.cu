@@ -291,8 +291,14 @@ void build_plan(zpx_batch* b, int di) {
         // component count over the scan's component list (entries past the scan's own count read as
         // component 0), and only allocated components are reconstructed (decoder.zig:1272-1279, :1644).
         im.recon_mask = 0;
+        // bits 4-7: the component is coded by some INTERLEAVED scan of a sequential frame, which visits every block
+        // of the MCU grid; a component that only has scans of its own is reconstructed where 8*bx < width and
+        // 8*by < height (decoder.zig:1331-1336) and keeps zeros in the rest of its padded plane
         for (const ZpxScanHost& sc : p.scans) {
-            for (int i = 0; i < sc.ncomp; i++) im.recon_mask |= 1u << sc.comp[i];
+            for (int i = 0; i < sc.ncomp; i++) {
+                im.recon_mask |= 1u << sc.comp[i];
+                if (sc.ncomp > 1) im.recon_mask |= 16u << sc.comp[i];
+            }
             if (p.progressive && sc.ncomp < p.ncomp) im.recon_mask |= 1u;
         }
         int bpm = 0;

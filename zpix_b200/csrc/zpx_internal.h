@@ -76,7 +76,9 @@ struct ZpxImageDev {
     int32_t plane_stride[4];
     int32_t plane_rows[4];
     uint32_t status_slot;     // index into the device status array
-    uint32_t recon_mask;      // bit c: component c is reconstructed (some scan covers it); the planes of the other
+    uint32_t recon_mask;      // bit 4+c: (sequential frames) some interleaved scan codes component c, i.e. every block
+                              // of its grid is reconstructed, not only those that touch the image;
+                              // bit c: component c is reconstructed (some scan covers it); the planes of the other
                               // components keep makeImg's zero fill (decoder.zig:1644, and reconstructBlock is
                               // only reached from scans)
 };

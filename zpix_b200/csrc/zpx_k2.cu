@@ -411,7 +411,10 @@ __global__ void __launch_bounds__(128) k2g_idct_planes(const K2GParams P) {
     const uint4* __restrict__ src = reinterpret_cast<const uint4*>(P.coef) + blk * 8;
     const int key = bx & 7;
     uint32_t px[16];
-    if (im->recon_mask >> c & 1u) {
+    bool recon = (im->recon_mask >> c & 1u) != 0;
+    // sequential frame, component without an interleaved scan: only blocks that touch the image were coded
+    if (!im->progressive && !(im->recon_mask >> (4 + c) & 1u) && (bx * 8 >= im->width || by * 8 >= im->height)) recon = false;
+    if (recon) {
         dequant_idct_block([&](int r) { return __ldg(src + (r ^ key)); }, qsm[c], px);
     } else {
         // no scan covers this component: the reference never reconstructs it and its plane keeps makeImg's zeros
