@@ -21,6 +21,7 @@ ap.add_argument("--seeds", type=int, default=20)
 ap.add_argument("--first", type=int, default=0)
 ap.add_argument("--out", default="gpurun_out/fuzz")
 ap.add_argument("--mode", type=int, default=0)
+ap.add_argument("--native", type=int, default=0, help="1: also compare the native variant (planes / interleave) byte for byte")
 ap.add_argument("--structural", type=int, default=0, help="N more files per base with marker-level damage")
 ap.add_argument("--synth", type=int, default=0, help="1: synthetic base files (other shapes, DRI, CMYK, YCbCrK) instead of the fixtures")
 a = ap.parse_args()
@@ -107,6 +108,8 @@ def structural_damage(data, rng, count):
 
 ctx = jpeg.Context([0])
 ctx.set_option(1, a.mode)
+if a.native:
+    ctx.set_option(2, 1)  # planes only exist on the unfused path
 bad = total = 0
 for seed in range(a.first, a.first + a.seeds):
     rng = np.random.default_rng(900000 + seed)
@@ -119,6 +122,7 @@ for seed in range(a.first, a.first + a.seeds):
         b.upload()
         b.decode()
         outs, st = b.fetch_rgba()
+        nats = b.fetch_native()[0] if a.native else None
     for i, d in enumerate(datas):
         total += 1
         try:
@@ -133,6 +137,10 @@ for seed in range(a.first, a.first + a.seeds):
         if err == "ReferencePanics" or (st[i] == 104 and ovf):
             continue
         ok = (got == err) if want is None else (st[i] == 0 and np.array_equal(outs[i], want))
+        if ok and want is not None and a.native:
+            ok = nats[i] is not None and np.array_equal(np.asarray(nats[i]).reshape(-1), np.asarray(img.pixels).reshape(-1))
+            if not ok:
+                got = "native variant differs"
         if not ok:
             bad += 1
             p = os.path.join(a.out, f"seed{seed}_case{i}.jpg")
