@@ -391,7 +391,7 @@ void build_plan(zpx_batch* b, int di) {
                 it = group_ix.emplace(key, (int)pl.groups.size() - 1).first;
             }
             FusedGroup& g = pl.groups[it->second];
-            const int tcap = std::max(1, 256 / bpm);
+            const int tcap = std::max(1, k2_fused_threads(p.h[0], p.v[0], nc) / bpm);
             const int per_row = (p.mxx + tcap - 1) / tcap;
             const int tn = (p.mxx + per_row - 1) / per_row;
             g.tmax = std::max(g.tmax, tn);
@@ -730,7 +730,7 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         k2.img_flags = img_flags;
         k2.ntiles = (int)g.tiles.size();
         k2.tmax = g.tmax;
-        const int grid = std::min<int>(k2.ntiles, dc.sm_count * 2);
+        const int grid = std::min<int>(k2.ntiles, dc.sm_count * (512 / k2_fused_threads(g.h, g.v, g.nc)));
         CU(ctx, k2_launch_fused(g.h, g.v, g.nc, k2, grid, st));
         k2_launches++;
     }

@@ -84,8 +84,8 @@ struct K2Cfg {
     }
 };
 
-template <int H, int V, int NC, int NS>
-__global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
+template <int H, int V, int NC, int NS, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
     using Cfg = K2Cfg<H, V, NC>;
     constexpr int BPM = Cfg::BPM;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
             }
         };
         if (!t.wide) {
-            for (int i = tid; i < nblk; i += 256) {
+            for (int i = tid; i < nblk; i += NT) {
                 int slot, bxa, pitch;
                 uint8_t* dst;
                 const uint32_t* q;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
         } else {
             // the image has coefficients outside [-4096, 4095] (garbage streams only): rows whose AC are all zero the
             // reference's way (zpx_idct.cuh)
-            for (int i = tid; i < nblk; i += 256) {
+            for (int i = tid; i < nblk; i += NT) {
                 int slot, bxa, pitch;
                 uint8_t* dst;
                 const uint32_t* q;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
             const uint32_t magic = ipr > 1 ? 0xffffffffu / (uint32_t)ipr + 1u : 0u;  // exact it/ipr for it, ipr < 2^16
             uint8_t* __restrict__ outp = P.out + t.out_off;
             const bool vec_ok = (W & 3) == 0;
-            for (int it = tid; it < items; it += 256) {
+            for (int it = tid; it < items; it += NT) {
                 const int rp = ipr > 1 ? (int)__umulhi((uint32_t)it, magic) : it;
                 const int xg = it - rp * ipr;
                 const int row0 = rp * RP;
@@ -336,22 +336,23 @@ __global__ void __launch_bounds__(256, 2) k2_fused(const K2Params P) {
     }
 }
 
-template <int H, int V, int NC, int NS>
+template <int H, int V, int NC, int NS, int NT>
 static cudaError_t launch_fused_ns(const K2Params& P, int grid, cudaStream_t s) {
     using Cfg = K2Cfg<H, V, NC>;
     const size_t smem = Cfg::smem_bytes(P.tmax, NS);
-    cudaError_t e = cudaFuncSetAttribute(k2_fused<H, V, NC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k2_fused<H, V, NC, NS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k2_fused<H, V, NC, NS><<<grid, 256, smem, s>>>(P);
+    k2_fused<H, V, NC, NS, NT><<<grid, NT, smem, s>>>(P);
     return cudaGetLastError();
 }
 
-// three stages when two CTAs of that size still fit one SM (227 KB), else two
+// three stages when all resident CTAs of that size still fit one SM (227 KB), else two
 template <int H, int V, int NC>
 static cudaError_t launch_fused_t(const K2Params& P, int grid, cudaStream_t s) {
     using Cfg = K2Cfg<H, V, NC>;
-    if (2 * (Cfg::smem_bytes(P.tmax, 3) + 1024) <= 227 * 1024) return launch_fused_ns<H, V, NC, 3>(P, grid, s);
-    return launch_fused_ns<H, V, NC, 2>(P, grid, s);
+    constexpr int NT = (NC == 3 && H == 2 && V == 2) ? 256 : 128;  // == k2_fused_threads(H, V, NC)
+    if ((512 / NT) * (Cfg::smem_bytes(P.tmax, 3) + 1024) <= 227 * 1024) return launch_fused_ns<H, V, NC, 3, NT>(P, grid, s);
+    return launch_fused_ns<H, V, NC, 2, NT>(P, grid, s);
 }
 
 int k2_fused_bpm(int h, int v, int nc) { return nc == 1 ? 1 : h * v + 2; }

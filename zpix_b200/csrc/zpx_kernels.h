@@ -47,6 +47,11 @@ cudaError_t k1s_launch_write(const K1SParams& P, cudaStream_t s);
 cudaError_t k3_launch_progressive(const K1Params& P, const uint32_t* list, int n_list, cudaStream_t s);
 
 // ---- K2: fused dequant + IDCT + upsample + colour ------------------------------
+// Threads per CTA of the fused kernel (= blocks a tile can hold) for a sampling; 512 / threads CTAs are resident
+// per SM.  Measured on B200: 4:2:0 is 1 % faster with 256-thread CTAs (tiles of 40 MCUs fill 240 of them), every
+// other sampling 4-9 % faster with 128 (4:2:2 3.69 -> 3.84 TB/s, gray + 4:4:4 512x512 3.30 -> 3.62 TB/s).
+static inline int k2_fused_threads(int h, int v, int nc) { return (nc == 3 && h == 2 && v == 2) ? 256 : 128; }
+
 struct K2Params {
     const int16_t* coef;
     uint8_t* out;
