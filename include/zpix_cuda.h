@@ -244,7 +244,6 @@ int32_t zpx_partition(const uint64_t *weights, int32_t n, int32_t n_devices, int
 #define ZPX_OPT_ENTROPY_MODE 1  /* 0 auto, 1 lane-per-interval, 2 warp-per-interval/subsequence */
 #define ZPX_OPT_FORCE_GENERIC 2 /* 1: always use the unfused planar IDCT + colour kernels */
 #define ZPX_OPT_SUBSEQ_BYTES 3  /* sub-sequence size of the self-synchronising decoder */
-#define ZPX_OPT_LANES_PER_WARP 5 /* lane-per-interval entropy kernel: intervals per warp, 32 (default) or 16 */
 #define ZPX_OPT_PIPELINE_CHUNK 4 /* images per chunk of zpx_decode_batch_rgba's copy/compute pipeline (0 = auto: about
                                     28 MB of compressed input per chunk; < 0 = off) */
 #define ZPX_OPT_PIPELINE_RAMP 6  /* 1 (default): the pipeline's first two chunks are 1/4 and 1/2 of the chunk size */

@@ -22,7 +22,6 @@ ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--generic", type=int, default=0)
 ap.add_argument("--emode", type=int, default=0)
 ap.add_argument("--subb", type=int, default=0)
-ap.add_argument("--lpw", type=int, default=0)
 ap.add_argument("--prog", type=int, default=0)
 a = ap.parse_args()
 
@@ -43,7 +42,6 @@ if a.generic:
     ctx.set_option(2, 1)
 ctx.set_option(1, a.emode)
 ctx.set_option(3, a.subb)
-ctx.set_option(5, a.lpw)
 t = time.time()
 b = jpeg.Batch(ctx, datas)
 t1 = time.time()

@@ -116,7 +116,7 @@ struct DeviceCtx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr};
-    DevBuf blob, coef, out, planes, desc, status, subs, scratch;
+    DevBuf blob, ublob, coef, out, planes, desc, status, subs, scratch;
     HostBuf stage, hdesc, hstatus, hflag;
 };
 
@@ -146,6 +146,8 @@ struct DevicePlan {
                                                      // of the sequential ones one lane per interval
     std::vector<uint8_t> iv_lane_only;               // per sequential interval (build time only)
     std::vector<ZpxWarpDev> warps;  // self-synchronising mode: one entry per warp
+    std::vector<ZpxSegDev> segs;    // pieces of the sequential intervals for the unstuffing kernel
+    size_t ublob_bytes = 0, off_segs = 0;
     size_t n_subs = 0;
     bool sub_mode = false;
     size_t off_warps = 0;
@@ -170,7 +172,7 @@ struct zpx_ctx {
     int last_cuda = 0;
     std::string last_cuda_str;
     std::atomic<uint64_t> launches{0};
-    int64_t opt_entropy_mode = 0, opt_force_generic = 0, opt_subseq = 0, opt_pipeline_chunk = 0, opt_lanes_per_warp = 0;
+    int64_t opt_entropy_mode = 0, opt_force_generic = 0, opt_subseq = 0, opt_pipeline_chunk = 0;
     int64_t opt_pipeline_ramp = 1, opt_pipeline_workers = 3;
     bool busy = false;
     const zpx_batch* resident = nullptr;  // the batch whose data currently occupies the device buffers
@@ -538,8 +540,25 @@ void build_plan(zpx_batch* b, int di) {
                     d.first_block = (uint32_t)coded_before(x0);
                     d.n_blocks = (uint32_t)(coded_before(x1) - coded_before(x0));
                 }
-                d.sub_first = d.nsub = d.sub_bytes = d.pad0 = 0;
-                if (!p.progressive) pl.iv_lane_only.push_back(eob_capable ? 1 : 0);
+                d.sub_first = d.nsub = d.sub_bytes = 0;
+                d.ulen = 0;
+                d.ustart = 0;
+                if (!p.progressive) {
+                    // the interval's place in the unstuffed blob and the pieces k0_unstuff works on
+                    d.ulen = d.len - iv.n_stuffed;
+                    d.ustart = pl.ublob_bytes;
+                    pl.ublob_bytes += align_up(d.ulen, 16);
+                    for (uint32_t q = 0; q < iv.n_segs; q++) {
+                        const ZpxSegHost& sh = s.segs[iv.seg_first + q];
+                        ZpxSegDev sgd;
+                        sgd.src = dst0 + (sh.src - src0);
+                        sgd.dst = d.ustart + sh.uoff;
+                        sgd.len = sh.len;
+                        sgd.flags = q + 1 == iv.n_segs ? 1u : 0u;
+                        pl.segs.push_back(sgd);
+                    }
+                    pl.iv_lane_only.push_back(eob_capable ? 1 : 0);
+                }
                 if (p.progressive) {
                     const size_t lv = (size_t)level[sd.scan_index];
                     if (pl.prog_lists.size() <= lv) pl.prog_lists.resize(lv + 1);
@@ -589,7 +608,7 @@ void build_plan(zpx_batch* b, int di) {
         const uint32_t submax = b->ctx->opt_subseq > 0 ? (uint32_t)align_up((size_t)b->ctx->opt_subseq, 4) : 256u;
         for (size_t k = 0; k < pl.n_sub_iv; k++) {
             ZpxIntervalDev& d = pl.ivs[k];
-            const uint32_t span = (uint32_t)(d.start & 3) + d.len;
+            const uint32_t span = d.ulen;
             uint32_t sub = (uint32_t)align_up((span + 31) / 32, 4);
             sub = std::max(32u, std::min(submax, sub));
             d.sub_bytes = sub;
@@ -613,6 +632,7 @@ void build_plan(zpx_batch* b, int di) {
     pl.off_quant = place(pl.quant.size() * sizeof(ZpxQuantDev));
     pl.off_generic = place(pl.generic.size() * sizeof(uint32_t));
     pl.off_warps = place(pl.warps.size() * sizeof(ZpxWarpDev));
+    pl.off_segs = place(pl.segs.size() * sizeof(ZpxSegDev));
     pl.prog_off.clear();
     for (auto& l : pl.prog_lists) pl.prog_off.push_back(place(l.size() * sizeof(uint32_t)));
     for (FusedGroup& g : pl.groups) g.tiles_off = place(g.tiles.size() * sizeof(ZpxTileDev));
@@ -647,6 +667,7 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
     // ---- K1: entropy decode ----
     K1Params k1;
     k1.blob = (const uint8_t*)dc.blob.p;
+    k1.ublob = (const uint8_t*)dc.ublob.p;
     k1.ivs = (const ZpxIntervalDev*)(desc + pl.off_ivs);
     k1.n_iv = (int)pl.n_seq;
     k1.scans = (const ZpxScanDev*)(desc + pl.off_scans);
@@ -655,7 +676,10 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
     k1.coef = (uint4*)dc.coef.p;
     k1.status = (unsigned long long*)dc.status.p;
     k1.img_flags = img_flags;
-    k1.lanes_per_warp = ctx->opt_lanes_per_warp == 16 ? 16 : 32;
+    if (!pl.segs.empty()) {
+        CU(ctx, k0_launch_unstuff(k1.blob, (uint8_t*)dc.ublob.p, (const ZpxSegDev*)(desc + pl.off_segs), (int)pl.segs.size(), st));
+        k1_launches++;
+    }
     if (k1.n_iv > 0 && !pl.sub_mode) {
         CU(ctx, k1_launch_lane_per_interval(k1, st));
         k1_launches++;
@@ -930,6 +954,7 @@ void zpx_ctx_destroy(zpx_ctx* c) {
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
         d.blob.release();
+        d.ublob.release();
         d.coef.release();
         d.out.release();
         d.planes.release();
@@ -965,7 +990,6 @@ int32_t zpx_ctx_set_option(zpx_ctx* c, int32_t option, int64_t value) {
             if (value < 1 || value > 8) return ZPX_E_INVALID_ARG;
             c->opt_pipeline_workers = value;
             return ZPX_OK;
-        case ZPX_OPT_LANES_PER_WARP: c->opt_lanes_per_warp = value; return ZPX_OK;
     }
     return ZPX_E_INVALID_ARG;
 }
@@ -1059,6 +1083,7 @@ int32_t zpx_batch_upload(zpx_batch* b) {
         DeviceCtx& dc = ctx->devs[di];
         CU(ctx, cudaSetDevice(dc.dev));
         CU(ctx, dc.blob.ensure(pl.blob_bytes + 64));
+        if (pl.ublob_bytes) CU(ctx, dc.ublob.ensure(pl.ublob_bytes + 256));
         CU(ctx, dc.coef.ensure(pl.coef_blocks * 128 + 256));
         CU(ctx, dc.out.ensure(pl.out_bytes + 256));
         if (pl.plane_bytes) CU(ctx, dc.planes.ensure(pl.plane_bytes + 256));
@@ -1076,6 +1101,7 @@ int32_t zpx_batch_upload(zpx_batch* b) {
         memcpy(hd + pl.off_quant, pl.quant.data(), pl.quant.size() * sizeof(ZpxQuantDev));
         memcpy(hd + pl.off_generic, pl.generic.data(), pl.generic.size() * sizeof(uint32_t));
         memcpy(hd + pl.off_warps, pl.warps.data(), pl.warps.size() * sizeof(ZpxWarpDev));
+        memcpy(hd + pl.off_segs, pl.segs.data(), pl.segs.size() * sizeof(ZpxSegDev));
         for (size_t k = 0; k < pl.prog_lists.size(); k++)
             memcpy(hd + pl.prog_off[k], pl.prog_lists[k].data(), pl.prog_lists[k].size() * sizeof(uint32_t));
         if (pl.sub_mode) {
@@ -1367,7 +1393,6 @@ int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const si
         sh->opt_entropy_mode = ctx->opt_entropy_mode;
         sh->opt_force_generic = ctx->opt_force_generic;
         sh->opt_subseq = ctx->opt_subseq;
-        sh->opt_lanes_per_warp = ctx->opt_lanes_per_warp;
     }
     // chunk list: the first two chunks are a quarter and a half of the regular size, so that the first
     // device->host copy starts early (the pipeline is bound by that copy; its fill time is pure loss)

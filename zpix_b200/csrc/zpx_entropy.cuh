@@ -1,7 +1,7 @@
 // zpx_entropy.cuh -- device code shared by the entropy kernels (zpx_k1.cu, zpx_k1s.cu, zpx_k3.cu):
-// stuffed-stream bit reader with position tracking, Huffman symbol decode, RECEIVE/EXTEND, error report.
-// Reference semantics: src/jpeg/decoder.zig:712-749 (readByteStuffedByte), :909-1022
-// (decodeHuffman, ensureNBits, decodeBit(s)), :1115-1134 (receiveExtend).
+// zig-zag table, canonical Huffman symbol decode from the tables in HBM, RECEIVE/EXTEND, error report.
+// Reference semantics: src/jpeg/decoder.zig:909-1022 (decodeHuffman, ensureNBits, decodeBit(s)),
+// :1115-1134 (receiveExtend).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -14,161 +14,6 @@ __constant__ uint8_t c_unzig[64] = {
     0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
     41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
     30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63,
-};
-
-// ---------------------------------------------------------------------------
-// bit reader over [start, start+len) of the stuffed stream
-// ---------------------------------------------------------------------------
-struct BitReader {
-    const uint32_t* words;  // 4-byte aligned base covering the range
-    uint32_t widx;          // next word to feed
-    uint32_t nextw;         // words[widx], loaded one refill ahead so its latency overlaps decoding
-    uint32_t first;         // byte offset (relative to words) of the first valid byte
-    uint32_t end;           // byte offset (relative to words) one past the last valid byte
-    uint64_t buf;           // unread bits, left aligned
-    int cnt;                // number of bits in buf (real + zero padding)
-    uint32_t fed;           // real data bits fed into buf so far
-    uint32_t pad;           // zero padding bits fed after the data ran out
-    uint32_t skip;          // the next byte is the 0x00 of an FF 00 pair
-    // sub-sequence boundary tracking (self-synchronising decoder): B = data bits fed before the
-    // feed position reached byte offset bnd (a multiple of 4)
-    uint32_t bnd;
-    uint32_t B;
-    uint32_t bpassed;
-
-    __device__ __forceinline__ void init(const uint8_t* blob, uint64_t start, uint32_t len) {
-        const uint64_t a = start & ~(uint64_t)3;
-        words = reinterpret_cast<const uint32_t*>(blob + a);
-        first = (uint32_t)(start - a);
-        end = first + len;
-        widx = 0;
-        buf = 0;
-        cnt = 0;
-        fed = 0;
-        pad = 0;
-        skip = 0;
-        bnd = 0xffffffffu;
-        B = 0;
-        bpassed = 0;
-        nextw = __ldg(words);
-        fill();
-    }
-
-    // start at raw bit position `bitpos` (relative to `w`), which must lie in a data byte;
-    // bytes before it are ignored.  end_off: byte offset of the limit.  boundary: see bnd.
-    __device__ __forceinline__ void init_at(const uint32_t* w, uint32_t bitpos, uint32_t end_off, uint32_t boundary) {
-        words = w;
-        first = bitpos >> 3;
-        end = end_off;
-        widx = first >> 2;
-        buf = 0;
-        cnt = 0;
-        fed = 0;
-        pad = 0;
-        skip = 0;
-        bnd = boundary;
-        B = 0;
-        bpassed = 0;
-        nextw = __ldg(words + widx);
-        fill();
-        consume((int)(bitpos & 7));
-    }
-
-    // raw bit position (relative to words) of the next unread bit.  Walks back over the buffered
-    // data bytes; an FF 00 pair counts as one data byte.  Deterministic for any input; exact
-    // whenever the reader started on a data byte of a well-formed stream.
-    __device__ __forceinline__ uint32_t rawpos() const {
-        const uint8_t* raw = reinterpret_cast<const uint8_t*>(words);
-        uint32_t e = widx * 4;
-        if (e > end) e = end;
-        const uint32_t u = used();
-        if (u > fed) return end * 8 + (u - fed);          // overran the data: past-the-end marker
-        const uint32_t real = fed - u;                    // data bits fed but not yet consumed
-        if (real == 0) return (e + skip) * 8;
-        const uint32_t nbytes = (real + 7) >> 3;
-        const uint32_t headbits = real - 8 * (nbytes - 1);  // unread bits of the head byte, 1..8
-        uint32_t r = e;
-        for (uint32_t k = 0; k < nbytes; k++) {
-            r -= 1;
-            if (r > first && raw[r] == 0x00 && raw[r - 1] == 0xff) r -= 1;
-        }
-        return r * 8 + (8 - headbits);
-    }
-
-    // bits consumed so far
-    __device__ __forceinline__ uint32_t used() const { return fed + pad - (uint32_t)cnt; }
-    // true if a symbol needed bits the stream does not have
-    __device__ __forceinline__ bool overrun() const { return used() > fed; }
-
-    // append up to one word, byte by byte (range edges, FF 00 pairs, zeros past the limit)
-    __device__ __forceinline__ void fill_once() {
-        const uint32_t off = widx * 4;
-        if (off >= bnd && !bpassed) {
-            bpassed = 1;
-            B = fed;
-        }
-        if (off >= end) {  // past the limit: zeros
-            cnt += 32;
-            pad += 32;
-            return;
-        }
-        const uint32_t raw = nextw;
-        widx++;
-        nextw = __ldg(words + widx);  // at most one word past the limit: the blob is padded
-        const uint32_t be = __byte_perm(raw, 0, 0x0123);
-        uint32_t acc = 0;
-        int nb = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t o = off + j;
-            const uint32_t b = (be >> (24 - 8 * j)) & 0xffu;
-            if (o < first || o >= end) continue;
-            if (skip) {  // the stuffed 0x00
-                skip = 0;
-                continue;
-            }
-            acc = (acc << 8) | b;
-            nb++;
-            if (b == 0xffu) skip = 1;
-        }
-        if (nb) {
-            const uint32_t w = acc << (32 - 8 * nb);
-            buf |= ((uint64_t)w << 32) >> cnt;
-            cnt += 8 * nb;
-            fed += 8 * nb;
-        }
-    }
-    // make sure more than 32 bits are buffered.  Common case (a whole word of data without 0xFF) is
-    // straight-line code; the next word is loaded by a predicated load straight into nextw's register,
-    // so nothing waits for it until the next refill.
-    __device__ __forceinline__ void fill() {
-        const bool need = cnt <= 32;
-        const uint32_t off = widx * 4;
-        const uint32_t raw = nextw;
-        const uint32_t nff = ~raw;
-        const uint32_t hasff = (nff - 0x01010101u) & raw & 0x80808080u;
-        const bool fast = need && (hasff | skip) == 0 && off >= first && off + 4 <= end && (bpassed || off < bnd);
-        if (fast) {
-            buf |= ((uint64_t)__byte_perm(raw, 0, 0x0123) << 32) >> cnt;
-            cnt += 32;
-            fed += 32;
-            widx++;
-        }
-        {
-            const uint32_t* p = words + widx;
-            asm volatile(
-                "{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p ld.global.nc.u32 %0, [%1];\n}\n"
-                : "+r"(nextw)
-                : "l"(p), "r"((uint32_t)fast));
-        }
-        if (need && !fast)
-            while (cnt <= 32) fill_once();
-    }
-    __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(buf >> 32); }
-    __device__ __forceinline__ void consume(int n) {
-        buf <<= n;
-        cnt -= n;
-    }
 };
 
 struct HuffSym {

@@ -127,12 +127,23 @@ struct ZpxIntervalDev {
                          // bit1: last interval of a scan that is not the image's last scan
     uint32_t first_block;  // ordinal (inside the scan) of the interval's first coded block
     uint32_t n_blocks;     // coded blocks in this interval
-    // self-synchronising mode: the interval is cut into nsub sub-sequences of sub_bytes raw bytes,
-    // boundaries at multiples of sub_bytes from (start & ~3); their state lives at sub_first + i
+    // self-synchronising mode: the interval is cut into nsub sub-sequences of sub_bytes UNSTUFFED bytes,
+    // boundaries at multiples of sub_bytes from ustart; their state lives at sub_first + i
     uint32_t sub_first;
     uint32_t nsub;
     uint32_t sub_bytes;
-    uint32_t pad0;
+    // sequential scans: the interval's bytes with the stuffing removed (FF 00 -> FF; k0_unstuff, zpx_k0.cu) live at
+    // ustart (16-byte aligned) in the unstuffed blob, ulen bytes, zeros up to the next 16-byte boundary
+    uint32_t ulen;
+    uint64_t ustart;
+};
+
+// One unit of work of k0_unstuff: a run of raw bytes of one interval that does not split an FF 00 pair
+struct ZpxSegDev {
+    uint64_t src;    // byte offset in the raw blob
+    uint64_t dst;    // byte offset in the unstuffed blob
+    uint32_t len;    // raw bytes
+    uint32_t flags;  // bit 0: last segment of its interval (zero fill up to the next 16-byte boundary)
 };
 
 // one warp of the self-synchronising decoder: 32 consecutive sub-sequences of one interval
@@ -169,6 +180,16 @@ struct ZpxIntervalHost {
     size_t limit;   // offset of the limit (first 0xFF followed by a byte != 0x00, or file end)
     uint32_t first_mcu, n_mcu;
     bool eof_limit;
+    uint32_t n_stuffed = 0;              // FF 00 pairs inside [start, limit): unstuffed length = limit - start - n_stuffed
+    uint32_t seg_first = 0, n_segs = 0;  // its pieces in ZpxScanHost::segs
+};
+
+// a piece of an interval for the unstuffing kernel: [src, src + len) of the file holds whole FF 00 pairs only
+#define ZPX_SEG_BYTES 4096
+struct ZpxSegHost {
+    size_t src;      // offset in the source file
+    uint32_t len;    // raw bytes
+    uint32_t uoff;   // unstuffed bytes of the interval before this piece
 };
 
 struct ZpxScanHost {
@@ -180,6 +201,7 @@ struct ZpxScanHost {
     ZpxHuffHost dc[ZPX_MAX_COMP], ac[ZPX_MAX_COMP];  // snapshot of the tables this scan uses
     int32_t quant[ZPX_MAX_COMP][64];                 // snapshot of quant[tq] (zig-zag order) per scan component
     std::vector<ZpxIntervalHost> intervals;
+    std::vector<ZpxSegHost> segs;  // sequential scans only
     // error the reference raises after `err_after_interval` intervals decoded fine (findRst / EOF)
     int pending_err = 0;
     int err_after_interval = -1;

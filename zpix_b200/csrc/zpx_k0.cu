@@ -1,0 +1,104 @@
+// zpx_k0.cu -- byte-stuffing removal for the sequential entropy kernels.
+//
+// Replaces readByteStuffedByte / unreadByteStuffedByte (src/jpeg/decoder.zig:712-749, 479-487) for SOF0/SOF1
+// scans: inside a restart interval the host's limit search guarantees that every 0xFF is followed by 0x00
+// (zpx_parse.cpp find_limit), so removing the stuffing means dropping each 0x00 whose predecessor is 0xFF.
+// Doing it once, in a streaming pass over the uploaded bytes, takes the FF 00 test and the byte-granular
+// position bookkeeping out of every Huffman symbol step of K1 (zpx_k1_common.cuh RingReader) and makes bit
+// positions of the unstuffed stream canonical for the self-synchronising decoder.
+//
+// Work unit: one warp per piece (ZpxSegDev: about 4 KB of raw bytes of one interval, cut by the host where no
+// FF 00 pair is split; the host also knows how many pairs precede the piece, i.e. where its output starts).
+// A round moves 512 raw bytes: coalesced 16-byte loads into shared memory, then 16 steps in which lane l looks
+// at byte 32 k + l (conflict-free), a ballot + popc gives its output position, and the kept bytes go to a 1 KB
+// output ring from which complete 16-byte vectors are stored to HBM; head and tail bytes that share a vector
+// with the neighbouring piece are stored one by one.  HBM-bound: reads and writes every entropy-coded byte once.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "zpx_internal.h"
+#include "zpx_kernels.h"
+
+namespace zpx {
+
+constexpr int K0_WARPS = 4;
+
+__global__ void __launch_bounds__(K0_WARPS * 32) k0_unstuff(const uint8_t* __restrict__ blob, uint8_t* __restrict__ ublob,
+                                                            const ZpxSegDev* __restrict__ segs, const int n_segs) {
+    __shared__ __align__(16) uint8_t s_in[K0_WARPS][512];
+    __shared__ __align__(16) uint8_t s_out[K0_WARPS][1024];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = blockIdx.x * K0_WARPS + warp;
+    if (gid >= n_segs) return;  // whole warps
+    const ZpxSegDev sg = segs[gid];
+    uint8_t* in = s_in[warp];
+    uint8_t* out = s_out[warp];
+    const uint64_t a0 = sg.src & ~(uint64_t)15;
+    const uint32_t m = (uint32_t)(sg.dst & 15u);
+    uint8_t* gbase = ublob + (sg.dst - m);   // 16-byte aligned; ring position p <-> gbase + p
+    uint32_t wpos = m, flushed = 0;          // bytes produced / bytes stored (flushed is a multiple of 16)
+    int rel0 = -(int)(sg.src - a0);          // (offset of the round's first byte) - src
+    uint32_t prev_last = 0;                  // last raw byte of the previous round
+    const uint32_t lt = (1u << lane) - 1u;
+
+    auto flush_full = [&]() {
+        const uint32_t nvec = (wpos - flushed) >> 4;
+        for (uint32_t v0 = 0; v0 < nvec; v0 += 32) {
+            const uint32_t v = v0 + lane;
+            if (v < nvec) {
+                const uint32_t off = flushed + 16u * v;
+                if (off == 0 && m != 0) {
+                    // the first vector is shared with the piece before this one: only bytes m..15 are ours
+                    for (uint32_t b = m; b < 16; b++) gbase[b] = out[b];
+                } else {
+                    *reinterpret_cast<uint4*>(gbase + off) = *reinterpret_cast<const uint4*>(out + (off & 1023u));
+                }
+            }
+        }
+        flushed += nvec << 4;
+    };
+
+    for (uint64_t base = a0; base < sg.src + sg.len; base += 512, rel0 += 512) {
+        const uint64_t my = base + 16u * (uint32_t)lane;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (my < sg.src + sg.len) v = __ldg(reinterpret_cast<const uint4*>(blob + my));
+        reinterpret_cast<uint4*>(in)[lane] = v;
+        __syncwarp();
+#pragma unroll 4
+        for (int k = 0; k < 16; k++) {
+            const int b = 32 * k + lane;
+            const int rel = rel0 + b;  // position inside the piece
+            const uint32_t x = in[b];
+            const uint32_t px = b > 0 ? in[b - 1] : prev_last;
+            const bool valid = rel >= 0 && rel < (int)sg.len;
+            const bool drop = x == 0u && rel >= 1 && px == 0xffu;  // the 0x00 of an FF 00 pair
+            const bool keep = valid && !drop;
+            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) out[(wpos + __popc(mask & lt)) & 1023u] = (uint8_t)x;
+            wpos += __popc(mask);
+        }
+        prev_last = in[511];
+        __syncwarp();
+        flush_full();
+        __syncwarp();
+    }
+    if (sg.flags & 1u) {
+        // last piece of its interval: zeros up to the next 16-byte boundary (K1 reads whole 16-byte chunks)
+        const uint32_t padn = (16u - (wpos & 15u)) & 15u;
+        if ((uint32_t)lane < padn) out[(wpos + lane) & 1023u] = 0;
+        wpos += padn;
+        __syncwarp();
+        flush_full();
+    }
+    // bytes of the last, incomplete vector (the piece after this one owns the rest of it)
+    const uint32_t rest = wpos - flushed;
+    if ((uint32_t)lane < rest && !(flushed == 0 && (uint32_t)lane < m)) gbase[flushed + lane] = out[(flushed + lane) & 1023u];
+}
+
+cudaError_t k0_launch_unstuff(const uint8_t* blob, uint8_t* ublob, const ZpxSegDev* segs, int n_segs, cudaStream_t s) {
+    if (n_segs <= 0) return cudaSuccess;
+    k0_unstuff<<<(n_segs + K0_WARPS - 1) / K0_WARPS, K0_WARPS * 32, 0, s>>>(blob, ublob, segs, n_segs);
+    return cudaGetLastError();
+}
+
+}  // namespace zpx

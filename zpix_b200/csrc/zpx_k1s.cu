@@ -25,13 +25,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "zpx_entropy.cuh"
-#include "zpx_internal.h"
-#include "zpx_kernels.h"
+#include "zpx_k1_common.cuh"
 
 namespace zpx {
 
-constexpr int K1S_NT = 128;  // threads per CTA (4 warps)
+constexpr int K1S_NT = K1_NT;  // threads per CTA (4 warps)
 
 __device__ __forceinline__ unsigned long long pack_state(uint32_t pos, int c, int z) {
     return (unsigned long long)pos | ((unsigned long long)(uint32_t)c << 32) | ((unsigned long long)(uint32_t)z << 40);
@@ -40,29 +38,20 @@ __device__ __forceinline__ unsigned long long pack_state(uint32_t pos, int c, in
 struct LaneCtx {
     const ZpxIntervalDev* iv;
     const ZpxScanDev* sc;
-    const ZpxImageDev* im;
-    const uint32_t* words;  // (blob + start) rounded down to 4 bytes
-    uint32_t first;         // byte offset of the domain's first byte inside words
-    uint32_t end;           // byte offset of the limit
-    uint32_t li;            // sub-sequence index inside the domain
-    uint32_t bnd;           // byte offset of this sub-sequence's end boundary
+    uint32_t li;   // sub-sequence index inside the domain
+    uint32_t bnd;  // byte offset (unstuffed, from the domain's start) of this sub-sequence's end boundary
 };
 
 __device__ __forceinline__ void lane_setup(const K1Params& P, const ZpxWarpDev w, int lane, LaneCtx& L) {
     L.iv = &P.ivs[w.iv];
     L.sc = &P.scans[L.iv->scan];
-    L.im = &P.imgs[L.sc->img];
-    const uint64_t a = L.iv->start & ~(uint64_t)3;
-    L.words = reinterpret_cast<const uint32_t*>(P.blob + a);
-    L.first = (uint32_t)(L.iv->start - a);
-    L.end = L.first + L.iv->len;
     L.li = w.first + lane;
     L.bnd = (L.li + 1) * L.iv->sub_bytes;
 }
 
 // Decode (without output) from state `in` until the first symbol that starts at or after the
 // sub-sequence boundary, or the data runs out.  Only the bit count and the zig-zag advance of each
-// symbol matter here (one 32-bit entry of ZpxHuffDev::fast); values are extracted for DC symbols only,
+// symbol matter here (one 32-bit ZPX_FE entry); values are extracted for DC symbols only,
 // to accumulate the per-component sums of DC differences.  Invalid codes advance one bit (any
 // deterministic rule works: true states of a well-formed stream never meet one; errors are reported
 // by k1s_write).  Called by the lanes in `mask` together; the vote keeps them in lock step.
@@ -70,10 +59,10 @@ __device__ __forceinline__ void lane_setup(const K1Params& P, const ZpxWarpDev w
 // Checkpoints (CK): a re-decode from a corrected start state joins the trajectory of the lane's previous
 // decode after a few dozen symbols (that is what self-synchronisation means), and from there on repeats
 // it.  Each decode therefore records its state at the first symbol boundary at or after 1/4, 1/2 and 3/4
-// of the sub-sequence -- (bits past that raw byte offset, block phase, zig-zag index), which does not
+// of the sub-sequence -- (bits past that byte offset, block phase, zig-zag index), which does not
 // depend on where the decode started -- together with the counts so far; a later decode that reaches a
 // checkpoint in the same state stops there and completes its counts from the previous decode's
-// (exact: equal state at equal raw position means identical continuation).  n_out / dc_out / old_out
+// (exact: equal state at equal position means identical continuation).  n_out / dc_out / old_out
 // carry the previous decode's results in.
 struct CkStore {          // this lane's slots in shared memory, [3] strided by K1S_NT
     uint32_t* st;         // rel | c << 16 | k << 24 ; 0xffffffff = none
@@ -81,9 +70,10 @@ struct CkStore {          // this lane's slots in shared memory, [3] strided by 
     int4* dc;
 };
 
-template <bool CK>
+template <bool CK, bool SMEM>
 __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, const LaneCtx& L, unsigned long long in,
                                                           unsigned mask, int& n_out, int4& dc_out, int& bad_out,
+                                                          const uint32_t sdesc, const uint32_t tb, const uint32_t ring_col,
                                                           unsigned long long old_out = 0, CkStore ck = CkStore{nullptr, nullptr, nullptr}) {
     const ZpxScanDev* __restrict__ sc = L.sc;
     // thresholds T_m = bnd - (3 - m) * step, m = 0..2, then the sub-sequence boundary itself (m == 3)
@@ -91,16 +81,16 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
     const bool use_ck = CK && sc->rotate == 0 && step >= 32;
     uint32_t m = 3;
     if (use_ck) {
-        // arm the first threshold that lies safely after the start position (the reader buffers ahead)
-        const uint32_t sbyte = (uint32_t)in >> 3;
+        // arm the first threshold that lies after the start position
         m = 0;
-        while (m < 3 && L.bnd - (3 - m) * step <= sbyte + 16) {
+        while (m < 3 && (L.bnd - (3 - m) * step) * 8u <= (uint32_t)in) {
             ck.st[m * K1S_NT] = 0xffffffffu;
             m++;
         }
     }
-    BitReader br;
-    br.init_at(L.words, (uint32_t)in, L.end, L.bnd - (3 - m) * step);
+    uint32_t thr = (L.bnd - (3 - m) * step) * 8u;  // m == 3: the boundary
+    RingReader rd;
+    rd.init(ring_col, P.ublob, L.iv->ustart, L.iv->ulen, (uint32_t)in);
     int c = (int)((in >> 32) & 0xff), k = (int)((in >> 40) & 0xff);
     const int nblk = sc->interleaved ? sc->nblk : 1;
     const uint4* __restrict__ bpack = reinterpret_cast<const uint4*>(sc->blk_pack);
@@ -109,23 +99,28 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
     const bool rotate = sc->rotate != 0;
     if (rotate) c = 0;
     int n = 0, d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-    uint4 bi = bpack[c];
-    const uint32_t* __restrict__ fdc = P.huff[bi.x].fast;
-    const uint32_t* __restrict__ fac = P.huff[bi.y].fast;
+    uint4 bi = SMEM ? lds_u128(sdesc + c * 16) : bpack[c];
+    const uint32_t* __restrict__ fdc = SMEM ? nullptr : P.huff[bi.x].fast;
+    const uint32_t* __restrict__ fac = SMEM ? nullptr : P.huff[bi.y].fast;
     bool go = true, merged = false;
     int bad = 0;  // an invalid code was skipped (one bit further).  If this decode started in the true state, the
                   // reference fails there; a skipped code at a block start is seen by no write-pass lane unless the
                   // lane that owns the preceding block probes the symbol after it (k1s_write)
+    int it = 0;
     while (__any_sync(mask, go)) {
+        if (it == K1_TOPUP) {  // uniform over the lanes in mask
+            rd.topup();
+            it = 0;
+        }
+        it++;
         if (go) {
-            const uint32_t u = br.used();
-            if (br.pad && u >= br.fed) {
-                go = false;
-            } else if (br.bpassed && u >= br.B) {
+            if (rd.bitpos >= rd.endbits) {
+                go = false;  // the data ran out
+            } else if (rd.bitpos >= thr) {
                 if (!CK || m >= 3) {
                     go = false;  // first symbol boundary at or after the end of the sub-sequence
                 } else {
-                    const uint32_t cur = (u - br.B) | (uint32_t)c << 16 | (uint32_t)k << 24;
+                    const uint32_t cur = (rd.bitpos - thr) | (uint32_t)c << 16 | (uint32_t)k << 24;
                     const int4 odc = ck.dc[m * K1S_NT];
                     const int on = ck.n[m * K1S_NT];
                     if (ck.st[m * K1S_NT] == cur) {
@@ -150,44 +145,35 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
                         ck.n[m * K1S_NT] = n;
                         ck.dc[m * K1S_NT] = make_int4(d0, d1, d2, d3);
                         m++;
-                        br.bnd = L.bnd - (3 - m) * step;
-                        br.bpassed = 0;
+                        thr = (L.bnd - (3 - m) * step) * 8u;
                     }
                 }
             } else {
-                br.fill();
-                const uint32_t hi = br.peek32();
+                const uint32_t hi = rd.peek();
                 const bool isdc = k == 0;
-                const uint32_t* __restrict__ ftab = isdc ? fdc : fac;
-                uint32_t e = __ldg(ftab + (hi >> (32 - ZPX_LUT_BITS)));
+                uint32_t e;
+                if (SMEM) e = lds_u32(isdc ? bi.x + ((hi >> (32 - K1_DLB)) << 2) : bi.y + ((hi >> (32 - K1_ALB)) << 2));
+                else e = __ldg((isdc ? fdc : fac) + (hi >> (32 - ZPX_LUT_BITS)));
                 if ((int)e <= 0) {
                     // longer code / invalid code / EOB run / DC category > 16 (about 1 % of the symbols)
-                    const ZpxHuffDev* __restrict__ tab = reinterpret_cast<const ZpxHuffDev*>(ftab);
-                    const HuffSym hs = huff_decode(tab, hi);
-                    if (hs.len == 0) {
+                    unsigned long long r;
+                    if (SMEM) r = k1_slow_symbol_sm(tb, isdc ? (bi.w >> 20) & 15u : (bi.w >> 24) & 15u, hi, isdc, e);
+                    else r = k1_slow_symbol(&P.huff[isdc ? bi.x : bi.y], hi, isdc, e);
+                    e = (uint32_t)r;
+                    if ((int)(r >> 32) == ZPX_E_BadHuffmanCode) {
                         bad = 1;
                         e = 1u;  // invalid: one bit further, same state (tot = 1, adv = 0)
-                    } else if (isdc) {
-                        const uint32_t size = hs.sym > 16 ? 0u : hs.sym;
-                        e = ZPX_FE((uint32_t)hs.len + size, hs.len, size, 1, 0);
-                    } else {
-                        const uint32_t r = hs.sym >> 4, s2 = hs.sym & 15;
-                        uint32_t size = s2, adv = r + 1, extra = 0;
-                        if (s2 == 0) {
-                            size = 0;
-                            adv = r == 15 ? 16 : 64;
-                            extra = (r != 15) ? r : 0;  // EOB run: r more bits belong to the symbol
-                        }
-                        e = ZPX_FE((uint32_t)hs.len + size + extra, hs.len, size, adv, 0);
+                    } else if (e >> 31) {
+                        // EOB run: r more bits belong to the symbol
+                        const uint32_t len = (e >> 8) & 0xffu, rr = (e >> 16) & 0xffu;
+                        e = ZPX_FE(len + rr, len, 0, 64, 0);
                     }
                 }
-                const int len = (int)__byte_perm(e, 0, 0x4441), size = (int)__byte_perm(e, 0, 0x4442);
-                int tot = (int)__byte_perm(e, 0, 0x4440);
-                const int adv = (int)(e >> 24);
+                const int len = fe_len(e), size = fe_size(e);
+                int tot = fe_tot(e);
+                const int adv = fe_adv(e);
                 if (isdc && adv) {
-                    const uint32_t t = (uint32_t)((br.buf << len) >> 32);
-                    int v = (int)((t >> 1) >> (31 - size));
-                    v += (~((int)t >> 31)) & (1 - (1 << size));
+                    const int v = fe_extend(hi << len, size);
                     const int comp = rotate ? c : (int)(bi.z & 0xff);
                     if (comp == 0) d0 += v; else if (comp == 1) d1 += v; else if (comp == 2) d2 += v; else d3 += v;
                     n++;
@@ -195,13 +181,17 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
                     tot = len;  // decoder.zig:1393-1395: run past the block end, the value bits stay unread
                 }
                 k += adv;
-                br.consume(tot);
+                rd.bitpos += tot;
                 if (k > 63) {
                     k = 0;
                     c = c + 1 == nblk ? 0 : c + 1;
-                    bi = bpack[c];
-                    fdc = P.huff[bi.x].fast;
-                    fac = P.huff[bi.y].fast;
+                    if (SMEM) {
+                        bi = lds_u128(sdesc + c * 16);
+                    } else {
+                        bi = bpack[c];
+                        fdc = P.huff[bi.x].fast;
+                        fac = P.huff[bi.y].fast;
+                    }
                 }
             }
         }
@@ -214,24 +204,42 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
         for (uint32_t q = m; q < 3; q++) ck.st[q * K1S_NT] = 0xffffffffu;
     // a DC symbol decoded in rotate mode belongs to relative phase c *before* the block ends; when the
     // sub-sequence ends inside a block, that block's phase is (c) and was counted -- nothing to fix
-    return pack_state(br.rawpos(), rotate ? 0 : c, k);
+    return pack_state(rd.bitpos, rotate ? 0 : c, k);
 }
 
 // ---------------------------------------------------------------------------
 // sweep kernel
 // ---------------------------------------------------------------------------
+struct K1SyncSmem {
+    uint32_t ring[K1_RW * K1S_NT];
+    uint32_t ck[3 * K1S_NT];
+    int cn[3 * K1S_NT];
+    int4 cdc[3 * K1S_NT];
+    K1Tables tab;
+};
+
 __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int sweep) {
-    __shared__ uint32_t s_ck[3 * K1S_NT];
-    __shared__ int s_cn[3 * K1S_NT];
-    __shared__ int4 s_cdc[3 * K1S_NT];
-    const CkStore ck{s_ck + threadIdx.x, s_cn + threadIdx.x, s_cdc + threadIdx.x};
-    for (int q = 0; q < 3; q++) s_ck[q * K1S_NT + threadIdx.x] = 0xffffffffu;
+    extern __shared__ __align__(16) uint8_t k1s_smem[];
+    K1SyncSmem& S = *reinterpret_cast<K1SyncSmem*>(k1s_smem);
+    const CkStore ck{S.ck + threadIdx.x, S.cn + threadIdx.x, S.cdc + threadIdx.x};
+    for (int q = 0; q < 3; q++) S.ck[q * K1S_NT + threadIdx.x] = 0xffffffffu;
     const int wid = blockIdx.x * (K1S_NT / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (wid >= P.n_warps) return;
-    const ZpxWarpDev w = P.warps[wid];
+    const bool wv = wid < P.n_warps;
+    const ZpxWarpDev w = P.warps[wv ? wid : P.n_warps - 1];
     LaneCtx L;
     lane_setup(P.k1, w, lane, L);
+    S.tab.lane_scan[threadIdx.x] = L.iv->scan;
+    __syncthreads();
+    const bool cached = k1_tables_setup(P.k1, S.tab);
+    if (!wv) return;
+    uint32_t sdesc = 0;
+    if (cached)
+        for (int i = 0; i < S.tab.nscan; i++)
+            if (S.tab.scan_id[i] == L.iv->scan) sdesc = smem_addr(&S.tab.desc[i][0]);
+    const uint32_t tb = smem_addr(&S.tab);
+    const uint32_t rc = smem_addr(S.ring) + threadIdx.x * 4;
+
     const bool active = L.li < L.iv->nsub;
     const uint32_t t = L.iv->sub_first + L.li;
     const bool last_active = active && (lane == 31 || L.li + 1 == L.iv->nsub);
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int 
     bool dirty = false;
     if (sweep == 0) {
         if (active) {
-            in = L.li == 0 ? pack_state(L.first * 8, 0, 0) : pack_state(L.li * L.iv->sub_bytes * 8, 0, 0);
+            in = pack_state(L.li * L.iv->sub_bytes * 8u, 0, 0);
             dirty = true;
         }
     } else {
@@ -274,7 +282,8 @@ __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int 
     do {
         const unsigned dm = __ballot_sync(0xffffffffu, dirty);
         if (dirty) {
-            out = sync_decode<true>(P.k1, L, in, dm, n, dc, bad, out, ck);
+            if (cached) out = sync_decode<true, true>(P.k1, L, in, dm, n, dc, bad, sdesc, tb, rc, out, ck);
+            else out = sync_decode<true, false>(P.k1, L, in, dm, n, dc, bad, 0, tb, rc, out, ck);
             touched = true;
         }
         const unsigned long long po = __shfl_up_sync(0xffffffffu, out, 1);
@@ -300,9 +309,11 @@ __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int 
 // state (it comes from the previous warp).  One lane per warp boundary re-decodes that sub-sequence from
 // the previous warp's end state; the lanes of a warp here are 32 different boundaries, so this costs
 // 1/32 of the warp instructions of another full sweep.  If such a re-decode ends in a new state, the rest
-// of that warp is stale: `changed` asks the host for another k1s_sync sweep.
+// of that warp is stale: `changed` asks the host for another k1s_sync sweep.  The lanes of a CTA belong to
+// up to 128 different scans here: tables are read in HBM.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(K1S_NT) k1s_fix(const K1SParams P) {
+    __shared__ uint32_t s_ring[K1_RW * K1S_NT];
     const int g = blockIdx.x * K1S_NT + threadIdx.x;
     const bool valid = g < P.n_warps;
     const ZpxWarpDev w = P.warps[valid ? g : 0];
@@ -323,7 +334,7 @@ __global__ void __launch_bounds__(K1S_NT) k1s_fix(const K1SParams P) {
     if (dirty) {
         int n = 0, bad = 0;
         int4 dc = make_int4(0, 0, 0, 0);
-        const unsigned long long out = sync_decode<false>(P.k1, L, in, dm, n, dc, bad);
+        const unsigned long long out = sync_decode<false, false>(P.k1, L, in, dm, n, dc, bad, 0, 0, smem_addr(s_ring) + threadIdx.x * 4);
         P.s_in[t] = in;
         P.s_out[t] = out;
         P.s_n[t] = n;
@@ -410,7 +421,9 @@ __global__ void __launch_bounds__(K1S_NT) k1s_scan(const K1SParams P) {
 cudaError_t k1s_launch_sync(const K1SParams& P, int sweep, cudaStream_t s) {
     if (P.n_warps <= 0) return cudaSuccess;
     const int wpc = K1S_NT / 32;
-    k1s_sync<<<(P.n_warps + wpc - 1) / wpc, K1S_NT, 0, s>>>(P, sweep);
+    cudaError_t e = cudaFuncSetAttribute(k1s_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SyncSmem));
+    if (e != cudaSuccess) return e;
+    k1s_sync<<<(P.n_warps + wpc - 1) / wpc, K1S_NT, sizeof(K1SyncSmem), s>>>(P, sweep);
     return cudaGetLastError();
 }
 cudaError_t k1s_launch_fix(const K1SParams& P, cudaStream_t s) {

@@ -9,7 +9,10 @@ namespace zpx {
 
 // ---- K1: entropy decode -----------------------------------------------------
 struct K1Params {
-    const uint8_t* blob;          // entropy-coded bytes of the whole device batch, still byte-stuffed
+    const uint8_t* blob;          // entropy-coded bytes of the whole device batch, still byte-stuffed (progressive scans
+                                  // read it directly, zpx_k3.cu)
+    const uint8_t* ublob;         // sequential scans: the same bytes with the stuffing removed (k0_unstuff), one
+                                  // 16-byte aligned run per restart interval (ZpxIntervalDev::ustart / ulen)
     const ZpxIntervalDev* ivs;
     int n_iv;
     const ZpxScanDev* scans;
@@ -20,8 +23,9 @@ struct K1Params {
     uint32_t* img_flags;          // per image (status slot), zeroed before the decode: bit 0 = some coefficient of a
                                   // sequential scan lies outside [-4096, 4095] (the fused IDCT then takes the
                                   // reference's all-AC-zero row literally, zpx_idct.cuh)
-    int lanes_per_warp;           // lane-per-interval kernel: 32 or 16 intervals per warp
 };
+// ---- K0: remove the byte stuffing (FF 00 -> FF) of the sequential scans' restart intervals, one warp per piece ----
+cudaError_t k0_launch_unstuff(const uint8_t* blob, uint8_t* ublob, const ZpxSegDev* segs, int n_segs, cudaStream_t s);
 cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s);
 
 // self-synchronising sub-sequence decoder (streams without DRI, or few large intervals)

@@ -224,31 +224,47 @@ struct Parser {
         return true;
     }
 
-    // first 0xFF followed by a byte != 0x00 at or after `from`; len if none
-    size_t find_limit(size_t from, bool* eof_limit) const {
-        size_t i = from;
+    // first 0xFF followed by a byte != 0x00 at or after `from`; len if none.
+    // Also counts the FF 00 pairs on the way (*n_stuffed) and, when `segs` is given, cuts [from, limit) into pieces
+    // of about ZPX_SEG_BYTES raw bytes that never split a pair: the work units of the unstuffing kernel (zpx_k0.cu).
+    size_t find_limit(size_t from, bool* eof_limit, uint32_t* n_stuffed, std::vector<ZpxSegHost>* segs) const {
+        size_t i = from, seg_begin = from;
+        uint32_t stuffed = 0, seg_uoff = 0;
+        size_t limit;
         for (;;) {
-            if (i >= len) {
-                *eof_limit = true;
-                return len;
+            const uint8_t* p = i < len ? (const uint8_t*)memchr(d + i, 0xff, len - i) : nullptr;
+            const size_t j = p ? (size_t)(p - d) : len;  // [i, j) holds no 0xFF
+            if (segs) {
+                while (j - seg_begin > ZPX_SEG_BYTES) {
+                    size_t c = seg_begin + ZPX_SEG_BYTES;
+                    if (c < i) c = i;  // i = just past the last pair: never cut between an 0xFF and its 0x00
+                    segs->push_back({seg_begin, (uint32_t)(c - seg_begin), seg_uoff});
+                    seg_begin = c;
+                    seg_uoff = (uint32_t)(c - from) - stuffed;
+                }
             }
-            const uint8_t* p = (const uint8_t*)memchr(d + i, 0xff, len - i);
             if (!p) {
                 *eof_limit = true;
-                return len;
+                limit = len;
+                break;
             }
-            size_t j = (size_t)(p - d);
             if (j + 1 >= len) {  // 0xFF is the last byte: the reader hits end of stream looking for the 0x00
                 *eof_limit = true;
-                return j;
+                limit = j;
+                break;
             }
             if (d[j + 1] == 0x00) {
+                stuffed++;
                 i = j + 2;
                 continue;
             }
             *eof_limit = false;
-            return j;
+            limit = j;
+            break;
         }
+        if (segs && limit > seg_begin) segs->push_back({seg_begin, (uint32_t)(limit - seg_begin), seg_uoff});
+        *n_stuffed = stuffed;
+        return limit;
     }
 
     // decoder.zig:1436-1439 + findRst :1671-1705, started at `q` (see file header).
@@ -351,7 +367,9 @@ struct Parser {
         for (uint32_t k = 0; k < n_int; k++) {
             ZpxIntervalHost iv;
             iv.start = p;
-            iv.limit = find_limit(p, &iv.eof_limit);
+            iv.seg_first = (uint32_t)sc.segs.size();
+            iv.limit = find_limit(p, &iv.eof_limit, &iv.n_stuffed, o.progressive ? nullptr : &sc.segs);
+            iv.n_segs = (uint32_t)sc.segs.size() - iv.seg_first;
             iv.first_mcu = ri > 0 ? k * ri : 0;
             iv.n_mcu = ri > 0 ? (total_mcu - iv.first_mcu < ri ? total_mcu - iv.first_mcu : ri) : total_mcu;
             sc.intervals.push_back(iv);
