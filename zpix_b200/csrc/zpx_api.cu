@@ -668,6 +668,7 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
     K1Params k1;
     k1.blob = (const uint8_t*)dc.blob.p;
     k1.ublob = (const uint8_t*)dc.ublob.p;
+    k1.dbg = getenv("ZPX_K1_DBG") ? atoi(getenv("ZPX_K1_DBG")) : 0;
     k1.ivs = (const ZpxIntervalDev*)(desc + pl.off_ivs);
     k1.n_iv = (int)pl.n_seq;
     k1.scans = (const ZpxScanDev*)(desc + pl.off_scans);
@@ -681,14 +682,14 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         k1_launches++;
     }
     if (k1.n_iv > 0 && !pl.sub_mode) {
-        CU(ctx, k1_launch_lane_per_interval(k1, st));
+        CU(ctx, k1_launch_lane_per_interval(k1, dc.sm_count, st));
         k1_launches++;
     } else if (k1.n_iv > 0) {
         if (pl.n_sub_iv < pl.n_seq) {  // scans the self-synchronising decoder does not take
             K1Params kl = k1;
             kl.ivs = k1.ivs + pl.n_sub_iv;
             kl.n_iv = (int)(pl.n_seq - pl.n_sub_iv);
-            CU(ctx, k1_launch_lane_per_interval(kl, st));
+            CU(ctx, k1_launch_lane_per_interval(kl, dc.sm_count, st));
             k1_launches++;
         }
         k1.n_iv = (int)pl.n_sub_iv;

@@ -26,12 +26,16 @@
 // ZpxHuffDev::fast entry, one per ZPX_LUT_BITS-bit prefix (byte-aligned fields: one PRMT each on the device):
 //   byte 0  total bits of the symbol (code + value bits)
 //   byte 1  code length
-//   byte 2  value bits (size); for a special entry: the run r of an End-Of-Band run
+//   byte 2  32 - value bits (the shift that right-aligns the value; 32 = no value bits)
 //   byte 3  zig-zag advance (DC: 1; AC: run + 1, ZRL 16, EOB 64) | special << 7
-//   special: AC (r, 0) with 0 < r < 15 (End-Of-Band run) or a DC category > 16
+//   special: the symbol takes the kernels' rare path -- AC (r, 0) with 0 < r < 15 (End-Of-Band run),
+//   an AC value of 13 or more bits (a coefficient outside [-4096, 4095]: the kernels flag the image for the exact
+//   IDCT rows, zpx_idct.cuh) or a DC category > 16
 //   0 = code longer than ZPX_LUT_BITS or invalid -> canonical search.
 #define ZPX_FE(tot, len, size, adv, special) \
-    ((uint32_t)(tot) | (uint32_t)(len) << 8 | (uint32_t)(size) << 16 | (uint32_t)(adv) << 24 | (uint32_t)(special) << 31)
+    ((uint32_t)(tot) | (uint32_t)(len) << 8 | (uint32_t)(32u - (size)) << 16 | (uint32_t)(adv) << 24 | (uint32_t)(special) << 31)
+// what the rare path hands back for an End-Of-Band run: byte 2 holds the run bits r, byte 3 = 64 | special
+#define ZPX_FE_RUN(tot, len, rr) ((uint32_t)(tot) | (uint32_t)(len) << 8 | (uint32_t)(rr) << 16 | 64u << 24 | 1u << 31)
 
 struct ZpxHuffDev {
     uint32_t fast[ZPX_LUT_SIZE];

@@ -29,10 +29,10 @@
 
 namespace zpx {
 
-// slow-path wrapper shared by the DC and AC steps: returns the entry fields, sets err / eob_run
+// slow-path wrapper shared by the DC and AC steps: returns the entry fields, sets err / eob_run / wide
 template <bool SMEM>
 __device__ __forceinline__ uint32_t k1_rare(const K1Params& P, uint32_t hi, bool isdc, uint32_t e, const uint4& bi, uint32_t tb,
-                                            uint32_t& eob_run, int& err) {
+                                            uint32_t& eob_run, int& err, int& wide) {
     unsigned long long r;
     if (SMEM) {
         r = k1_slow_symbol_sm(tb, isdc ? (bi.w >> 20) & 15u : (bi.w >> 24) & 15u, hi, isdc, e);
@@ -47,6 +47,8 @@ __device__ __forceinline__ uint32_t k1_rare(const K1Params& P, uint32_t hi, bool
         eob_run = (1u << rr) | ((hi << len) >> (32 - rr));
         eob_run = (eob_run - 1) & 0xffffu;
         e = ZPX_FE(len + rr, len, 0, 64, 0);  // consume code + run bits, end of block
+    } else if (!isdc) {
+        wide = max(wide, 32 - fe_s32(e));  // AC values of 13 bits or more only come this way (special entries)
     }
     // an error ends the block: advance past index 63 (the caller's err stays set for the block-end code)
     if (err) e = (e & 0x00ffffffu) | 64u << 24;
@@ -77,17 +79,60 @@ struct K1Start {
 // Lanes of a warp sit at the same block phase of the MCU (all on luma or all on chroma), so the number
 // of AC iterations is close to the lanes' own symbol counts, and the block-end code runs once per
 // block for all lanes instead of once per symbol for a few.
-template <bool SMEM, bool SUB>
+//
+// The AC step is straight-line code that every lane executes (a lane whose block is complete advances by zero
+// bits and stores nothing): the only branches are the rare-symbol call and the loop's vote.  The stream window is
+// three ring words in registers -- the word under the bit position and the two after it -- so the 32 bits of a
+// step come from one funnel shift; when a step crosses a word boundary the registers move up and the third is
+// reloaded from the ring, a load nothing waits for until the step after the next.
+template <int RS>
+struct Window {
+    uint32_t w0, w1, w2;
+    uint32_t a2;  // shared address of w2's ring word
+    __device__ __forceinline__ void load(const RingReader<RS>& rd) {
+        w0 = lds_u32(rd.word_addr(0));
+        w1 = lds_u32(rd.word_addr(1));
+        a2 = rd.word_addr(2);
+        w2 = lds_u32(a2);
+    }
+    __device__ __forceinline__ uint32_t peek(uint32_t bitpos) const { return __funnelshift_l(w1, w0, bitpos); }
+    // the position moves from `from` by tot <= 32 bits.  Branch-free: m is all ones when it enters the next word
+    // (then the registers move up and w2 is the next ring word; otherwise w2 is simply read again)
+    __device__ __forceinline__ void advance(const RingReader<RS>& rd, uint32_t from, uint32_t tot) {
+        const uint32_t t = (from & 31u) + tot;
+        const uint32_t m = (uint32_t)((int)(t << 26) >> 31);
+        w0 = (w1 & m) | (w0 & ~m);
+        w1 = (w2 & m) | (w1 & ~m);
+        a2 += m & (uint32_t)RS;
+        if (a2 == rd.ring + K1_RW * RS) a2 = rd.ring;
+        w2 = lds_u32(a2);
+    }
+};
+
+// what a lane that idles (its block is complete) or takes the rare path sees in the common code of a step:
+// no bits, no value, no advance
+constexpr uint32_t K1_NULL_E = ZPX_FE(0, 0, 0, 0, 0);
+
+// shared-memory bytes per lane of the block under assembly: 8 rows x 16 bytes, + 16 so that the lanes' rows start in
+// different banks
+constexpr int K1_BLKB = 144;
+
+template <int SLOTS, int LPW, bool SMEM, bool SUB>
 __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxIntervalDev& iv, const K1Start& st, const uint32_t sb,
                                              const uint32_t su, const uint32_t sdesc /* smem: this lane's scan's blk table */,
-                                             const uint32_t tb /* smem: K1Tables */, const uint32_t ring_col) {
-    constexpr int NT = K1_NT;
+                                             const uint32_t tb /* smem: K1Tables */, const uint32_t ring_col,
+                                             const uint32_t sbw /* smem: block of the warp's first lane */,
+                                             const uint32_t siw /* smem: flush record of the warp's first lane */) {
+    constexpr int RS = SLOTS * 4;
+    const int lane = threadIdx.x & 31;
     const ZpxScanDev* __restrict__ sc = &P.scans[iv.scan];
     const ZpxImageDev* __restrict__ im = &P.imgs[sc->img];
 
-    RingReader rd;
+    RingReader<RS> rd;
     if (st.count != 0 || (SUB && st.probe)) rd.init(ring_col, P.ublob, iv.ustart, iv.ulen, st.bitpos);
     else rd.init_idle(ring_col);
+    Window<RS> win;
+    win.load(rd);  // (top-ups never touch the ring words under the window: it stays valid from block to block)
 
     const bool interleaved = sc->interleaved != 0;
     const int nblk = interleaved ? sc->nblk : 1;
@@ -126,7 +171,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
 
     int dc0 = st.dc0, dc1 = st.dc1, dc2 = st.dc2, dc3 = st.dc3;
     uint32_t eob_run = 0;
-    int wide = 0;  // max over the lane's symbols of (AC value bits, DC magnitude >> 8): >= 13 / >= 16 flags the image
+    int wide = 0;  // >= 13: some coefficient of the lane lies outside [-4096, 4095]
     const bool probe = SUB && st.probe;
     const uint32_t total = st.count + (probe ? 1u : 0u);
     uint32_t left = total;  // blocks still to decode (including the current one and the probe)
@@ -134,26 +179,26 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     while (__any_sync(0xffffffffu, left != 0)) {
         int k = 64;  // > 63: no block in flight on this lane
         int err = 0;
-        rd.topup();
+        rd.topup();  // the ring now holds what the DC symbol and K1_TOPUP AC symbols can take
         if (SUB && tail) {
             k = st.k;
         } else if (left != 0) {
             // ---- DC (decoder.zig:1366-1376) ----
-            const uint32_t hi = rd.peek();
+            const uint32_t hi = win.peek(rd.bitpos);
             uint32_t e;
             if (SMEM) e = lds_u32(bi.x + ((hi >> (32 - K1_DLB)) << 2));
             else e = __ldg(gdc + (hi >> (32 - ZPX_LUT_BITS)));
-            if ((int)e <= 0) e = k1_rare<SMEM>(P, hi, true, e, bi, tb, eob_run, err);
+            if ((int)e <= 0) e = k1_rare<SMEM>(P, hi, true, e, bi, tb, eob_run, err, wide);
             if (bi.w & 0x10000u) err = ZPX_E_UninitializedHuffmanTable;
-            const int len = fe_len(e), size = fe_size(e);
-            const int v = fe_extend(hi << len, size);
+            const int v = fe_extend(hi << fe_len(e), fe_s32(e));
             const int comp = (int)(bi.z & 0xff);
             int dc = comp == 0 ? dc0 : comp == 1 ? dc1 : comp == 2 ? dc2 : dc3;
             dc += v;
             if (comp == 0) dc0 = dc; else if (comp == 1) dc1 = dc; else if (comp == 2) dc2 = dc; else dc3 = dc;
             if (dc < -32768 || dc > 32767) report_coef_range(P.status, im->status_slot);
             wide = max(wide, ((dc ^ (dc >> 31)) >> 12) ? 13 : 0);
-            rd.bitpos += fe_tot(e);
+            win.advance(rd, rd.bitpos, (uint32_t)fe_tot(e));
+            rd.bitpos += (uint32_t)fe_tot(e);
             sts_u16(sb, dc);
             k = 1;
             if (eob_run > 0) {  // decoder.zig:1379-1380 (End-Of-Band run)
@@ -175,44 +220,59 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
             }
         }
         // ---- AC (decoder.zig:1383-1411): one symbol per lane per vote ----
-        int step = 1;  // symbols since the last top-up (the DC symbol was the first)
-        while (__any_sync(0xffffffffu, k <= 63)) {
-            if (step == K1_TOPUP) {  // warp-uniform
-                rd.topup();
-                step = 0;
-            }
-            step++;
-            if (k <= 63) {
-                const uint32_t hi = rd.peek();
-                uint32_t e;
-                if (SMEM) e = lds_u32(bi.y + ((hi >> (32 - K1_ALB)) << 2));
-                else e = __ldg(gac + (hi >> (32 - ZPX_LUT_BITS)));
-                if ((int)e <= 0) {
-                    e = k1_rare<SMEM>(P, hi, false, e, bi, tb, eob_run, err);
+        // K1_TOPUP steps, unrolled, between two top-ups.  The common code of a step is branch-free; lanes that idle
+        // or meet a rare symbol see a null entry there, and the rare ones are dealt with at the end of the step.
+        const bool nostore = SUB && tail;
+        bool more = __any_sync(0xffffffffu, k <= 63);
+        while (more) {
+#pragma unroll
+            for (int u = 0; u < K1_TOPUP; u++) {
+                const uint32_t hi = win.peek(rd.bitpos);
+                uint32_t e0;
+                if (SMEM) e0 = lds_u32(bi.y + ((hi >> (32 - K1_ALB)) << 2));
+                else e0 = __ldg(gac + (hi >> (32 - ZPX_LUT_BITS)));
+                const bool act = k <= 63;
+                const bool rare = act && (int)e0 <= 0;
+                const uint32_t e = (act && (int)e0 > 0) ? e0 : K1_NULL_E;
+                {
+                    const int len = fe_len(e), s32 = fe_s32(e);
+                    int tot = fe_tot(e);
+                    const int v = fe_extend(hi << len, s32);
+                    const int kn = k + fe_adv(e);  // the value goes to zig-zag index kn - 1
+                    // decoder.zig:1393-1395: a run past the block end leaves the value bits unread
+                    if (kn > 64 && s32 != 32) tot = len;
+                    win.advance(rd, rd.bitpos, (uint32_t)tot);
+                    rd.bitpos += (uint32_t)tot;
+                    if (s32 != 32 && kn <= 64 && !nostore) sts_u16(sb + lds_u16(su + 2 * kn - 2), v);
+                    k = kn;
+                }
+                if (rare) {
+                    const uint32_t e2 = k1_rare<SMEM>(P, hi, false, e0, bi, tb, eob_run, err, wide);
                     // End-Of-Band RUN inside a sequential scan: the synchronisation passes do not
                     // model that state
                     if (SUB && eob_run != 0) {
                         eob_run = 0;
                         if (!err) err = ZPX_E_UNSUPPORTED_STREAM;
                     }
+                    const int len = fe_len(e2), s32 = fe_s32(e2);
+                    int tot = fe_tot(e2);
+                    const int v = fe_extend(hi << len, s32);
+                    const int kn = k + fe_adv(e2);  // 64 after an error: the block ends here
+                    if (kn > 64 && s32 != 32) tot = len;  // (an End-Of-Band run keeps its r run bits: no value bits)
+                    win.advance(rd, rd.bitpos, (uint32_t)tot);
+                    rd.bitpos += (uint32_t)tot;
+                    if (s32 != 32 && kn <= 64 && !nostore) sts_u16(sb + lds_u16(su + 2 * kn - 2), v);
+                    k = kn;
                 }
-                const int len = fe_len(e), size = fe_size(e);
-                int tot = fe_tot(e);
-                const int adv = fe_adv(e);  // 64 after an error: the block ends here
-                wide = max(wide, size);
-                const int v = fe_extend(hi << len, size);
-                const int kk = k + adv - 1;                    // zig-zag index the value goes to
-                bool store = size != 0 && !(SUB && tail);
-                if (kk > 63) {  // decoder.zig:1393-1395: run past the block end, the value bits stay unread
-                    if (size != 0) tot = len;  // (an End-Of-Band run keeps its r run bits: size == 0 there)
-                    store = false;
-                }
-                k += adv;
-                rd.bitpos += tot;
-                if (store) sts_u16(sb + lds_u16(su + 2 * kk), v);
+                more = __any_sync(0xffffffffu, k <= 63);
+                if (!more) break;
             }
+            if (more) rd.topup();
         }
         // ---- block end ----
+        // flush record of this lane's block: x = block index (low 32 bits), y = high bits | key << 16 |
+        // (store it) << 24 | (zero it) << 25; 0 = nothing to do
+        uint32_t fx = 0, fy = 0;
         if (SUB && tail) {
             // end of the skipped tail (its errors are the previous lane's to report): block j0 comes next
             tail = false;
@@ -250,15 +310,9 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                     const int comp = (int)(bi.z & 0xff);
                     blk = im->comp_base[comp] + (uint64_t)byn * im->comp_bw[comp] + bx;
                 }
-                uint4* __restrict__ dst = P.coef + blk * 8;
-                const uint32_t key = bx & 7;
-                const bool keep = !(bi.w & 0x40000u);  // not superseded by a later scan of the same component
-#pragma unroll
-                for (uint32_t slot = 0; slot < 8; slot++) {
-                    const uint32_t a = sb + (slot ^ key) * (NT * 16);
-                    if (keep) dst[slot] = lds_u128(a);
-                    sts_zero16(a);
-                }
+                const bool keep = !(bi.w & 0x40000u) && !(P.dbg & 1);  // not superseded by a later scan of the same component
+                fx = (uint32_t)blk;
+                fy = (uint32_t)(blk >> 32) | (bx & 7u) << 16 | (keep ? 1u << 24 : 0u) | 1u << 25;
                 left--;
                 if (interleaved) {
                     if (++c == nblk) {
@@ -279,6 +333,29 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 }
             }
         }
+        // The warp stores its lanes' blocks together: eight lanes per block, one 16-byte row each, so that a store
+        // instruction writes four whole 128-byte lines (a lane storing its own block row by row touches 32 lines
+        // per instruction).  The rows are cleared for the next block on the way.
+        if (__any_sync(0xffffffffu, fy != 0)) {
+            if (lane < LPW) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(siw + lane * 8), "r"(fx), "r"(fy) : "memory");
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < LPW / 4; i++) {
+                const int s = 4 * i + (lane >> 3);
+                uint32_t ix, iy;
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ix), "=r"(iy) : "r"(siw + s * 8));
+                if (iy >> 24) {
+                    const uint32_t r = lane & 7u;
+                    const uint32_t a = sbw + s * K1_BLKB + ((r ^ ((iy >> 16) & 7u)) << 4);
+                    if (iy & (1u << 24)) {
+                        const uint64_t blk = (uint64_t)ix | (uint64_t)(iy & 0xffffu) << 32;
+                        P.coef[blk * 8 + r] = lds_u128(a);
+                    }
+                    sts_zero16(a);
+                }
+            }
+            __syncwarp();
+        }
     }
     // The reference keeps its End-Of-Band run across scans (decoder.zig:144, reset only at RSTn :1451); here
     // every scan starts from zero, so a run that is still open when a scan ends (corrupt streams only) would
@@ -289,48 +366,65 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
 }
 
 // Dynamic shared memory of the write kernels
+template <int SLOTS>
 struct K1WriteSmem {
-    uint32_t ring[K1_RW * K1_NT];  // per-lane stream rings: [word slot][lane]
-    uint4 sblk[8 * K1_NT];         // per-lane block under assembly: [8 rows][lanes] x 16 bytes
+    uint32_t ring[K1_RW * SLOTS];  // per-lane stream rings: [word slot][lane]
+    uint4 sblk[(K1_BLKB / 16) * SLOTS];  // per-lane block under assembly: [lanes][8 rows + 1] x 16 bytes
+    uint2 sinfo[SLOTS];            // per-lane flush record (see the block end of k1_lane_loop)
     K1Tables tab;
 };
 
-// One CTA: K1_NT lanes, each with an interval and a start inside it (K1Start).  Collects the distinct scans and
-// Huffman tables of the CTA's lanes, stages their first-level LUTs and block descriptors in shared memory and
-// runs the block-synchronous loop.
-template <bool SUB>
+// One CTA: WARPS warps whose first LPW lanes each carry a stream ("slot" = warp * LPW + lane): an interval and a
+// start inside it (K1Start).  Collects the distinct scans and Huffman tables of the CTA's streams, stages their
+// first-level LUTs and block descriptors in shared memory and runs the block-synchronous loop.
+// Why fewer than 32 streams per warp: the loop is a chain of dependent instructions (a warp issues one every 4-5
+// cycles), so its throughput comes from the number of resident warps.  A batch with fewer streams than
+// 32 x resident warps is spread over narrower warps: the same work per stream, more warps to hide the latency.
+template <int LPW, int WARPS, bool SUB>
 __device__ __forceinline__ void k1_cta_run(const K1Params& P, const ZpxIntervalDev& iv, const K1Start& st) {
+    constexpr int SLOTS = WARPS * LPW;
     extern __shared__ __align__(16) uint8_t k1_smem[];
-    K1WriteSmem& S = *reinterpret_cast<K1WriteSmem*>(k1_smem);
-    const int tid = threadIdx.x;
-    for (int r = 0; r < 8; r++) S.sblk[r * K1_NT + tid] = make_uint4(0, 0, 0, 0);
-    S.tab.lane_scan[tid] = iv.scan;
+    K1WriteSmem<SLOTS>& S = *reinterpret_cast<K1WriteSmem<SLOTS>*>(k1_smem);
+    const int lane = threadIdx.x & 31;
+    const bool owner = lane < LPW;
+    // lanes without a stream run the same straight-line code on a neighbour's (never written) addresses
+    const int slot = (threadIdx.x >> 5) * LPW + (owner ? lane : lane - LPW);
+    if (owner) {
+        for (int r = 0; r < K1_BLKB / 16; r++) S.sblk[slot * (K1_BLKB / 16) + r] = make_uint4(0, 0, 0, 0);
+        S.tab.lane_scan[slot] = iv.scan;
+    }
     __syncthreads();
-    const bool cached = k1_tables_setup(P, S.tab);
+    const bool cached = k1_tables_setup(P, S.tab, SLOTS);
     uint32_t sdesc = 0;
     if (cached)
         for (int i = 0; i < S.tab.nscan; i++)
             if (S.tab.scan_id[i] == iv.scan) sdesc = smem_addr(&S.tab.desc[i][0]);
-    uint32_t sb = smem_addr(S.sblk) + tid * 16;  // this lane's row 0
+    uint32_t sb = smem_addr(S.sblk) + slot * K1_BLKB;  // this lane's row 0
+    const int wslot0 = (threadIdx.x >> 5) * LPW;
+    uint32_t sbw = smem_addr(S.sblk) + wslot0 * K1_BLKB, siw = smem_addr(S.sinfo) + wslot0 * 8;
     uint32_t su = smem_addr(S.tab.unzig);
     uint32_t tb = smem_addr(&S.tab);
-    uint32_t rc = smem_addr(S.ring) + tid * 4;
+    uint32_t rc = smem_addr(S.ring) + slot * 4;
     // opaque copies: keeps the shared-window address arithmetic out of the symbol loop
     asm volatile("mov.u32 %0, %0;" : "+r"(sb));
     asm volatile("mov.u32 %0, %0;" : "+r"(su));
     asm volatile("mov.u32 %0, %0;" : "+r"(tb));
     asm volatile("mov.u32 %0, %0;" : "+r"(rc));
-    if (cached) k1_lane_loop<true, SUB>(P, iv, st, sb, su, sdesc, tb, rc);
-    else k1_lane_loop<false, SUB>(P, iv, st, sb, su, 0, tb, rc);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sbw));
+    asm volatile("mov.u32 %0, %0;" : "+r"(siw));
+    if (cached) k1_lane_loop<SLOTS, LPW, true, SUB>(P, iv, st, sb, su, sdesc, tb, rc, sbw, siw);
+    else k1_lane_loop<SLOTS, LPW, false, SUB>(P, iv, st, sb, su, 0, tb, rc, sbw, siw);
 }
 
-// K1a: one lane per restart interval.
-__global__ void __launch_bounds__(K1_NT, 4) k1_lane_per_interval(const K1Params P) {
-    const int tid = threadIdx.x;
-    const int gid = blockIdx.x * K1_NT + tid;
-    // lanes past the end of the interval list idle through the loop (its head is a warp vote)
-    const bool live = gid < P.n_iv;
-    const ZpxIntervalDev iv = P.ivs[live ? gid : P.n_iv - 1];
+// K1a: one lane per restart interval, LPW intervals per warp.
+template <int LPW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 ? (LPW <= 20 ? 4 : 3) : 4)) k1_lane_per_interval(const K1Params P) {
+    const int lane = threadIdx.x & 31;
+    // lanes past LPW shadow the stream of lane - LPW (same interval, so every table address they form is valid)
+    // and lanes past the end of the interval list the last interval; both idle through the loop
+    const int gid = (blockIdx.x * WARPS + (threadIdx.x >> 5)) * LPW + (lane < LPW ? lane : lane - LPW);
+    const bool live = lane < LPW && gid < P.n_iv;
+    const ZpxIntervalDev iv = P.ivs[gid < P.n_iv ? gid : P.n_iv - 1];
     K1Start st;
     st.bitpos = 0;
     st.k = 0;
@@ -338,15 +432,16 @@ __global__ void __launch_bounds__(K1_NT, 4) k1_lane_per_interval(const K1Params 
     st.j0 = 0;
     st.count = live ? iv.n_blocks : 0;
     st.probe = false;
-    k1_cta_run<false>(P, iv, st);
+    k1_cta_run<LPW, WARPS, false>(P, iv, st);
 }
 
 // K1b, last pass (zpx_k1s.cu): one lane per sub-sequence, 32 consecutive sub-sequences of one segment per warp.
 // Every lane starts from its true state (found by k1s_sync), skips the tail of a block begun in the previous
 // sub-sequence and writes the blocks that START inside its own (their number and the DC predictors at that
 // point come from k1s_scan), running past its boundary to finish the last one.
-__global__ void __launch_bounds__(K1_NT, 4) k1s_write(const K1SParams P) {
-    const int wid = blockIdx.x * (K1_NT / 32) + (threadIdx.x >> 5);
+constexpr int K1S_WWARPS = 4;  // warps per CTA of k1s_write
+__global__ void __launch_bounds__(K1S_WWARPS * 32, 4) k1s_write(const K1SParams P) {
+    const int wid = blockIdx.x * K1S_WWARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const bool wv = wid < P.n_warps;
     const ZpxWarpDev w = P.warps[wv ? wid : P.n_warps - 1];
@@ -369,32 +464,41 @@ __global__ void __launch_bounds__(K1_NT, 4) k1s_write(const K1SParams P) {
     st.count = valid && next > excl ? next - excl : 0;
     // probe the symbol after the lane's last block if the lane skipped an invalid code and a block follows
     st.probe = valid && P.s_bad[t] != 0 && st.j0 + st.count < iv.n_blocks;
-    k1_cta_run<true>(P.k1, iv, st);
+    k1_cta_run<32, K1S_WWARPS, true>(P.k1, iv, st);
 }
 
-template <typename K>
-static cudaError_t k1_smem_attr(K kernel) {
-    static bool done = false;
-    if (done) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1WriteSmem));
-    if (e == cudaSuccess) done = true;
-    return e;
+// Streams per warp for a batch of n intervals: the narrowest warps whose single wave still holds the whole batch
+// (capacity = SMs x resident CTAs x warps x LPW); 32 when no width does (several waves: full warps do the most
+// work per issued instruction).  ZPX_K1_LPW / ZPX_K1_WARPS override (experiments).
+static int k1_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
-cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s) {
-    if (P.n_iv <= 0) return cudaSuccess;
-    cudaError_t e = k1_smem_attr(k1_lane_per_interval);
+template <int LPW, int WARPS>
+static cudaError_t k1_launch_lpw(const K1Params& P, cudaStream_t s) {
+    constexpr int per_cta = WARPS * LPW;
+    const size_t smem = sizeof(K1WriteSmem<per_cta>);
+    cudaError_t e = cudaFuncSetAttribute(k1_lane_per_interval<LPW, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k1_lane_per_interval<<<(P.n_iv + K1_NT - 1) / K1_NT, K1_NT, sizeof(K1WriteSmem), s>>>(P);
+    k1_lane_per_interval<LPW, WARPS><<<(P.n_iv + per_cta - 1) / per_cta, WARPS * 32, smem, s>>>(P);
     return cudaGetLastError();
+}
+
+cudaError_t k1_launch_lane_per_interval(const K1Params& P, int sm_count, cudaStream_t s) {
+    if (P.n_iv <= 0) return cudaSuccess;
+    (void)sm_count;
+    const int lpw = k1_env("ZPX_K1_LPW", 32), warps = k1_env("ZPX_K1_WARPS", 4);
+    if (lpw == 16) return warps == 8 ? k1_launch_lpw<16, 8>(P, s) : k1_launch_lpw<16, 4>(P, s);
+    return warps == 8 ? k1_launch_lpw<32, 8>(P, s) : k1_launch_lpw<32, 4>(P, s);
 }
 
 cudaError_t k1s_launch_write(const K1SParams& P, cudaStream_t s) {
     if (P.n_warps <= 0) return cudaSuccess;
-    cudaError_t e = k1_smem_attr(k1s_write);
+    const size_t smem = sizeof(K1WriteSmem<K1S_WWARPS * 32>);
+    cudaError_t e = cudaFuncSetAttribute(k1s_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int wpc = K1_NT / 32;
-    k1s_write<<<(P.n_warps + wpc - 1) / wpc, K1_NT, sizeof(K1WriteSmem), s>>>(P);
+    k1s_write<<<(P.n_warps + K1S_WWARPS - 1) / K1S_WWARPS, K1S_WWARPS * 32, smem, s>>>(P);
     return cudaGetLastError();
 }
 

@@ -22,10 +22,11 @@
 
 namespace zpx {
 
-constexpr int K1_NT = 128;       // lanes per CTA
+constexpr int K1_MAXSLOTS = 256;  // lanes with a stream ("slots") per CTA, at most
 constexpr int K1_RW = 16;        // ring words per lane (64 bytes)
-constexpr int K1_TOPUP = 8;      // symbols between two top-ups: after one, >= 4*K1_RW - 15 = 49 bytes lie ahead, and
-                                 // 8 symbols take at most 8 * 32 bits = 32 bytes, the window 8 more
+constexpr int K1_TOPUP = 8;      // AC symbols between two top-ups: after one, >= 4*K1_RW - 15 = 49 bytes lie ahead; a DC
+                                 // symbol and 8 AC symbols take at most 9 * 32 bits = 36 bytes, and the three-word
+                                 // window of the write kernels reaches at most 11 bytes further
 constexpr int K1_DLB = 7;        // first-level bits of DC tables in shared memory
 constexpr int K1_ALB = 9;        //                     AC tables
 constexpr int K1_MAXT = 12;      // tables cached per CTA
@@ -66,21 +67,23 @@ __device__ __forceinline__ void sts_zero16(uint32_t addr) {
 // fields of a ZPX_FE entry: one PRMT / SHF each
 __device__ __forceinline__ int fe_tot(uint32_t e) { return (int)__byte_perm(e, 0, 0x4440); }
 __device__ __forceinline__ int fe_len(uint32_t e) { return (int)__byte_perm(e, 0, 0x4441); }
-__device__ __forceinline__ int fe_size(uint32_t e) { return (int)__byte_perm(e, 0, 0x4442); }
+__device__ __forceinline__ int fe_s32(uint32_t e) { return (int)__byte_perm(e, 0, 0x4442); }  // 32 - value bits
 __device__ __forceinline__ int fe_adv(uint32_t e) { return (int)(e >> 24); }  // special bit is clear where this is used
-// RECEIVE + EXTEND (decoder.zig:1115-1134) on the `size` bits at the top of t (size 0 -> 0): PTX shr clamps a
-// shift by 32 to zero
-__device__ __forceinline__ int fe_extend(uint32_t t, int size) {
-    uint32_t v;
-    asm("shr.u32 %0, %1, %2;" : "=r"(v) : "r"(t), "r"(32 - size));
-    return (int)v + (((int)t >= 0) ? 1 - (1 << size) : 0);
+// RECEIVE + EXTEND (decoder.zig:1115-1134) on the value bits at the top of t, s32 = 32 - their number (32: no value
+// bits -> 0): PTX shr clamps a shift by 32 to zero.  A value whose first bit is 0 is negative: v - (2^size - 1).
+__device__ __forceinline__ int fe_extend(uint32_t t, int s32) {
+    uint32_t v, m;
+    asm("shr.u32 %0, %1, %2;" : "=r"(v) : "r"(t), "r"(s32));
+    asm("shr.u32 %0, %1, %2;" : "=r"(m) : "r"(0xffffffffu), "r"(s32));
+    return (int)t >= 0 ? (int)(v - m) : (int)v;
 }
 
 // ---------------------------------------------------------------------------
 // reader
 // ---------------------------------------------------------------------------
+template <int RS>  // bytes between consecutive ring words of one lane = 4 * (lanes with a stream per CTA)
 struct RingReader {
-    uint32_t ring;       // shared address of this lane's column: word slot s at ring + s * (K1_NT * 4)
+    uint32_t ring;       // shared address of this lane's column: word slot s at ring + s * RS
     const uint8_t* src;  // first byte of the interval in the unstuffed blob (16-byte aligned)
     uint32_t bitpos;     // next unread bit, from src
     uint32_t endbits;    // 8 * unstuffed length: a symbol that ends beyond it needed bits the stream does not have
@@ -96,11 +99,11 @@ struct RingReader {
     // chunks can be added as long as the one that holds the read position stays in the ring
     __device__ __forceinline__ void topup() {
         while (wbyte - ((bitpos >> 7) << 4) <= (uint32_t)(4 * K1_RW - 16)) {
-            const uint32_t a = ring + ((wbyte >> 2) & (uint32_t)(K1_RW - 1)) * (uint32_t)(K1_NT * 4);
+            const uint32_t a = ring + ((wbyte >> 2) & (uint32_t)(K1_RW - 1)) * (uint32_t)RS;
             sts_u32(a, __byte_perm(nxt.x, 0, 0x0123));
-            sts_u32(a + K1_NT * 4, __byte_perm(nxt.y, 0, 0x0123));
-            sts_u32(a + 2 * K1_NT * 4, __byte_perm(nxt.z, 0, 0x0123));
-            sts_u32(a + 3 * K1_NT * 4, __byte_perm(nxt.w, 0, 0x0123));
+            sts_u32(a + RS, __byte_perm(nxt.y, 0, 0x0123));
+            sts_u32(a + 2 * RS, __byte_perm(nxt.z, 0, 0x0123));
+            sts_u32(a + 3 * RS, __byte_perm(nxt.w, 0, 0x0123));
             wbyte += 16;
             nxt = fetch(wbyte);
         }
@@ -123,13 +126,13 @@ struct RingReader {
         wbyte = 4 * K1_RW;
         nxt = make_uint4(0u, 0u, 0u, 0u);
     }
+    // shared address of ring word (bitpos >> 5) + d
+    __device__ __forceinline__ uint32_t word_addr(uint32_t d) const {
+        return ring + (((bitpos >> 5) + d) & (uint32_t)(K1_RW - 1)) * (uint32_t)RS;
+    }
     // the next 32 bits
     __device__ __forceinline__ uint32_t peek() const {
-        const uint32_t t = bitpos << 4;  // word index * (K1_NT * 4), K1_NT * 4 = 512
-        static_assert(K1_NT * 4 == 512, "ring column stride");
-        const uint32_t w0 = lds_u32(ring + (t & (uint32_t)((K1_RW - 1) * 512)));
-        const uint32_t w1 = lds_u32(ring + ((t + 512u) & (uint32_t)((K1_RW - 1) * 512)));
-        return __funnelshift_l(w1, w0, bitpos);
+        return __funnelshift_l(lds_u32(word_addr(1)), lds_u32(word_addr(0)), bitpos);
     }
     __device__ __forceinline__ bool overrun() const { return bitpos > endbits; }
 };
@@ -152,22 +155,23 @@ struct K1Tables {
     uint32_t tab_id[K1_MAXT];   // device table index of each cache slot
     uint32_t tab_lut[K1_MAXT];  // word offset of the slot's LUT inside lut[]
     uint32_t tab_bits[K1_MAXT]; // first-level bits of the slot: K1_DLB (a DC table) or K1_ALB
-    uint32_t lane_scan[K1_NT];
+    uint32_t lane_scan[K1_MAXSLOTS];
     // zig-zag index -> byte offset of that coefficient inside a lane's block in the write kernels
-    // (row * K1_NT * 16 + column * 2); padded: k + run <= 78
+    // (row * 16 + column * 2); padded: k + run <= 78
     uint16_t unzig[80];
     int nscan, ntab, ok;
 };
 
-// Collect the distinct scans and Huffman tables of the CTA's lanes (lane_scan[] filled by the caller, followed by
-// __syncthreads) and stage them.  Returns false when they do not fit: the CTA then reads the tables in HBM.
-// Ends with __syncthreads.
-__device__ __forceinline__ bool k1_tables_setup(const K1Params& P, K1Tables& T) {
+// Collect the distinct scans and Huffman tables of the CTA's `slots` streams (lane_scan[] filled by the caller,
+// followed by __syncthreads) and stage them.  Returns false when they do not fit: the CTA then reads the tables in
+// HBM.  Ends with __syncthreads.
+__device__ __forceinline__ bool k1_tables_setup(const K1Params& P, K1Tables& T, const int slots) {
     const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
     if (tid == 0) {
         int ns = 0, nt = 0, ok = 1;
         uint32_t words = 0;
-        for (int l = 0; l < K1_NT && ok; l++) {
+        for (int l = 0; l < slots && ok; l++) {
             const uint32_t scn = T.lane_scan[l];
             if (l > 0 && scn == T.lane_scan[l - 1]) continue;
             int f = -1;
@@ -210,7 +214,7 @@ __device__ __forceinline__ bool k1_tables_setup(const K1Params& P, K1Tables& T) 
     }
     if (tid < 80) {
         const int nat = tid < 64 ? c_unzig[tid] : 63;
-        T.unzig[tid] = (uint16_t)((nat >> 3) * (K1_NT * 16) + (nat & 7) * 2);
+        T.unzig[tid] = (uint16_t)((nat >> 3) * 16 + (nat & 7) * 2);
     }
     __syncthreads();
     const bool cached = T.ok != 0;
@@ -220,7 +224,7 @@ __device__ __forceinline__ bool k1_tables_setup(const K1Params& P, K1Tables& T) 
             const uint32_t w0 = T.tab_lut[s];
             const int bits = (int)T.tab_bits[s];
             const ZpxHuffDev* __restrict__ tab = &P.huff[T.tab_id[s]];
-            for (int i = tid; i < (1 << bits); i += K1_NT) {
+            for (int i = tid; i < (1 << bits); i += nthr) {
                 uint32_t e = __ldg(&tab->fast[i << (ZPX_LUT_BITS - bits)]);
                 if (((e >> 8) & 0xffu) > (uint32_t)bits) e = 0;
                 T.lut[w0 + i] = e;
@@ -229,7 +233,7 @@ __device__ __forceinline__ bool k1_tables_setup(const K1Params& P, K1Tables& T) 
                 T.lim[s][tid] = __ldg(&tab->limit[tid + 1]);
                 T.valoff[s][tid] = __ldg(&tab->valoff[tid + 1]);
             }
-            for (int i = tid; i < 64; i += K1_NT)
+            for (int i = tid; i < 64; i += nthr)
                 reinterpret_cast<uint32_t*>(T.vals[s])[i] = __ldg(reinterpret_cast<const uint32_t*>(tab->vals) + i);
         }
     }
@@ -260,7 +264,7 @@ __device__ __forceinline__ unsigned long long k1_pack_symbol(uint32_t sym, int l
         else if (r == 0) { size = 0; adv = 64; }
         else { size = 0; adv = 64; special = 1; rr = r; }
     }
-    const uint32_t e = ZPX_FE((uint32_t)len + size, len, special ? rr : size, adv, special);
+    const uint32_t e = special ? ZPX_FE_RUN((uint32_t)len, len, rr) : ZPX_FE((uint32_t)len + size, len, size, adv, 0);
     return (unsigned long long)e | ((unsigned long long)(uint32_t)err << 32);
 }
 

@@ -29,7 +29,8 @@
 
 namespace zpx {
 
-constexpr int K1S_NT = K1_NT;  // threads per CTA (4 warps)
+constexpr int K1S_NT = 128;     // threads per CTA (4 warps), one stream per thread
+constexpr int K1S_RS = K1S_NT * 4;  // ring word stride
 
 __device__ __forceinline__ unsigned long long pack_state(uint32_t pos, int c, int z) {
     return (unsigned long long)pos | ((unsigned long long)(uint32_t)c << 32) | ((unsigned long long)(uint32_t)z << 40);
@@ -89,7 +90,7 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
         }
     }
     uint32_t thr = (L.bnd - (3 - m) * step) * 8u;  // m == 3: the boundary
-    RingReader rd;
+    RingReader<K1S_RS> rd;
     rd.init(ring_col, P.ublob, L.iv->ustart, L.iv->ulen, (uint32_t)in);
     int c = (int)((in >> 32) & 0xff), k = (int)((in >> 40) & 0xff);
     const int nblk = sc->interleaved ? sc->nblk : 1;
@@ -162,22 +163,22 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
                     e = (uint32_t)r;
                     if ((int)(r >> 32) == ZPX_E_BadHuffmanCode) {
                         bad = 1;
-                        e = 1u;  // invalid: one bit further, same state (tot = 1, adv = 0)
+                        e = 1u | 32u << 16;  // invalid: one bit further, same state (tot = 1, no value bits, adv = 0)
                     } else if (e >> 31) {
                         // EOB run: r more bits belong to the symbol
                         const uint32_t len = (e >> 8) & 0xffu, rr = (e >> 16) & 0xffu;
                         e = ZPX_FE(len + rr, len, 0, 64, 0);
                     }
                 }
-                const int len = fe_len(e), size = fe_size(e);
+                const int len = fe_len(e), s32 = fe_s32(e);
                 int tot = fe_tot(e);
                 const int adv = fe_adv(e);
                 if (isdc && adv) {
-                    const int v = fe_extend(hi << len, size);
+                    const int v = fe_extend(hi << len, s32);
                     const int comp = rotate ? c : (int)(bi.z & 0xff);
                     if (comp == 0) d0 += v; else if (comp == 1) d1 += v; else if (comp == 2) d2 += v; else d3 += v;
                     n++;
-                } else if (k + adv - 1 > 63 && size != 0) {
+                } else if (k + adv - 1 > 63 && s32 != 32) {
                     tot = len;  // decoder.zig:1393-1395: run past the block end, the value bits stay unread
                 }
                 k += adv;
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int 
     lane_setup(P.k1, w, lane, L);
     S.tab.lane_scan[threadIdx.x] = L.iv->scan;
     __syncthreads();
-    const bool cached = k1_tables_setup(P.k1, S.tab);
+    const bool cached = k1_tables_setup(P.k1, S.tab, K1S_NT);
     if (!wv) return;
     uint32_t sdesc = 0;
     if (cached)

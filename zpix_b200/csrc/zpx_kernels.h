@@ -11,6 +11,7 @@ namespace zpx {
 struct K1Params {
     const uint8_t* blob;          // entropy-coded bytes of the whole device batch, still byte-stuffed (progressive scans
                                   // read it directly, zpx_k3.cu)
+    int dbg;                      // experiments only (ZPX_K1_DBG): bit 0 = skip the coefficient stores
     const uint8_t* ublob;         // sequential scans: the same bytes with the stuffing removed (k0_unstuff), one
                                   // 16-byte aligned run per restart interval (ZpxIntervalDev::ustart / ulen)
     const ZpxIntervalDev* ivs;
@@ -26,7 +27,7 @@ struct K1Params {
 };
 // ---- K0: remove the byte stuffing (FF 00 -> FF) of the sequential scans' restart intervals, one warp per piece ----
 cudaError_t k0_launch_unstuff(const uint8_t* blob, uint8_t* ublob, const ZpxSegDev* segs, int n_segs, cudaStream_t s);
-cudaError_t k1_launch_lane_per_interval(const K1Params& P, cudaStream_t s);
+cudaError_t k1_launch_lane_per_interval(const K1Params& P, int sm_count, cudaStream_t s);
 
 // self-synchronising sub-sequence decoder (streams without DRI, or few large intervals)
 struct K1SParams {

@@ -541,7 +541,7 @@ uint32_t zpx_fast_entry(bool is_ac, int len, int sym) {
         if (sym > 16) { special = 1; size = 0; }
     } else {
         const uint32_t r = (uint32_t)sym >> 4, s2 = (uint32_t)sym & 15;
-        if (s2 != 0) { size = s2; adv = r + 1; }
+        if (s2 != 0) { size = s2; adv = r + 1; special = s2 >= 13 ? 1 : 0; }
         else if (r == 15) { size = 0; adv = 16; }
         else if (r == 0) { size = 0; adv = 64; }
         else { size = 0; adv = 64; special = 1; }
