@@ -199,7 +199,8 @@ int32_t zpx_batch_decode(zpx_batch *b, void *stream);
  * (= 4*width).  status receives the final per-image status (may be NULL). */
 int32_t zpx_batch_fetch_rgba(zpx_batch *b, uint8_t *const *out, const size_t *out_stride, int32_t *status);
 /* Copy the native variant's .pixels buffer (exact layout of the Image jpeg.load
- * returns: MCU-padded Gray / planar YCbCr, or 4*W*H RGBA / CMYK). */
+ * returns: MCU-padded Gray / planar YCbCr, or 4*W*H RGBA / CMYK).  Images that took the fused kernel have planes
+ * only if the batch was opened with ZPX_OPT_NATIVE_PLANES != 0 (else their status becomes ZPX_E_UNSUPPORTED_STREAM). */
 int32_t zpx_batch_fetch_native(zpx_batch *b, uint8_t *const *out, int32_t *status);
 /* Final per-image status after decode (header errors, device-detected entropy errors). */
 int32_t zpx_batch_status(zpx_batch *b, int32_t *status);
@@ -208,6 +209,19 @@ const void *zpx_batch_device_rgba(const zpx_batch *b, int32_t i);
 /* Test hook: copy image i's int16 coefficient blocks (128 B each, natural order,
  * un-swizzled, scan order for interleaved frames / per-component raster otherwise). */
 int32_t zpx_batch_fetch_coefficients(zpx_batch *b, int32_t i, int16_t *out, size_t cap_blocks, size_t *n_blocks);
+/* Test hooks: the reconstruction kernels (reconstructBlock decoder.zig:1553-1634, idct.zig:77-201, rgbaPixels
+ * image.zig:103-130 + toRGBA color.zig:90-126, convertToRGB / applyBlack decoder.zig:751-902) without the entropy
+ * stage.  zpx_batch_open_synthetic makes a batch of ONE sequential frame from its geometry alone: comp_hv[c] =
+ * h << 4 | v, quant = ncomp x 64 values in zig-zag order as a DQT segment holds them (8- or 16-bit), mode 0 gray,
+ * 1 YCbCr, 2 RGB-tagged, 3 CMYK, 4 YCbCrK.  After zpx_batch_upload, zpx_batch_set_coefficients injects the frame's
+ * int16 blocks (natural order, the block order zpx_batch_fetch_coefficients returns); zpx_batch_decode then runs
+ * the reconstruction kernels only and the fetch calls work as usual. */
+int32_t zpx_batch_open_synthetic(zpx_ctx *ctx, int32_t width, int32_t height, int32_t ncomp, const uint8_t *comp_hv,
+                                 const uint16_t *quant, int32_t mode, zpx_batch **out);
+int32_t zpx_batch_set_coefficients(zpx_batch *b, int32_t i, const int16_t *blocks, size_t n_blocks);
+/* The kernels' colour functions on n free-standing samples: mode 1 {Y,Cb,Cr} (3 bytes each), 3 {C,M,Y,K} as stored
+ * in Image{.CMYK}, 4 {Y,Cb,Cr,K plane byte}; rgba receives 4 bytes per sample. */
+int32_t zpx_test_colour(zpx_ctx *ctx, int32_t mode, const uint8_t *samples, size_t n, uint8_t *rgba);
 int32_t zpx_batch_timing(const zpx_batch *b, int32_t device_index, zpx_timing *out);
 void zpx_batch_close(zpx_batch *b);
 
@@ -215,6 +229,13 @@ void zpx_batch_close(zpx_batch *b);
  * (sizes from zpx_probe / zpx_batch_info). */
 int32_t zpx_decode_batch_rgba(zpx_ctx *ctx, const uint8_t *const *bufs, const size_t *lens, int32_t n,
                               uint8_t *const *out, const size_t *out_stride, int32_t *status);
+
+/* The same for the value jpeg.load itself returns (decoder.zig:361-370): out[i] receives the native variant's
+ * .pixels buffer, zpx_image_info.native_len bytes -- MCU-padded Gray / planar YCbCr (Y, Cb, Cr with makeImg's
+ * strides), or 4*w*h RGBA / CMYK.  What `jpeg.loadBatch` binds when the caller wants Image{.YCbCr} like the
+ * reference; 2.7x fewer bytes to bring back than RGBA for 4:2:0. */
+int32_t zpx_decode_batch_native(zpx_ctx *ctx, const uint8_t *const *bufs, const size_t *lens, int32_t n,
+                                uint8_t *const *out, int32_t *status);
 
 /* Header-only probe of one buffer (decodeConfig, decoder.zig:178); no GPU needed. */
 int32_t zpx_probe(const uint8_t *buf, size_t len, zpx_image_info *out);
@@ -232,6 +253,13 @@ typedef struct zpx_parse_report {
     int32_t fused;         /* 1 if the image takes the fused IDCT/colour kernel */
     int32_t mode;          /* colour exit: 0 gray, 1 YCbCr, 2 RGB-tagged, 3 CMYK, 4 YCbCrK */
     uint64_t entropy_bytes;
+    /* sequential scans: what the unstuffing pass (k0_unstuff) is handed */
+    uint64_t stuffed_bytes;    /* FF 00 pairs inside the restart intervals */
+    uint64_t unstuffed_bytes;  /* bytes of the intervals once the stuffing is removed */
+    int32_t n_pieces;          /* work units of the unstuffing kernel */
+    int32_t max_piece;         /* largest one, raw bytes */
+    int32_t pieces_ok;         /* 1: the pieces tile every interval and none starts on the 0x00 of a pair */
+    int32_t reserved;
 } zpx_parse_report;
 int32_t zpx_parse_report_of(const uint8_t *buf, size_t len, zpx_image_info *info, zpx_parse_report *rep);
 
@@ -248,6 +276,11 @@ int32_t zpx_partition(const uint64_t *weights, int32_t n, int32_t n_devices, int
                                     28 MB of compressed input per chunk; < 0 = off) */
 #define ZPX_OPT_PIPELINE_RAMP 6  /* 1 (default): the pipeline's first two chunks are 1/4 and 1/2 of the chunk size */
 #define ZPX_OPT_PIPELINE_WORKERS 7 /* host threads (each with its own device buffers) of that pipeline: 1..8, default 3 */
+#define ZPX_OPT_NATIVE_PLANES 9 /* 0 (default): native planes exist only for images on the unfused kernels;
+                                   1: the fused kernel writes them too, beside the RGBA (zpx_batch_fetch_native works
+                                   for every image); 2: planes only, no RGBA.  Read when a batch is opened. */
+#define ZPX_OPT_TEST_WIDE 8  /* test hook: 1 = frames filled by zpx_batch_set_coefficients take the kernels' exact
+                                all-AC-zero-row IDCT variant whatever their coefficients */
 int32_t zpx_ctx_set_option(zpx_ctx *ctx, int32_t option, int64_t value);
 
 /* ---- misc ---------------------------------------------------------------- */

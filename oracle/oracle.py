@@ -97,6 +97,14 @@ def lib():
         L.zo_cmyk_to_rgba16.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint8, C.c_void_p]
         L.zo_load_rgba.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.zo_load_rgba.restype = C.c_int
+        L.zo_reconstruct_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.zo_reconstruct_blocks.restype = None
+        L.zo_ycbcr_to_rgba8_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.zo_ycbcr_to_rgba8_batch.restype = None
+        L.zo_cmyk_to_rgba8_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.zo_cmyk_to_rgba8_batch.restype = None
+        L.zo_compare_rgba.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.zo_compare_rgba.restype = C.c_int
         _lib = L
     return _lib
 
@@ -231,3 +239,33 @@ def cmyk_to_rgba8(c: int, m: int, y: int, k: int):
     out = (C.c_uint32 * 4)()
     lib().zo_cmyk_to_rgba16(c, m, y, k, out)
     return tuple(v >> 8 for v in out)
+
+
+def reconstruct_blocks(coef: np.ndarray, quant_zz: np.ndarray) -> np.ndarray:
+    """reconstructBlock (decoder.zig:1553-1634) on free-standing blocks: coef (n, 64) natural order, quant_zz (64,)
+    zig-zag order -> (n, 8, 8) uint8."""
+    c = np.ascontiguousarray(coef, dtype=np.int32).reshape(-1, 64)
+    q = np.ascontiguousarray(quant_zz, dtype=np.int32).reshape(64)
+    out = np.empty((c.shape[0], 8, 8), np.uint8)
+    lib().zo_reconstruct_blocks(c.ctypes.data, q.ctypes.data, c.shape[0], out.ctypes.data)
+    return out
+
+
+def ycbcr_to_rgba8_batch(ycc: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(ycc, dtype=np.uint8).reshape(-1, 3)
+    out = np.empty((a.shape[0], 4), np.uint8)
+    lib().zo_ycbcr_to_rgba8_batch(a.ctypes.data, a.shape[0], out.ctypes.data)
+    return out
+
+
+def cmyk_to_rgba8_batch(cmyk: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(cmyk, dtype=np.uint8).reshape(-1, 4)
+    out = np.empty((a.shape[0], 4), np.uint8)
+    lib().zo_cmyk_to_rgba8_batch(a.ctypes.data, a.shape[0], out.ctypes.data)
+    return out
+
+
+def compare_rgba(data: bytes, got_ptr: int, got_len: int) -> int:
+    """jpeg.load + rgbaPixels of `data` against the bytes at got_ptr: 0 identical, 1 different, < 0 -(error code).
+    Releases the GIL: callable from a thread pool."""
+    return lib().zo_compare_rgba(data, len(data), got_ptr, got_len)

@@ -676,11 +676,24 @@ static int make_img(decoder *d, int32_t mxx, int32_t myy) {
 }
 
 /* decoder.zig:1553-1634 */
-static int reconstruct_block(decoder *d, int32_t *b, int32_t bx, int32_t by, int ci) {
-    const int32_t *qt = d->quant[d->comp[ci].tq];
+/* the arithmetic of reconstructBlock (decoder.zig:1564-1570, 1611-1633): dequantise (tables in zig-zag order),
+ * idct.transform, level shift, clamp, store 8x8 */
+static void dequant_idct_store(int32_t *b, const int32_t *qt, uint8_t *dst, size_t stride) {
     for (int zig = 0; zig < BLOCK_SIZE; zig++) b[unzig[zig]] = wmul(b[unzig[zig]], qt[zig]);
     zo_idct(b);
+    for (int y = 0; y < 8; y++) {
+        for (int x = 0; x < 8; x++) {
+            int32_t c = b[y * 8 + x];
+            if (c < -128) c = 0;
+            else if (c > 127) c = 255;
+            else c += 128;
+            dst[(size_t)y * stride + x] = (uint8_t)c;
+        }
+    }
+}
 
+static int reconstruct_block(decoder *d, int32_t *b, int32_t bx, int32_t by, int ci) {
+    const int32_t *qt = d->quant[d->comp[ci].tq];
     uint8_t *dst;
     size_t stride;
     if (d->num_components == 1) {
@@ -697,16 +710,18 @@ static int reconstruct_block(decoder *d, int32_t *b, int32_t bx, int32_t by, int
         default: return ZO_UnsupportedComponent;
         }
     }
-    for (int y = 0; y < 8; y++) {
-        for (int x = 0; x < 8; x++) {
-            int32_t c = b[y * 8 + x];
-            if (c < -128) c = 0;
-            else if (c > 127) c = 255;
-            else c += 128;
-            dst[(size_t)y * stride + x] = (uint8_t)c;
-        }
-    }
+    dequant_idct_store(b, qt, dst, stride);
     return ZO_OK;
+}
+
+/* test helper: reconstructBlock on n free-standing blocks (coef: int32[n][64], natural order as decoded; quant_zz:
+ * 64 values in zig-zag order as a DQT segment holds them; out: u8[n][64], row-major 8x8 each) */
+void zo_reconstruct_blocks(const int32_t *coef, const int32_t *quant_zz, size_t n, uint8_t *out) {
+    for (size_t i = 0; i < n; i++) {
+        int32_t b[BLOCK_SIZE];
+        memcpy(b, coef + i * BLOCK_SIZE, sizeof(b));
+        dequant_idct_store(b, quant_zz, out + i * BLOCK_SIZE, 8);
+    }
 }
 
 static void tap_block(decoder *d, int ci, int32_t bx, int32_t by, const int32_t *b) {
@@ -1366,4 +1381,41 @@ int zo_load_rgba(const uint8_t *data, size_t len, uint8_t *out, size_t out_cap, 
     }
     zo_free(&img);
     return ZO_OK;
+}
+
+/* test helpers: Color.toRGBA (color.zig:90-121) followed by the >> 8 of Image.rgbaPixels (image.zig:122-125) on n
+ * samples.  ycc: n x {Y, Cb, Cr}; cmyk: n x {C, M, Y, K} as stored in Image{.CMYK}; rgba: n x 4 bytes */
+void zo_ycbcr_to_rgba8_batch(const uint8_t *ycc, size_t n, uint8_t *rgba) {
+    for (size_t i = 0; i < n; i++) {
+        uint32_t c[4];
+        zo_ycbcr_to_rgba16(ycc[3 * i], ycc[3 * i + 1], ycc[3 * i + 2], c);
+        for (int k = 0; k < 4; k++) rgba[4 * i + k] = (uint8_t)(c[k] >> 8);
+    }
+}
+void zo_cmyk_to_rgba8_batch(const uint8_t *cmyk, size_t n, uint8_t *rgba) {
+    for (size_t i = 0; i < n; i++) {
+        uint32_t c[4];
+        zo_cmyk_to_rgba16(cmyk[4 * i], cmyk[4 * i + 1], cmyk[4 * i + 2], cmyk[4 * i + 3], c);
+        for (int k = 0; k < 4; k++) rgba[4 * i + k] = (uint8_t)(c[k] >> 8);
+    }
+}
+
+/* parity helper: jpeg.load + rgbaPixels of `data` compared with `got` (what the GPU path produced).
+ * Returns 0 when identical, 1 when the bytes (or the length) differ, a negative error code (-ZO_*) when the
+ * reference path fails on the file. */
+int zo_compare_rgba(const uint8_t *data, size_t len, const uint8_t *got, size_t got_len) {
+    zo_image img;
+    int e = zo_decode(data, len, &img);
+    if (e != ZO_OK) return -e;
+    size_t need = (size_t)4 * (size_t)img.width * (size_t)img.height;
+    int r = 1;
+    if (need == got_len) {
+        uint8_t *tmp = (uint8_t *)malloc(need ? need : 1);
+        if (!tmp) { zo_free(&img); return -ZO_OutOfMemory; }
+        zo_rgba_pixels(&img, tmp);
+        r = memcmp(tmp, got, need) != 0;
+        free(tmp);
+    }
+    zo_free(&img);
+    return r;
 }

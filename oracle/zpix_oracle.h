@@ -153,6 +153,15 @@ void zo_cmyk_to_rgba16(uint8_t c, uint8_t m, uint8_t y, uint8_t k, uint32_t out[
  * out may be NULL (a scratch buffer is used and freed). Returns error code. */
 int zo_load_rgba(const uint8_t *data, size_t len, uint8_t *out, size_t out_cap, int32_t *w, int32_t *h);
 
+/* Test helpers. reconstructBlock (decoder.zig:1553-1634) on n free-standing blocks: coef int32[n][64] natural
+ * order, quant_zz 64 values in zig-zag order, out u8[n][64]. */
+void zo_reconstruct_blocks(const int32_t *coef, const int32_t *quant_zz, size_t n, uint8_t *out);
+/* Color.toRGBA (color.zig:90-121) + the >> 8 of rgbaPixels (image.zig:122-125) on n samples */
+void zo_ycbcr_to_rgba8_batch(const uint8_t *ycc, size_t n, uint8_t *rgba);
+void zo_cmyk_to_rgba8_batch(const uint8_t *cmyk, size_t n, uint8_t *rgba);
+/* jpeg.load + rgbaPixels of data vs got: 0 identical, 1 different, < 0: -(error of the reference path) */
+int zo_compare_rgba(const uint8_t *data, size_t len, const uint8_t *got, size_t got_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -615,8 +615,8 @@ def test_empty_batch_and_api_contract(jpeg, ctx):
     assert res[0].name == "InvalidSOIMarker" and res[1].name == "UnexpectedEof"
 
 
-def test_idct_and_colour_exhaustive_blocks(jpeg, ctx):
-    """Property test of K2 through real files: random coefficient content at the extremes of the 8-bit
+def test_noise_images_at_quality_extremes(jpeg, ctx):
+    """K2 through real files (block-level property tests live in test_gpu_blocks.py): noise at the extremes of the 8-bit
     range (quality 100 and quality 1 images of pure noise) still matches the oracle bit for bit."""
     rng = np.random.default_rng(5)
     from PIL import Image
@@ -655,3 +655,76 @@ def test_cpp_host_layer_end_to_end(fixtures_dir, tmp_path):
             h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
         assert line.split()[1] == f"{want.width}x{want.height}"
         assert line.split()[2] == f"fnv1a={h:016x}", line
+
+
+def test_image_over_the_memory_budget_fails_alone(jpeg, fixtures_dir, monkeypatch):
+    """An image whose device buffers do not fit gets error.OutOfMemory (the reference's answer to a failed makeImg
+    allocation, decoder.zig:1708-1783) as ITS status; the rest of the batch decodes.  ZPX_IMAGE_BUDGET_MB shrinks the
+    budget so that an ordinary file plays the part of the 65535 x 65535 one."""
+    small = _read(fixtures_dir, "video-001.q50.420.jpeg")
+    big = S.encode(91000, 1920, 1080, subsampling="4:2:0", restart_rows=1)
+    monkeypatch.setenv("ZPX_IMAGE_BUDGET_MB", "4")   # 1080p needs ~17 MB, the fixtures ~0.1 MB
+    c = jpeg.Context([0])
+    outs, st = jpeg.decodeBatchOneCall([small, big, small], c)
+    assert st[0] == 0 and st[2] == 0 and jpeg.lib.zpx_error_name(st[1]).decode() == "OutOfMemory"
+    want = O.decode(small).rgbaPixels()
+    assert np.array_equal(outs[0], want) and np.array_equal(outs[2], want) and outs[1] is None
+    monkeypatch.delenv("ZPX_IMAGE_BUDGET_MB")
+    outs, st = jpeg.decodeBatchOneCall([small, big, small], c)
+    assert st == [0, 0, 0] and np.array_equal(outs[1], O.decode(big).rgbaPixels())
+    c.close()
+
+
+def test_results_read_after_a_decode_on_the_callers_stream(jpeg, fixtures_dir):
+    """zpx_batch_decode(b, stream) returns once the work is enqueued; status and pixels fetched right after, without
+    the caller synchronising, must still be the decode's (the library orders its own stream after the caller's)."""
+    import torch
+    datas = S.make_batch(2, 24, 1920, 1080, subsampling="4:2:0", restart_rows=1)
+    bad = datas[5][: len(datas[5]) // 2]
+    datas[5] = bad
+    c = jpeg.Context([0])
+    stream = torch.cuda.Stream()
+    with jpeg.Batch(c, datas) as b:
+        b.upload()
+        for _ in range(3):
+            b.decode(stream.cuda_stream)
+            outs, st = b.fetch_rgba()      # no stream.synchronize() in between
+            assert st[5] != 0 and all(s == 0 for i, s in enumerate(st) if i != 5)
+            for i in (0, 7, 23):
+                assert np.array_equal(outs[i], O.decode(datas[i]).rgbaPixels())
+    c.close()
+
+
+def test_native_batch_one_call(jpeg, fixtures_dir):
+    """zpx_decode_batch_native: the whole batch comes back as the Image variants jpeg.load returns -- planes of the
+    fused kernel (MCU padding included) for the ordinary files, unfused kernels for the rest -- through the chunk
+    pipeline, with a failing file in the middle."""
+    names = ["video-001.q50.420.jpeg", "video-001.q50.422.jpeg", "video-001.jpeg", "video-005.gray.jpeg", "video-001.221212.jpeg",
+             "video-001.q50.411.jpeg", "video-001.q50.410.jpeg", "video-001.q50.440.jpeg", "video-001.q50.420.progressive.jpeg",
+             "video-001.rgb.jpeg", "video-001.cmyk.jpeg", "video-001.restart2.jpeg"]
+    datas = [_read(fixtures_dir, n) for n in names]
+    datas += S.make_batch(2, 3, 1920, 1080, subsampling="4:2:0", restart_rows=1)
+    datas += [S.encode(54000, 513, 511, mode="L"), S.encode(54001, 641, 479, subsampling="4:4:4")]
+    bad = datas[0][: len(datas[0]) // 2]
+    batch = (datas + [bad]) * 6
+    for chunk in (0, 16, -1):
+        c = jpeg.Context([0])
+        c.set_option(4, chunk)
+        res = jpeg.decodeBatchNative(batch, c)
+        for k, (d, img) in enumerate(zip(batch, res)):
+            if d is bad:
+                assert isinstance(img, jpeg.JpegError) and img.name == "UnexpectedEof"
+                continue
+            ref = O.decode(d)
+            assert img.tag == ref.variant_name, k
+            if img.tag == "Gray":
+                assert np.array_equal(img.Gray.pixels.reshape(-1, img.Gray.stride), ref.pix)
+            elif img.tag == "YCbCr":
+                m = img.YCbCr
+                assert (m.y_stride, m.c_stride) == (ref.y_stride, ref.c_stride)
+                assert np.array_equal(m.y.reshape(-1, m.y_stride), ref.y)
+                assert np.array_equal(m.cb.reshape(-1, m.c_stride), ref.cb)
+                assert np.array_equal(m.cr.reshape(-1, m.c_stride), ref.cr)
+            else:
+                assert np.array_equal(img.payload.pixels.reshape(-1), ref.pix.reshape(-1))
+        c.close()

@@ -198,6 +198,42 @@ def test_probe_is_decode_config(zlib, fixtures_dir):
     assert jpeg.probeBuffer(_read(fixtures_dir, "iceberg.jpg")) and not jpeg.probeBuffer(b"\x89PNG")
 
 
+def test_probe_reports_the_sizes_of_the_full_parse(zlib, fixtures_dir):
+    """zpx_probe stops at the frame header (decodeConfig) but callers size their output buffers from it: variant,
+    MCU grid, strides and byte lengths must be those of the full parse (decoder.zig:1258-1263, 1708-1783)."""
+    L = zlib.lib
+    for name in sorted(os.listdir(fixtures_dir)):
+        data = np.frombuffer(_read(fixtures_dir, name), np.uint8)
+        a, b = zlib.ZpxImageInfo(), zlib.ZpxImageInfo()
+        rep = zlib.ZpxParseReport()
+        assert L.zpx_probe(data.ctypes.data, data.size, C.byref(a)) == 0, name
+        assert L.zpx_parse_report_of(data.ctypes.data, data.size, C.byref(b), C.byref(rep)) == 0
+        for f in ("width", "height", "num_components", "variant", "subsample_ratio", "mxx", "myy", "y_stride", "c_stride",
+                  "rgba_len", "native_len", "native_cb_off", "native_cr_off"):
+            assert getattr(a, f) == getattr(b, f), (name, f)
+        ref = O.decode(data.tobytes())
+        assert a.native_len == ref.pixels.size, name
+
+
+def test_unstuffing_plan_covers_every_interval(zlib, fixtures_dir):
+    """host side of k0_unstuff: the pieces the parser cuts never split an FF 00 pair and add up to the unstuffed
+    length (raw length minus stuffed zeros), for files with and without restart markers"""
+    L = zlib.lib
+    from tools import synth_jpeg as S
+    datas = [_read(fixtures_dir, n) for n in ("video-001.restart2.jpeg", "video-001.jpeg", "iceberg.jpg")]
+    datas.append(S.encode(70001, 640, 480, subsampling="4:2:0", restart_rows=1, quality=100))
+    for d in datas:
+        a = np.frombuffer(d, np.uint8)
+        info, rep = zlib.ZpxImageInfo(), zlib.ZpxParseReport()
+        assert L.zpx_parse_report_of(a.ctypes.data, a.size, C.byref(info), C.byref(rep)) == 0
+        sos = d.index(b"\xff\xda")
+        stuffed = d.count(b"\xff\x00", sos)
+        assert rep.stuffed_bytes == stuffed
+        assert rep.unstuffed_bytes + rep.stuffed_bytes + 2 * (rep.n_intervals - 1) <= rep.entropy_bytes + 2 * rep.n_intervals
+        assert rep.n_pieces >= rep.n_intervals and rep.max_piece <= 16384 + 2
+        assert rep.pieces_ok == 1
+
+
 def test_partition_rule(zlib):
     rng = np.random.default_rng(0)
     for n, nd in [(0, 1), (1, 8), (7, 2), (1024, 1), (1024, 2), (1024, 4), (1024, 8), (513, 8)]:

@@ -28,7 +28,8 @@ class ZpxParseReport(C.Structure):
     _fields_ = [
         ("status", C.c_int32), ("n_scans", C.c_int32), ("n_intervals", C.c_int32), ("pending_err", C.c_int32),
         ("pending_after_interval", C.c_int32), ("trailing_err", C.c_int32), ("fused", C.c_int32),
-        ("mode", C.c_int32), ("entropy_bytes", C.c_uint64),
+        ("mode", C.c_int32), ("entropy_bytes", C.c_uint64), ("stuffed_bytes", C.c_uint64), ("unstuffed_bytes", C.c_uint64),
+        ("n_pieces", C.c_int32), ("max_piece", C.c_int32), ("pieces_ok", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -63,10 +64,14 @@ SYMBOLS = [
     ("zpx_batch_status", C.c_int32, [_P, C.POINTER(C.c_int32)]),
     ("zpx_batch_device_rgba", _P, [_P, C.c_int32]),
     ("zpx_batch_fetch_coefficients", C.c_int32, [_P, C.c_int32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    ("zpx_batch_open_synthetic", C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.POINTER(_P)]),
+    ("zpx_batch_set_coefficients", C.c_int32, [_P, C.c_int32, _P, C.c_size_t]),
+    ("zpx_test_colour", C.c_int32, [_P, C.c_int32, _P, C.c_size_t, _P]),
     ("zpx_batch_timing", C.c_int32, [_P, C.c_int32, C.POINTER(ZpxTiming)]),
     ("zpx_batch_close", None, [_P]),
     ("zpx_decode_batch_rgba", C.c_int32, [_P, C.POINTER(_P), C.POINTER(C.c_size_t), C.c_int32, C.POINTER(_P),
                                           C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]),
+    ("zpx_decode_batch_native", C.c_int32, [_P, C.POINTER(_P), C.POINTER(C.c_size_t), C.c_int32, C.POINTER(_P), C.POINTER(C.c_int32)]),
     ("zpx_probe", C.c_int32, [_P, C.c_size_t, C.POINTER(ZpxImageInfo)]),
     ("zpx_parse_report_of", C.c_int32, [_P, C.c_size_t, C.POINTER(ZpxImageInfo), C.POINTER(ZpxParseReport)]),
     ("zpx_partition", C.c_int32, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),

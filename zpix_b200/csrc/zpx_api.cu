@@ -78,8 +78,10 @@ struct DevBuf {
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
+            (void)cudaGetLastError();  // the failed attempt must not be what the next launch check reports
             e = cudaMalloc(&p, bytes);
             want = bytes;
+            if (e != cudaSuccess) (void)cudaGetLastError();
         }
         if (e == cudaSuccess) cap = want;
         return e;
@@ -102,6 +104,7 @@ struct HostBuf {  // pinned
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
         if (e == cudaSuccess) cap = want;
+        else (void)cudaGetLastError();
         return e;
     }
     void release() {
@@ -114,6 +117,7 @@ struct HostBuf {  // pinned
 struct DeviceCtx {
     int dev = 0;
     int sm_count = 148;
+    size_t total_mem = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr};
     DevBuf blob, ublob, coef, out, planes, desc, status, subs, scratch;
@@ -161,8 +165,10 @@ struct DevicePlan {
     // descriptor buffer layout (byte offsets)
     size_t off_imgs = 0, off_scans = 0, off_ivs = 0, off_huff = 0, off_quant = 0, off_generic = 0, desc_bytes = 0;
     std::vector<uint64_t> out_off, plane_off0;  // per device image
+    std::vector<uint32_t> inject_flags;         // test hook (zpx_batch_set_coefficients): per image, copied over img_flags
     zpx_timing timing;
     bool uploaded = false, decoded = false;
+    int native = 0;  // ZPX_OPT_NATIVE_PLANES at the time the plan was built
 };
 
 }  // namespace
@@ -173,7 +179,7 @@ struct zpx_ctx {
     std::string last_cuda_str;
     std::atomic<uint64_t> launches{0};
     int64_t opt_entropy_mode = 0, opt_force_generic = 0, opt_subseq = 0, opt_pipeline_chunk = 0;
-    int64_t opt_pipeline_ramp = 1, opt_pipeline_workers = 3;
+    int64_t opt_pipeline_ramp = 1, opt_pipeline_workers = 3, opt_test_wide = 0, opt_native = 0;
     bool busy = false;
     const zpx_batch* resident = nullptr;  // the batch whose data currently occupies the device buffers
     std::vector<zpx_ctx*> shadows;  // further sets of device buffers/streams for the chunk pipeline of zpx_decode_batch_rgba
@@ -216,12 +222,6 @@ const char* const kErrNames[] = {
     "UnexpectedHuffmanCode", "TooManyCoefficients", "BadRSTMarker", "CreateImageFailed", "UnsupportedComponent",
     "InvalidImageType", "ConfigOnly", "OutOfMemory",
 };
-
-// can this image be decoded on the GPU by this build?
-int unsupported_reason(const ZpxParsed& p) {
-    (void)p;
-    return 0;
-}
 
 bool fused_eligible(const ZpxParsed& p) {
     if (p.progressive || p.scans.size() != 1) return false;
@@ -273,6 +273,7 @@ void build_plan(zpx_batch* b, int di) {
     DevicePlan& pl = b->plans[di];
     TableDedup dd;
     const bool force_generic = b->ctx->opt_force_generic != 0;
+    pl.native = (int)b->ctx->opt_native;
     std::map<int, int> group_ix;  // (h<<8|v<<4|nc) -> index
     for (size_t k = 0; k < pl.images.size(); k++) {
         const int bi = pl.images[k];
@@ -347,7 +348,7 @@ void build_plan(zpx_batch* b, int di) {
         pl.out_bytes += align_up((size_t)4 * p.width * p.height, 256);
         // native planes (generic path): exact makeImg layout: Y, Cb, Cr contiguous, then black
         pl.plane_off0.push_back(pl.plane_bytes);
-        if (!im.fused) {
+        if (!im.fused || pl.native != 0) {
             zpx_image_info info;
             zpx_fill_info(p, &info);
             size_t base = pl.plane_bytes;
@@ -375,6 +376,8 @@ void build_plan(zpx_batch* b, int di) {
                 }
             }
             pl.plane_bytes = align_up(base, 256);
+        }
+        if (!im.fused) {
             pl.generic.push_back((uint32_t)k);
             pl.generic_max_blocks = std::max<int>(pl.generic_max_blocks, (int)nblocks);
             pl.generic_max_pixels = std::max<size_t>(pl.generic_max_pixels, (size_t)p.width * p.height);
@@ -661,7 +664,11 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
     CU(ctx, cudaMemsetAsync(dc.status.p, 0xff, pl.imgs.size() * sizeof(unsigned long long), st));
     uint32_t* img_flags = (uint32_t*)((uint8_t*)dc.status.p + align_up(pl.imgs.size() * sizeof(unsigned long long), 256));
     CU(ctx, cudaMemsetAsync(img_flags, 0, pl.imgs.size() * sizeof(uint32_t), st));
-    if (pl.plane_bytes) CU(ctx, cudaMemsetAsync(dc.planes.p, 0, pl.plane_bytes, st));
+    if (!pl.inject_flags.empty())  // coefficients came from zpx_batch_set_coefficients, not from the entropy kernels
+        CU(ctx, cudaMemcpyAsync(img_flags, pl.inject_flags.data(), pl.imgs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    // (the unfused kernels leave the planes of components no scan covers at makeImg's zeros; the fused kernel
+    // writes every byte of its images' planes)
+    if (pl.plane_bytes && !pl.generic.empty()) CU(ctx, cudaMemsetAsync(dc.planes.p, 0, pl.plane_bytes, st));
 
     int k1_launches = 0, k2_launches = 0;
     // ---- K1: entropy decode ----
@@ -748,7 +755,8 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
     for (const FusedGroup& g : pl.groups) {
         K2Params k2;
         k2.coef = (const int16_t*)dc.coef.p;
-        k2.out = (uint8_t*)dc.out.p;
+        k2.out = pl.native == 2 ? nullptr : (uint8_t*)dc.out.p;
+        k2.planes = pl.native != 0 ? (uint8_t*)dc.planes.p : nullptr;
         k2.imgs = k1.imgs;
         k2.tiles = (const ZpxTileDev*)(desc + g.tiles_off);
         k2.quant = (const ZpxQuantDev*)(desc + pl.off_quant);
@@ -803,6 +811,10 @@ int collect_timing(zpx_batch* b, int di) {
     return ZPX_OK;
 }
 
+// Results are read on the context's own stream; the kernels may have been launched on the caller's
+// (zpx_batch_decode(b, stream)): order the former after the latter's last launch (event recorded there).
+cudaError_t after_decode(DeviceCtx& dc) { return cudaStreamWaitEvent(dc.stream, dc.ev[3], 0); }
+
 // combine header status, host-side pending errors and the device error records
 int finalize_status(zpx_batch* b) {
     if (b->status_ready) return ZPX_OK;
@@ -813,6 +825,7 @@ int finalize_status(zpx_batch* b) {
         DeviceCtx& dc = ctx->devs[di];
         CU(ctx, cudaSetDevice(dc.dev));
         CU(ctx, dc.hstatus.ensure(pl.imgs.size() * sizeof(unsigned long long)));
+        CU(ctx, after_decode(dc));
         CU(ctx, cudaMemcpyAsync(dc.hstatus.p, dc.status.p, pl.imgs.size() * sizeof(unsigned long long),
                                 cudaMemcpyDeviceToHost, dc.stream));
         CU(ctx, cudaStreamSynchronize(dc.stream));
@@ -894,6 +907,29 @@ int32_t zpx_parse_report_of(const uint8_t* buf, size_t len, zpx_image_info* info
             rep->pending_after_interval = s.err_after_interval;
         }
         if (!s.intervals.empty()) rep->entropy_bytes += s.intervals.back().limit - s.intervals.front().start;
+        if (p.progressive) continue;
+        rep->pieces_ok = 1;
+        for (const ZpxIntervalHost& iv : s.intervals) {
+            rep->stuffed_bytes += iv.n_stuffed;
+            rep->unstuffed_bytes += iv.limit - iv.start - iv.n_stuffed;
+            size_t at = iv.start;
+            uint32_t u = 0;
+            for (uint32_t q = 0; q < iv.n_segs; q++) {
+                const ZpxSegHost& sg = s.segs[iv.seg_first + q];
+                rep->n_pieces++;
+                rep->max_piece = std::max<int32_t>(rep->max_piece, (int32_t)sg.len);
+                bool ok = sg.src == at && sg.uoff == u && sg.len > 0;
+                // inside an interval every 0xFF opens a pair: a piece that starts with 0x00 after 0xFF splits one
+                if (sg.src > iv.start && buf[sg.src] == 0x00 && buf[sg.src - 1] == 0xff) ok = false;
+                uint32_t pairs = 0;
+                for (size_t k = sg.src; k + 1 < sg.src + sg.len; k++)
+                    if (buf[k] == 0xff && buf[k + 1] == 0x00) { pairs++; k++; }
+                at += sg.len;
+                u += sg.len - pairs;
+                if (!ok) rep->pieces_ok = 0;
+            }
+            if (at != iv.limit || u != iv.limit - iv.start - iv.n_stuffed) rep->pieces_ok = 0;
+        }
     }
     rep->trailing_err = p.trailing_err;
     rep->fused = (p.status == 0 && fused_eligible(p)) ? 1 : 0;
@@ -941,6 +977,11 @@ int32_t zpx_ctx_create(const int32_t* device_ids, int32_t n_devices, zpx_ctx** o
             return ZPX_E_CUDA;
         }
         cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, id);
+        {
+            size_t fr = 0, tot = 0;
+            if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) d.total_mem = tot;
+            else (void)cudaGetLastError();
+        }
         for (auto& ev : d.ev) cudaEventCreate(&ev);
         c->devs.push_back(d);
     }
@@ -987,6 +1028,11 @@ int32_t zpx_ctx_set_option(zpx_ctx* c, int32_t option, int64_t value) {
         case ZPX_OPT_SUBSEQ_BYTES: c->opt_subseq = value; return ZPX_OK;
         case ZPX_OPT_PIPELINE_CHUNK: c->opt_pipeline_chunk = value; return ZPX_OK;
         case ZPX_OPT_PIPELINE_RAMP: c->opt_pipeline_ramp = value; return ZPX_OK;
+        case ZPX_OPT_TEST_WIDE: c->opt_test_wide = value; return ZPX_OK;
+        case ZPX_OPT_NATIVE_PLANES:
+            if (value < 0 || value > 2) return ZPX_E_INVALID_ARG;
+            c->opt_native = value;
+            return ZPX_OK;
         case ZPX_OPT_PIPELINE_WORKERS:
             if (value < 1 || value > 8) return ZPX_E_INVALID_ARG;
             c->opt_pipeline_workers = value;
@@ -1017,6 +1063,12 @@ int32_t zpx_batch_open(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* l
     b->dev_of.assign(n, -1);
     b->slot_of.assign(n, -1);
     b->status.assign(n, 0);
+    // per-image device memory budget: half of the smallest device (ZPX_IMAGE_BUDGET_MB overrides, tests)
+    uint64_t image_budget = ~0ull;
+    for (const DeviceCtx& d : ctx->devs)
+        if (d.total_mem) image_budget = std::min<uint64_t>(image_budget, d.total_mem / 2);
+    if (const char* e = getenv("ZPX_IMAGE_BUDGET_MB")) image_budget = (uint64_t)atoll(e) << 20;
+    std::vector<uint64_t> need_of((size_t)n, 0);
     // header parse, parallel over host cores (decodeInner's marker loop; no entropy decode)
     parallel_for((size_t)n, 4, [&](size_t i) {
         if (!b->bufs[i] && b->lens[i]) {
@@ -1024,9 +1076,16 @@ int32_t zpx_batch_open(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* l
             return;
         }
         zpx_parse_jpeg(b->bufs[i], b->lens[i], false, &b->parsed[i]);
-        if (b->parsed[i].status == 0) {
-            int u = unsupported_reason(b->parsed[i]);
-            if (u) b->parsed[i].status = u;
+        // An image whose buffers alone would not fit the device (a few bytes can declare 65535 x 65535) gets the
+        // reference's own answer to a failed allocation (makeImg, decoder.zig:1708-1783: error.OutOfMemory) and
+        // stays out of the plan, instead of failing the upload of the whole batch.
+        ZpxParsed& p = b->parsed[i];
+        if (p.status == 0 && p.mxx > 0 && p.myy > 0) {
+            uint64_t bpm = 0;
+            for (int c = 0; c < p.ncomp; c++) bpm += (uint64_t)p.h[c] * p.v[c];
+            const uint64_t blocks = (uint64_t)p.mxx * p.myy * bpm;
+            need_of[i] = blocks * (128 + 64) + (uint64_t)4 * p.width * p.height;  // coefficients + planes + RGBA
+            if (need_of[i] > image_budget) p.status = ZPX_E_OutOfMemory;
         }
     });
     // schedule: contiguous index ranges balanced by entropy-coded bytes (images are independent,
@@ -1045,6 +1104,20 @@ int32_t zpx_batch_open(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* l
     }
     (void)total;
     zpx_partition(w.data(), n, nd, b->dev_of.data());
+    // the same budget for a device's whole share: images that no longer fit are refused one by one (the caller can
+    // submit them again in a later batch), the others decode
+    std::vector<uint64_t> used((size_t)nd, 0);
+    for (int i = 0; i < n; i++) {
+        const int d = b->dev_of[i];
+        if (d < 0) continue;
+        const uint64_t cap = getenv("ZPX_IMAGE_BUDGET_MB") ? image_budget : (ctx->devs[d].total_mem ? ctx->devs[d].total_mem / 10 * 8 : ~0ull);
+        if (used[(size_t)d] + need_of[i] > cap) {
+            b->status[i] = b->parsed[i].status = ZPX_E_OutOfMemory;
+            b->dev_of[i] = -1;
+            continue;
+        }
+        used[(size_t)d] += need_of[i];
+    }
     for (int i = 0; i < n; i++) {
         const int d = b->dev_of[i];
         if (d < 0) continue;
@@ -1186,7 +1259,7 @@ int32_t zpx_batch_timing(const zpx_batch* b, int32_t di, zpx_timing* out) {
 const void* zpx_batch_device_rgba(const zpx_batch* b, int32_t i) {
     if (!b || i < 0 || i >= b->n || b->dev_of[i] < 0) return nullptr;
     const DevicePlan& pl = b->plans[b->dev_of[i]];
-    if (!pl.decoded) return nullptr;
+    if (!pl.decoded || b->ctx->resident != b) return nullptr;  // (evicted by a later upload: no stale pointers)
     return (const uint8_t*)b->ctx->devs[b->dev_of[i]].out.p + pl.out_off[b->slot_of[i]];
 }
 
@@ -1208,6 +1281,7 @@ int32_t zpx_batch_fetch_rgba(zpx_batch* b, uint8_t* const* out, const size_t* ou
         if (pl.images.empty()) continue;
         DeviceCtx& dc = ctx->devs[di];
         CU(ctx, cudaSetDevice(dc.dev));
+        CU(ctx, after_decode(dc));
         CU(ctx, cudaEventRecord(dc.ev[6], dc.stream));
         size_t k = 0;
         while (k < pl.images.size()) {
@@ -1216,6 +1290,7 @@ int32_t zpx_batch_fetch_rgba(zpx_batch* b, uint8_t* const* out, const size_t* ou
             const size_t row = (size_t)4 * p.width;
             const size_t len = row * p.height;
             if (!out[bi] || b->status[bi] != 0) { k++; continue; }
+            if (pl.native == 2 && pl.imgs[k].fused) return ZPX_E_BAD_STATE;  // decoded with ZPX_OPT_NATIVE_PLANES = 2: no RGBA
             const uint8_t* src = (const uint8_t*)dc.out.p + pl.out_off[k];
             if (out_stride && out_stride[bi] != 0 && out_stride[bi] != row) {
                 CU(ctx, cudaMemcpy2DAsync(out[bi], out_stride[bi], src, row, row, p.height, cudaMemcpyDeviceToHost, dc.stream));
@@ -1255,42 +1330,78 @@ int32_t zpx_batch_fetch_rgba(zpx_batch* b, uint8_t* const* out, const size_t* ou
 int32_t zpx_batch_fetch_native(zpx_batch* b, uint8_t* const* out, int32_t* status) {
     if (!b || (b->n > 0 && !out)) return ZPX_E_INVALID_ARG;
     zpx_ctx* ctx = b->ctx;
+    if (b->n > 0 && ctx->resident != b) {
+        for (const DevicePlan& pl : b->plans)
+            if (!pl.images.empty()) return ZPX_E_BAD_STATE;  // its results were evicted by a later upload on this context
+    }
     int e = finalize_status(b);
     if (e) return e;
-    for (int i = 0; i < b->n; i++) {
-        if (!out[i] || b->status[i] != 0 || b->dev_of[i] < 0) continue;
-        const int di = b->dev_of[i];
+    for (size_t di = 0; di < b->plans.size(); di++) {
         DevicePlan& pl = b->plans[di];
+        if (pl.images.empty()) continue;
         if (!pl.decoded) return ZPX_E_BAD_STATE;
         DeviceCtx& dc = ctx->devs[di];
-        const ZpxImageDev& im = pl.imgs[b->slot_of[i]];
-        const ZpxParsed& p = b->parsed[i];
         CU(ctx, cudaSetDevice(dc.dev));
-        zpx_image_info info;
-        zpx_fill_info(p, &info);
-        if (p.variant == ZPX_VARIANT_RGBA) {
-            CU(ctx, cudaMemcpyAsync(out[i], (const uint8_t*)dc.out.p + im.out_off, info.native_len, cudaMemcpyDeviceToHost, dc.stream));
-        } else if (im.fused) {
-            // planes only exist on the unfused path (ZPX_OPT_FORCE_GENERIC routes every image there)
-            b->status[i] = ZPX_E_UNSUPPORTED_STREAM;
-        } else if (p.variant == ZPX_VARIANT_CMYK) {
-            // Image{.CMYK}: applyBlack's interleave, built from the planes on demand (4-component frames
-            // always take the unfused path)
-            CU(ctx, dc.scratch.ensure(info.native_len));
-            K2GParams kg{};
-            kg.planes = (uint8_t*)dc.planes.p;
-            kg.imgs = (const ZpxImageDev*)((const uint8_t*)dc.desc.p + pl.off_imgs);
-            CU(ctx, k2g_launch_cmyk_native(kg, (uint32_t)b->slot_of[i], (size_t)p.width * p.height, (uint8_t*)dc.scratch.p, dc.stream));
-            ctx->launches++;
-            CU(ctx, cudaMemcpyAsync(out[i], dc.scratch.p, info.native_len, cudaMemcpyDeviceToHost, dc.stream));
-            CU(ctx, cudaStreamSynchronize(dc.stream));  // scratch is reused by the next image
-        } else {
-            CU(ctx, cudaMemcpyAsync(out[i], (const uint8_t*)dc.planes.p + im.plane_off[0], info.native_len, cudaMemcpyDeviceToHost, dc.stream));
+        CU(ctx, after_decode(dc));
+        CU(ctx, cudaEventRecord(dc.ev[6], dc.stream));
+        size_t k = 0;
+        while (k < pl.images.size()) {
+            const int i = pl.images[k];
+            const ZpxImageDev& im = pl.imgs[k];
+            const ZpxParsed& p = b->parsed[i];
+            if (!out[i] || b->status[i] != 0) { k++; continue; }
+            zpx_image_info info;
+            zpx_fill_info(p, &info);
+            if (p.variant == ZPX_VARIANT_RGBA) {
+                CU(ctx, cudaMemcpyAsync(out[i], (const uint8_t*)dc.out.p + im.out_off, info.native_len, cudaMemcpyDeviceToHost, dc.stream));
+                k++;
+            } else if (im.fused && pl.native == 0) {
+                // the fused kernel keeps its planes in shared memory unless ZPX_OPT_NATIVE_PLANES asked for them
+                b->status[i] = ZPX_E_UNSUPPORTED_STREAM;
+                k++;
+            } else if (p.variant == ZPX_VARIANT_CMYK) {
+                // Image{.CMYK}: applyBlack's interleave, built from the planes on demand (4-component frames
+                // always take the unfused path)
+                CU(ctx, dc.scratch.ensure(info.native_len));
+                K2GParams kg{};
+                kg.planes = (uint8_t*)dc.planes.p;
+                kg.imgs = (const ZpxImageDev*)((const uint8_t*)dc.desc.p + pl.off_imgs);
+                CU(ctx, k2g_launch_cmyk_native(kg, (uint32_t)k, (size_t)p.width * p.height, (uint8_t*)dc.scratch.p, dc.stream));
+                ctx->launches++;
+                CU(ctx, cudaMemcpyAsync(out[i], dc.scratch.p, info.native_len, cudaMemcpyDeviceToHost, dc.stream));
+                CU(ctx, cudaStreamSynchronize(dc.stream));  // scratch is reused by the next image
+                k++;
+            } else {
+                // Gray / YCbCr planes: merge runs that are contiguous on both sides into one copy
+                size_t run = info.native_len, k2 = k + 1;
+                while (k2 < pl.images.size()) {
+                    const int j = pl.images[k2];
+                    const ZpxParsed& pj = b->parsed[j];
+                    const ZpxImageDev& imj = pl.imgs[k2];
+                    if (!out[j] || b->status[j] != 0) break;
+                    if (pj.variant != ZPX_VARIANT_GRAY && pj.variant != ZPX_VARIANT_YCBCR) break;
+                    if (imj.fused && pl.native == 0) break;
+                    if (imj.plane_off[0] != im.plane_off[0] + run || out[j] != out[i] + run) break;
+                    zpx_image_info ij;
+                    zpx_fill_info(pj, &ij);
+                    run += ij.native_len;
+                    k2++;
+                }
+                CU(ctx, cudaMemcpyAsync(out[i], (const uint8_t*)dc.planes.p + im.plane_off[0], run, cudaMemcpyDeviceToHost, dc.stream));
+                k = k2;
+            }
         }
+        CU(ctx, cudaEventRecord(dc.ev[7], dc.stream));
     }
-    for (DeviceCtx& dc : ctx->devs) {
+    for (size_t di = 0; di < b->plans.size(); di++) {
+        DevicePlan& pl = b->plans[di];
+        if (pl.images.empty()) continue;
+        DeviceCtx& dc = ctx->devs[di];
         CU(ctx, cudaSetDevice(dc.dev));
         CU(ctx, cudaStreamSynchronize(dc.stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, dc.ev[6], dc.ev[7]);
+        pl.timing.d2h_ms = ms;
     }
     if (status) memcpy(status, b->status.data(), sizeof(int32_t) * b->n);
     return ZPX_OK;
@@ -1301,7 +1412,7 @@ int32_t zpx_batch_fetch_coefficients(zpx_batch* b, int32_t i, int16_t* out, size
     zpx_ctx* ctx = b->ctx;
     const int di = b->dev_of[i];
     DevicePlan& pl = b->plans[di];
-    if (!pl.decoded) return ZPX_E_BAD_STATE;
+    if (!pl.decoded || ctx->resident != b) return ZPX_E_BAD_STATE;
     DeviceCtx& dc = ctx->devs[di];
     const ZpxImageDev& im = pl.imgs[b->slot_of[i]];
     const ZpxParsed& p = b->parsed[i];
@@ -1310,6 +1421,7 @@ int32_t zpx_batch_fetch_coefficients(zpx_batch* b, int32_t i, int16_t* out, size
     if (!out) return ZPX_OK;
     if (cap_blocks < nb) return ZPX_E_INVALID_ARG;
     CU(ctx, cudaSetDevice(dc.dev));
+    CU(ctx, after_decode(dc));
     CU(ctx, cudaStreamSynchronize(dc.stream));
     CU(ctx, cudaMemcpy(out, (const uint8_t*)dc.coef.p + im.coef_base * 128, nb * 128, cudaMemcpyDeviceToHost));
     // undo the row swizzle: block with component-x index bx stores row r at slot r ^ (bx & 7)
@@ -1341,6 +1453,132 @@ int32_t zpx_batch_fetch_coefficients(zpx_batch* b, int32_t i, int16_t* out, size
     return ZPX_OK;
 }
 
+// ---- test hooks: the reconstruction kernels without the entropy stage ----
+int32_t zpx_batch_open_synthetic(zpx_ctx* ctx, int32_t width, int32_t height, int32_t ncomp, const uint8_t* comp_hv,
+                                 const uint16_t* quant, int32_t mode, zpx_batch** out) {
+    if (!ctx || !out || !comp_hv || !quant || width <= 0 || height <= 0 || width > 65535 || height > 65535) return ZPX_E_INVALID_ARG;
+    if (ncomp != 1 && ncomp != 3 && ncomp != 4) return ZPX_E_INVALID_ARG;
+    if (mode < ZPX_MODE_GRAY || mode > ZPX_MODE_YCCK || (ncomp == 1) != (mode == ZPX_MODE_GRAY) || (ncomp == 4) != (mode >= ZPX_MODE_CMYK))
+        return ZPX_E_INVALID_ARG;
+    *out = nullptr;
+    zpx_batch* b = new (std::nothrow) zpx_batch();
+    if (!b) return ZPX_E_OutOfMemory;
+    b->ctx = ctx;
+    b->n = 1;
+    b->bufs.assign(1, nullptr);
+    b->lens.assign(1, 0);
+    b->parsed.resize(1);
+    b->dev_of.assign(1, 0);
+    b->slot_of.assign(1, 0);
+    b->status.assign(1, 0);
+    ZpxParsed& p = b->parsed[0];
+    p.width = width;
+    p.height = height;
+    p.ncomp = ncomp;
+    p.baseline = true;
+    int total_hv = 0;
+    for (int c = 0; c < ncomp; c++) {
+        p.h[c] = ncomp == 1 ? 1 : comp_hv[c] >> 4;   // gray forces h = v = 1 (decoder.zig:559-560)
+        p.v[c] = ncomp == 1 ? 1 : comp_hv[c] & 15;
+        p.tq[c] = c;
+        p.cid[c] = (uint8_t)(c + 1);
+        total_hv += p.h[c] * p.v[c];
+        const bool ok = (p.h[c] == 1 || p.h[c] == 2 || p.h[c] == 4) && (p.v[c] == 1 || p.v[c] == 2 || p.v[c] == 4);
+        if (!ok || (c > 0 && (p.h[0] % p.h[c] || p.v[0] % p.v[c]))) {
+            delete b;
+            return ZPX_E_INVALID_ARG;
+        }
+    }
+    if (ncomp > 1 && total_hv > 10) {
+        delete b;
+        return ZPX_E_INVALID_ARG;
+    }
+    p.jfif = mode == ZPX_MODE_YCBCR;
+    p.adobe_valid = mode == ZPX_MODE_RGB || mode >= ZPX_MODE_CMYK;
+    p.adobe_transform = mode == ZPX_MODE_YCCK ? 2 : 0;
+    p.mxx = (width + 8 * p.h[0] - 1) / (8 * p.h[0]);
+    p.myy = (height + 8 * p.v[0] - 1) / (8 * p.v[0]);
+    p.saw_sos = true;
+    ZpxScanHost sc;
+    sc.ncomp = ncomp;
+    for (int c = 0; c < ncomp; c++) {
+        sc.comp[c] = c;
+        for (int z = 0; z < 64; z++) {
+            sc.quant[c][z] = quant[c * 64 + z];
+            p.final_quant[c][z] = quant[c * 64 + z];
+        }
+    }
+    p.scans.push_back(sc);  // no intervals: the entropy stage has nothing to do
+    zpx_derive(&p);
+    b->plans.resize(ctx->devs.size());
+    b->plans[0].images.push_back(0);
+    for (size_t d = 0; d < ctx->devs.size(); d++) build_plan(b, (int)d);
+    *out = b;
+    return ZPX_OK;
+}
+
+int32_t zpx_batch_set_coefficients(zpx_batch* b, int32_t i, const int16_t* blocks, size_t n_blocks) {
+    if (!b || !blocks || i < 0 || i >= b->n || b->dev_of[i] < 0) return ZPX_E_INVALID_ARG;
+    zpx_ctx* ctx = b->ctx;
+    const int di = b->dev_of[i];
+    DevicePlan& pl = b->plans[di];
+    if (!pl.uploaded || ctx->resident != b) return ZPX_E_BAD_STATE;
+    DeviceCtx& dc = ctx->devs[di];
+    const ZpxImageDev& im = pl.imgs[b->slot_of[i]];
+    const ZpxParsed& p = b->parsed[i];
+    const size_t nb = (size_t)p.mxx * p.myy * im.bpm;
+    if (n_blocks != nb) return ZPX_E_INVALID_ARG;
+    std::vector<int16_t> sw(nb * 64);
+    bool wide = ctx->opt_test_wide != 0;
+    for (size_t k = 0; k < nb; k++) {
+        int bx;
+        if (im.layout == ZPX_LAYOUT_INTERLEAVED) {
+            const size_t mcu = k / im.bpm;
+            const int slot = (int)(k % im.bpm);
+            int c = 0;
+            for (int cc = 0; cc < im.ncomp; cc++)
+                if ((int)im.blk_off[cc] <= slot) c = cc;
+            bx = im.h[c] * (int)(mcu % p.mxx) + (slot - (int)im.blk_off[c]) % im.h[c];
+        } else {
+            size_t kk = k;
+            int c = 0;
+            for (; c < im.ncomp; c++) {
+                const size_t cnt = (size_t)im.comp_bw[c] * im.comp_bh[c];
+                if (kk < cnt) break;
+                kk -= cnt;
+            }
+            bx = (int)(kk % im.comp_bw[c]);
+        }
+        const int16_t* src = blocks + k * 64;
+        for (int r = 0; r < 8; r++) memcpy(&sw[k * 64 + (size_t)((r ^ (bx & 7)) * 8)], src + r * 8, 16);
+        for (int z = 0; z < 64; z++) wide = wide || src[z] < -4096 || src[z] > 4095;
+    }
+    CU(ctx, cudaSetDevice(dc.dev));
+    CU(ctx, cudaStreamSynchronize(dc.stream));
+    CU(ctx, cudaMemcpy((uint8_t*)dc.coef.p + im.coef_base * 128, sw.data(), nb * 128, cudaMemcpyHostToDevice));
+    if (pl.inject_flags.size() != pl.imgs.size()) pl.inject_flags.assign(pl.imgs.size(), 0);
+    pl.inject_flags[b->slot_of[i]] = wide ? 1u : 0u;
+    return ZPX_OK;
+}
+
+int32_t zpx_test_colour(zpx_ctx* ctx, int32_t mode, const uint8_t* samples, size_t n, uint8_t* rgba) {
+    if (!ctx || !samples || !rgba || (mode != ZPX_MODE_YCBCR && mode != ZPX_MODE_CMYK && mode != ZPX_MODE_YCCK)) return ZPX_E_INVALID_ARG;
+    if (n == 0) return ZPX_OK;
+    DeviceCtx& dc = ctx->devs[0];
+    const size_t in_bytes = n * (mode == ZPX_MODE_YCBCR ? 3 : 4);
+    CU(ctx, cudaSetDevice(dc.dev));
+    CU(ctx, cudaStreamSynchronize(dc.stream));
+    CU(ctx, dc.scratch.ensure(align_up(in_bytes, 256) + n * 4));
+    uint8_t* din = (uint8_t*)dc.scratch.p;
+    uint8_t* dout = din + align_up(in_bytes, 256);
+    CU(ctx, cudaMemcpyAsync(din, samples, in_bytes, cudaMemcpyHostToDevice, dc.stream));
+    CU(ctx, k2_launch_test_colour(mode, din, n, dout, dc.stream));
+    ctx->launches++;
+    CU(ctx, cudaMemcpyAsync(rgba, dout, n * 4, cudaMemcpyDeviceToHost, dc.stream));
+    CU(ctx, cudaStreamSynchronize(dc.stream));
+    return ZPX_OK;
+}
+
 void zpx_batch_close(zpx_batch* b) {
     if (!b) return;
     if (b->ctx->resident == b) b->ctx->resident = nullptr;
@@ -1352,13 +1590,13 @@ void zpx_batch_close(zpx_batch* b) {
 }
 
 static int32_t decode_range_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* lens, int32_t n,
-                                 uint8_t* const* out, const size_t* out_stride, int32_t* status) {
+                                 uint8_t* const* out, const size_t* out_stride, int32_t* status, bool native) {
     zpx_batch* b = nullptr;
     int e = zpx_batch_open(ctx, bufs, lens, n, &b);
     if (e) return e;
     e = zpx_batch_upload(b);
     if (!e) e = zpx_batch_decode(b, nullptr);
-    if (!e) e = zpx_batch_fetch_rgba(b, out, out_stride, status);
+    if (!e) e = native ? zpx_batch_fetch_native(b, out, status) : zpx_batch_fetch_rgba(b, out, out_stride, status);
     zpx_batch_close(b);
     return e;
 }
@@ -1367,8 +1605,8 @@ static int32_t decode_range_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const
 // (context + shadow contexts, one host thread each): while one chunk's RGBA travels back over PCIe,
 // the next chunk is parsed, uploaded and decoded.  Images are independent, so chunking changes
 // nothing in the results.
-int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* lens, int32_t n,
-                              uint8_t* const* out, const size_t* out_stride, int32_t* status) {
+static int32_t decode_batch_pipelined(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* lens, int32_t n,
+                                      uint8_t* const* out, const size_t* out_stride, int32_t* status, bool native) {
     if (!ctx || n < 0 || (n > 0 && (!bufs || !lens || !out))) return ZPX_E_INVALID_ARG;
     int32_t chunk = (int32_t)ctx->opt_pipeline_chunk;
     if (chunk == 0) {
@@ -1380,7 +1618,7 @@ int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const si
         const uint64_t avg = std::max<uint64_t>(1, total / (uint64_t)std::max(n, 1));
         chunk = (int32_t)std::min<uint64_t>(2048, std::max<uint64_t>(16, (28u << 20) / avg));
     }
-    if (ctx->opt_pipeline_chunk < 0 || n < 2 * chunk) return decode_range_rgba(ctx, bufs, lens, n, out, out_stride, status);
+    if (ctx->opt_pipeline_chunk < 0 || n < 2 * chunk) return decode_range_rgba(ctx, bufs, lens, n, out, out_stride, status, native);
     const int n_workers = (int)std::min<int64_t>(ctx->opt_pipeline_workers, (n + chunk - 1) / chunk);
     while ((int)ctx->shadows.size() < n_workers - 1) {
         std::vector<int32_t> ids;
@@ -1394,6 +1632,7 @@ int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const si
         sh->opt_entropy_mode = ctx->opt_entropy_mode;
         sh->opt_force_generic = ctx->opt_force_generic;
         sh->opt_subseq = ctx->opt_subseq;
+        sh->opt_native = ctx->opt_native;
     }
     // chunk list: the first two chunks are a quarter and a half of the regular size, so that the first
     // device->host copy starts early (the pipeline is bound by that copy; its fill time is pure loss)
@@ -1419,8 +1658,10 @@ int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const si
             const int32_t k = next.fetch_add(1);
             if (k >= n_chunks) break;
             const int32_t i0 = chunks[k].first, cnt = chunks[k].second;
-            const int e = decode_range_rgba(c, bufs + i0, lens + i0, cnt, out + i0, out_stride ? out_stride + i0 : nullptr, stp + i0);
+            const int e = decode_range_rgba(c, bufs + i0, lens + i0, cnt, out + i0, out_stride ? out_stride + i0 : nullptr, stp + i0, native);
             if (e) {
+                // the chunk's images did not get a result: say so per image, then stop this worker
+                for (int32_t i = i0; i < i0 + cnt; i++) stp[i] = e;
                 rc[(size_t)w] = e;
                 break;
             }
@@ -1442,6 +1683,24 @@ int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const si
         }
     }
     return ret;
+}
+
+int32_t zpx_decode_batch_rgba(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* lens, int32_t n,
+                              uint8_t* const* out, const size_t* out_stride, int32_t* status) {
+    return decode_batch_pipelined(ctx, bufs, lens, n, out, out_stride, status, false);
+}
+
+// The same pipeline with jpeg.load's own return value as the result: the native Image variant's .pixels buffer
+// (planar, MCU-padded Y/Cb/Cr or Gray: 1.5 bytes per pixel for 4:2:0 instead of RGBA's 4).  The fused kernel writes
+// planes only for the duration of the call.
+int32_t zpx_decode_batch_native(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* lens, int32_t n,
+                                uint8_t* const* out, int32_t* status) {
+    if (!ctx) return ZPX_E_INVALID_ARG;
+    const int64_t saved = ctx->opt_native;
+    ctx->opt_native = 2;
+    const int32_t e = decode_batch_pipelined(ctx, bufs, lens, n, out, nullptr, status, true);
+    ctx->opt_native = saved;
+    return e;
 }
 
 }  // extern "C"

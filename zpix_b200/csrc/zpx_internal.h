@@ -142,7 +142,7 @@ struct ZpxIntervalDev {
     uint64_t ustart;
 };
 
-// One unit of work of k0_unstuff: a run of raw bytes of one interval that does not split an FF 00 pair
+// One unit of work of k0_unstuff: a run of raw bytes (about ZPX_SEG_BYTES) of one interval that does not split an FF 00 pair
 struct ZpxSegDev {
     uint64_t src;    // byte offset in the raw blob
     uint64_t dst;    // byte offset in the unstuffed blob
@@ -189,7 +189,7 @@ struct ZpxIntervalHost {
 };
 
 // a piece of an interval for the unstuffing kernel: [src, src + len) of the file holds whole FF 00 pairs only
-#define ZPX_SEG_BYTES 4096
+#define ZPX_SEG_BYTES 16384
 struct ZpxSegHost {
     size_t src;      // offset in the source file
     uint32_t len;    // raw bytes
@@ -239,5 +239,7 @@ void zpx_parse_jpeg(const uint8_t* data, size_t len, bool config_only, ZpxParsed
 void zpx_build_huff_dev(const ZpxHuffHost& h, bool is_ac, ZpxHuffDev* out, int* malformed);
 uint32_t zpx_fast_entry(bool is_ac, int len, int sym);
 void zpx_fill_info(const ZpxParsed& p, zpx_image_info* info);
+// colour exit / Image variant / sub-sampling ratio from the frame header fields (decoder.zig:361-370, 699-709)
+void zpx_derive(ZpxParsed* o);
 
 extern const uint8_t zpx_unzig[64];

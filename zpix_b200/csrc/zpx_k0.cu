@@ -7,12 +7,13 @@
 // position bookkeeping out of every Huffman symbol step of K1 (zpx_k1_common.cuh RingReader) and makes bit
 // positions of the unstuffed stream canonical for the self-synchronising decoder.
 //
-// Work unit: one warp per piece (ZpxSegDev: about 4 KB of raw bytes of one interval, cut by the host where no
+// Work unit: one warp per piece (ZpxSegDev: about 16 KB of raw bytes of one interval, cut by the host where no
 // FF 00 pair is split; the host also knows how many pairs precede the piece, i.e. where its output starts).
-// A round moves 512 raw bytes: coalesced 16-byte loads into shared memory, then 16 steps in which lane l looks
-// at byte 32 k + l (conflict-free), a ballot + popc gives its output position, and the kept bytes go to a 1 KB
-// output ring from which complete 16-byte vectors are stored to HBM; head and tail bytes that share a vector
-// with the neighbouring piece are stored one by one.  HBM-bound: reads and writes every entropy-coded byte once.
+// A round moves 512 raw bytes: coalesced 16-byte loads into shared memory, then 4 steps in which lane l looks
+// at word 32 k + l (conflict-free; stuffed bytes found with byte-parallel arithmetic), ballots + popc give its
+// output position, and the kept bytes go to a 1 KB output ring from which complete 16-byte vectors are stored to
+// HBM; head and tail bytes that share a vector with the neighbouring piece are stored one by one.  Reads and
+// writes every entropy-coded byte once.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -38,7 +39,6 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_unstuff(const uint8_t* __res
     uint8_t* gbase = ublob + (sg.dst - m);   // 16-byte aligned; ring position p <-> gbase + p
     uint32_t wpos = m, flushed = 0;          // bytes produced / bytes stored (flushed is a multiple of 16)
     int rel0 = -(int)(sg.src - a0);          // (offset of the round's first byte) - src
-    uint32_t prev_last = 0;                  // last raw byte of the previous round
     const uint32_t lt = (1u << lane) - 1u;
 
     auto flush_full = [&]() {
@@ -58,26 +58,64 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_unstuff(const uint8_t* __res
         flushed += nvec << 4;
     };
 
+    uint32_t prev_lastw = 0;  // last raw word of the previous round
     for (uint64_t base = a0; base < sg.src + sg.len; base += 512, rel0 += 512) {
         const uint64_t my = base + 16u * (uint32_t)lane;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (my < sg.src + sg.len) v = __ldg(reinterpret_cast<const uint4*>(blob + my));
         reinterpret_cast<uint4*>(in)[lane] = v;
         __syncwarp();
-#pragma unroll 4
-        for (int k = 0; k < 16; k++) {
-            const int b = 32 * k + lane;
-            const int rel = rel0 + b;  // position inside the piece
-            const uint32_t x = in[b];
-            const uint32_t px = b > 0 ? in[b - 1] : prev_last;
-            const bool valid = rel >= 0 && rel < (int)sg.len;
-            const bool drop = x == 0u && rel >= 1 && px == 0xffu;  // the 0x00 of an FF 00 pair
-            const bool keep = valid && !drop;
-            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
-            if (keep) out[(wpos + __popc(mask & lt)) & 1023u] = (uint8_t)x;
-            wpos += __popc(mask);
+        // a round whose 512 bytes all belong to the piece, the first one not being the piece's first byte
+        const bool interior = rel0 >= 1 && rel0 + 512 <= (int)sg.len;
+        // four steps of 128 bytes; lane l looks at word 32 k + l (conflict-free) and the word before it
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int w = 32 * k + lane;
+            const uint32_t x = reinterpret_cast<const uint32_t*>(in)[w];
+            const uint32_t pw = (k > 0 || lane > 0) ? reinterpret_cast<const uint32_t*>(in)[w > 0 ? w - 1 : 0] : prev_lastw;
+            const uint32_t ny = ~__funnelshift_l(pw, x, 8);  // byte i = ~(the byte before byte i of x)
+            // 0x80 in every byte of x that is 0x00 and whose predecessor is 0xFF: the 0x00 of an FF 00 pair
+            // (exact per byte: no carries between bytes)
+            const uint32_t drop = ~((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) | (((ny & 0x7f7f7f7fu) + 0x7f7f7f7fu) | ny) | 0x7f7f7f7fu);
+            if (interior && !__any_sync(0xffffffffu, drop != 0)) {
+                // nothing to remove in these 128 bytes (three steps out of four)
+                const uint32_t o = wpos + 4u * (uint32_t)lane;
+                out[o & 1023u] = (uint8_t)x;
+                out[(o + 1) & 1023u] = (uint8_t)(x >> 8);
+                out[(o + 2) & 1023u] = (uint8_t)(x >> 16);
+                out[(o + 3) & 1023u] = (uint8_t)(x >> 24);
+                wpos += 128u;
+            } else if (interior) {
+                // some words of these 128 bytes lose one or two bytes
+                const int ngone = __popc(drop);
+                const uint32_t b1 = __ballot_sync(0xffffffffu, ngone >= 1), b2 = __ballot_sync(0xffffffffu, ngone >= 2);
+                uint32_t o = wpos + 4u * (uint32_t)lane - (uint32_t)(__popc(b1 & lt) + __popc(b2 & lt));
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (!(drop & (0x80u << (8 * i)))) out[(o++) & 1023u] = (uint8_t)(x >> (8 * i));
+                wpos += 128u - (uint32_t)(__popc(b1) + __popc(b2));
+            } else {
+                // first / last round of the piece: bytes outside [0, len) are not kept either; the piece's first
+                // byte is never a stuffed 0x00 (its predecessor is not part of the piece)
+                const int rel = rel0 + 4 * w;
+                uint32_t gone = drop;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (rel + i == 0) gone &= ~(0x80u << (8 * i));
+                    if (rel + i < 0 || rel + i >= (int)sg.len) gone |= 0x80u << (8 * i);
+                }
+                const int ngone = __popc(gone);
+                // kept bytes before this lane's word = 4 * lane - bytes gone in the lanes below
+                const uint32_t b1 = __ballot_sync(0xffffffffu, ngone >= 1), b2 = __ballot_sync(0xffffffffu, ngone >= 2);
+                const uint32_t b3 = __ballot_sync(0xffffffffu, ngone >= 3), b4 = __ballot_sync(0xffffffffu, ngone >= 4);
+                uint32_t o = wpos + 4u * (uint32_t)lane - (uint32_t)(__popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt) + __popc(b4 & lt));
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (!(gone & (0x80u << (8 * i)))) out[(o++) & 1023u] = (uint8_t)(x >> (8 * i));
+                wpos += 128u - (uint32_t)(__popc(b1) + __popc(b2) + __popc(b3) + __popc(b4));
+            }
         }
-        prev_last = in[511];
+        prev_lastw = reinterpret_cast<const uint32_t*>(in)[127];
         __syncwarp();
         flush_full();
         __syncwarp();

@@ -61,9 +61,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // fused kernel
 // ---------------------------------------------------------------------------
 // Shared memory (dynamic):
-//   [0,16)     two mbarriers
-//   [16,32)    reserved
-//   QS         3 x 32 words: 8-bit quantisers packed q[2j] | q[2j+1] << 24 (dp2a operands)
+//   [0,32)     the stages' mbarriers
 //   PL         Y plane 8V rows x PY bytes, then Cb, Cr: 8 rows x PC bytes each
 //   ST0..      NS coefficient stages, tmax * BPM * 128 bytes each (ring fed by bulk copies)
 template <int H, int V, int NC>
@@ -74,7 +72,7 @@ struct K2Cfg {
     __host__ __device__ static int pitch_y(int tmax) { return tmax * MCU_W + 16; }
     __host__ __device__ static int pitch_c(int tmax) { return tmax * 8 + 16; }
     __host__ __device__ static size_t smem_bytes(int tmax, int ns) {
-        size_t s = 32 + 3 * 64 * 4;
+        size_t s = 32;
         s += (size_t)YROWS * pitch_y(tmax);
         if (NC == 1) s += 2048;  // gray tiles may span up to 16 MCU rows, each with 16 bytes of row padding
         if (NC == 3) s += (size_t)2 * 8 * pitch_c(tmax);
@@ -90,13 +88,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
     constexpr int BPM = Cfg::BPM;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-    uint32_t* qs = reinterpret_cast<uint32_t*>(smem + 32);
     const int PY0 = Cfg::pitch_y(P.tmax), PC = Cfg::pitch_c(P.tmax);
     const int PY = PY0;  // layout constant; gray tiles use a per-tile pitch inside the same area
-    uint8_t* planeY = smem + 32 + 3 * 64 * 4;
+    uint8_t* planeY = smem + 32;
     uint8_t* planeCb = planeY + Cfg::YROWS * PY;
     uint8_t* planeCr = planeCb + 8 * PC;
-    size_t st_off = 32 + 3 * 64 * 4 + (size_t)Cfg::YROWS * PY + (NC == 3 ? (size_t)2 * 8 * PC : 2048);
+    size_t st_off = 32 + (size_t)Cfg::YROWS * PY + (NC == 3 ? (size_t)2 * 8 * PC : 2048);
     st_off = (st_off + 127) & ~(size_t)127;
     uint8_t* stage0 = smem + st_off;
     const uint32_t stage_bytes = (uint32_t)P.tmax * BPM * 128;
@@ -121,10 +118,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
         uint64_t out_off;
         uint32_t nr, wt;  // gray: the tile is nr whole MCU rows of wt MCUs (n = nr * wt); else nr = 1, wt = n
         uint32_t wide;    // the image has coefficients outside [-4096, 4095]: exact all-AC-zero rows (zpx_idct.cuh)
+        // native planes (makeImg's layout, decoder.zig:1708-1783), when the launch writes them
+        uint64_t poff[3];
+        int32_t ystride, cstride;
     };
     __shared__ TileCtx ctx[NS];
     __shared__ __align__(16) uint32_t qsm[NS][3 * 32];  // per row four words q[2j] | q[2j+1] << 24 (dp2a operands)
-    (void)qs;
 
     // issue the bulk copy of one tile into a stage and publish its context (thread 0);
     // threads < 32*NC stage the image's quantisers when the image changes
@@ -147,6 +146,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
             c.nr = tn.pad & 0xffu ? tn.pad & 0xffu : 1u;
             c.wt = tn.pad >> 16 ? tn.pad >> 16 : tn.n;
             c.wide = P.img_flags[imn->status_slot] & 1u;
+            c.poff[0] = imn->plane_off[0];
+            c.poff[1] = imn->plane_off[1];
+            c.poff[2] = imn->plane_off[2];
+            c.ystride = imn->plane_stride[0];
+            c.cstride = imn->plane_stride[1];
             ctx[stg] = c;
         }
         if (tid < 32 * NC) {
@@ -251,10 +255,34 @@ __global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
         }
         __syncthreads();
 
+        // ---------------- native planes (jpeg.load's Image{.YCbCr} / {.Gray}) ----------------
+        // The tile's 8x8 outputs already sit in shared memory as planes: copy them out with makeImg's strides,
+        // MCU padding included (reconstructBlock stores every decoded block, decoder.zig:1611-1633).
+        if (P.planes != nullptr) {
+            const int wt = (NC == 1) ? (int)t.wt : n;
+            const int PYt = (NC == 1) ? wt * 8 + 16 : PY;
+            const int rowsY = (NC == 1) ? (int)t.nr * 8 : Cfg::YROWS;
+            const int v8 = wt * (Cfg::MCU_W / 8);  // 8-byte units per luma row of the tile
+            uint8_t* dY = P.planes + t.poff[0] + (size_t)((int)t.my * Cfg::YROWS) * t.ystride + (size_t)t.mx0 * Cfg::MCU_W;
+            for (int i = tid; i < rowsY * v8; i += NT) {
+                const int r = i / v8, c8 = i - r * v8;
+                *reinterpret_cast<uint2*>(dY + (size_t)r * t.ystride + c8 * 8) = *reinterpret_cast<const uint2*>(planeY + r * PYt + c8 * 8);
+            }
+            if (NC == 3) {
+                uint8_t* dB = P.planes + t.poff[1] + (size_t)((int)t.my * 8) * t.cstride + (size_t)t.mx0 * 8;
+                uint8_t* dR = P.planes + t.poff[2] + (size_t)((int)t.my * 8) * t.cstride + (size_t)t.mx0 * 8;
+                for (int i = tid; i < 8 * n; i += NT) {
+                    const int r = i / n, c8 = i - r * n;
+                    *reinterpret_cast<uint2*>(dB + (size_t)r * t.cstride + c8 * 8) = *reinterpret_cast<const uint2*>(planeCb + r * PC + c8 * 8);
+                    *reinterpret_cast<uint2*>(dR + (size_t)r * t.cstride + c8 * 8) = *reinterpret_cast<const uint2*>(planeCr + r * PC + c8 * 8);
+                }
+            }
+        }
+
         // ---------------- phase 2: colour + coalesced RGBA stores ----------------
         // One item = RP luma rows x PXW pixels.  V = 2: both rows of a chroma row, 4 px wide, so the
         // per-chroma-sample terms are computed once per 2x2 (4:2:0) replication; V = 1: 8 px wide.
-        {
+        if (P.out != nullptr) {
             constexpr int RP = V;                    // luma rows per item
             constexpr int PXW = (V == 2) ? 4 : 8;    // pixels per item row
             constexpr int NCS = (PXW / H) > 0 ? (PXW / H) : 1;  // chroma samples per item row
@@ -508,6 +536,30 @@ __global__ void __launch_bounds__(256) k2g_cmyk_native(const K2GParams P, const 
 cudaError_t k2g_launch_cmyk_native(const K2GParams& P, uint32_t img, size_t pixels, uint8_t* dst, cudaStream_t s) {
     if (pixels == 0) return cudaSuccess;
     k2g_cmyk_native<<<(unsigned)((pixels + 255) / 256), 256, 0, s>>>(P, img, dst);
+    return cudaGetLastError();
+}
+
+// test hook: the device functions the colour phases above are made of (chroma_terms + ycc_pixel, cmyk_pixel) on
+// free-standing samples.  YCbCrK: {Y, Cb, Cr, K plane byte} -> RGB of the YCbCr part, K = 255 - plane, then the .cmyk formula
+__global__ void __launch_bounds__(256) k2_test_colour(const int mode, const uint8_t* __restrict__ in, const size_t n, uint32_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t px;
+    if (mode == ZPX_MODE_CMYK) {
+        px = cmyk_pixel(in[4 * i], in[4 * i + 1], in[4 * i + 2], in[4 * i + 3]);
+    } else {
+        const size_t st = mode == ZPX_MODE_YCBCR ? 3 : 4;
+        int rr, gg, bb;
+        chroma_terms(in[st * i + 1], in[st * i + 2], rr, gg, bb);
+        px = ycc_pixel(in[st * i], rr, gg, bb);
+        if (mode == ZPX_MODE_YCCK) px = cmyk_pixel(px & 0xff, (px >> 8) & 0xff, (px >> 16) & 0xff, 255u - in[4 * i + 3]);
+    }
+    out[i] = px;
+}
+
+cudaError_t k2_launch_test_colour(int mode, const uint8_t* samples, size_t n, uint8_t* rgba, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    k2_test_colour<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mode, samples, n, reinterpret_cast<uint32_t*>(rgba));
     return cudaGetLastError();
 }
 

@@ -59,7 +59,8 @@ static inline int k2_fused_threads(int h, int v, int nc) { return (nc == 3 && h 
 
 struct K2Params {
     const int16_t* coef;
-    uint8_t* out;
+    uint8_t* out;     // RGBA (Image.rgbaPixels layout), or NULL: planes only
+    uint8_t* planes;  // native planes with makeImg's strides (ZpxImageDev::plane_off / plane_stride), or NULL
     const ZpxImageDev* imgs;
     const ZpxTileDev* tiles;
     const ZpxQuantDev* quant;
@@ -82,5 +83,8 @@ struct K2GParams {
 cudaError_t k2g_launch(const K2GParams& P, int n_list, int max_blocks, size_t max_pixels, cudaStream_t s);
 // Image{.CMYK} pixels (applyBlack's result) of one 4-component image into dst (4*W*H bytes, device)
 cudaError_t k2g_launch_cmyk_native(const K2GParams& P, uint32_t img, size_t pixels, uint8_t* dst, cudaStream_t s);
+
+// test hook: the colour functions of the kernels above on n free-standing samples ({Y,Cb,Cr} / {C,M,Y,K} / {Y,Cb,Cr,K})
+cudaError_t k2_launch_test_colour(int mode, const uint8_t* samples, size_t n, uint8_t* rgba, cudaStream_t s);
 
 }  // namespace zpx

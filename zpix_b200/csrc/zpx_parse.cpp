@@ -466,7 +466,7 @@ struct Parser {
 
 }  // namespace
 
-static void derive(ZpxParsed* o) {
+void zpx_derive(ZpxParsed* o) {
     // decoder.zig:361-370 / 699-709 / 792-811 / 1743-1753
     if (o->ncomp == 1) {
         o->mode = ZPX_MODE_GRAY;
@@ -506,7 +506,7 @@ void zpx_parse_jpeg(const uint8_t* data, size_t len, bool config_only, ZpxParsed
     p.out = out;
     bool ok = p.run(config_only);
     memcpy(out->final_quant, p.quant, sizeof(p.quant));
-    if (out->ncomp >= 1) derive(out);
+    if (out->ncomp >= 1) zpx_derive(out);
     if (config_only) {
         // decodeConfig (decoder.zig:178-218)
         if (!ok && p.err != ZPX_E_ConfigOnly) out->status = p.err;
@@ -598,15 +598,22 @@ void zpx_fill_info(const ZpxParsed& p, zpx_image_info* info) {
     info->subsample_ratio = p.ratio;
     info->progressive = p.progressive ? 1 : 0;
     info->restart_interval = p.scans.empty() ? 0 : p.scans[0].restart_interval;
-    info->mxx = p.mxx;
-    info->myy = p.myy;
+    // the MCU grid is fixed by the frame header (decoder.zig:1258-1263 computes it at each SOS): a header-only
+    // probe (zpx_probe stops before the first SOS) reports the same sizes as the full parse
+    int mxx = p.mxx, myy = p.myy;
+    if (mxx == 0 && p.ncomp >= 1 && p.h[0] > 0 && p.v[0] > 0 && p.width > 0 && p.height > 0) {
+        mxx = (p.width + 8 * p.h[0] - 1) / (8 * p.h[0]);
+        myy = (p.height + 8 * p.v[0] - 1) / (8 * p.v[0]);
+    }
+    info->mxx = mxx;
+    info->myy = myy;
     info->rgba_len = (uint64_t)4 * (uint64_t)p.width * (uint64_t)p.height;
     if (p.ncomp == 1) {
-        info->y_stride = 8 * p.mxx;
-        info->native_len = (uint64_t)(8 * p.mxx) * (uint64_t)(8 * p.myy);
-    } else if (p.ncomp >= 3 && p.mxx > 0) {
+        info->y_stride = 8 * mxx;
+        info->native_len = (uint64_t)(8 * mxx) * (uint64_t)(8 * myy);
+    } else if (p.ncomp >= 3 && mxx > 0) {
         // makeImg + yCbCrSize (decoder.zig:1755-1760, image.zig:521-555)
-        uint64_t w = (uint64_t)8 * p.h[0] * p.mxx, h = (uint64_t)8 * p.v[0] * p.myy, cw, ch;
+        uint64_t w = (uint64_t)8 * p.h[0] * mxx, h = (uint64_t)8 * p.v[0] * myy, cw, ch;
         switch (p.ratio) {
             case ZPX_RATIO_422: cw = (w + 1) / 2; ch = h; break;
             case ZPX_RATIO_420: cw = (w + 1) / 2; ch = (h + 1) / 2; break;

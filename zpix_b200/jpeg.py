@@ -165,6 +165,34 @@ class Batch:
         self.close()
 
 
+class SyntheticBatch(Batch):
+    """Test hook (zpx_batch_open_synthetic): ONE sequential frame given by its geometry and quantisers; its int16
+    coefficient blocks are injected with set_coefficients(), so decode() runs the reconstruction kernels only.
+    comp_hv: per component (h, v); quant_zz: (ncomp, 64) zig-zag order; mode 0 gray, 1 YCbCr, 2 RGB, 3 CMYK, 4 YCbCrK."""
+
+    def __init__(self, ctx: Context, width: int, height: int, comp_hv, quant_zz, mode: int):
+        self.ctx = ctx
+        self.n = 1
+        self._keep = []
+        hv = (C.c_uint8 * len(comp_hv))(*[(h << 4) | v for h, v in comp_hv])
+        q = np.ascontiguousarray(quant_zz, dtype=np.uint16).reshape(len(comp_hv), 64)
+        self._h = C.c_void_p()
+        _check(ctx.handle, lib.zpx_batch_open_synthetic(ctx.handle, width, height, len(comp_hv), hv, q.ctypes.data, mode, C.byref(self._h)))
+
+    def set_coefficients(self, blocks: np.ndarray):
+        b = np.ascontiguousarray(blocks, dtype=np.int16).reshape(-1, 64)
+        _check(self.ctx.handle, lib.zpx_batch_set_coefficients(self._h, 0, b.ctypes.data, b.shape[0]))
+
+
+def test_colour(ctx: Context, mode: int, samples: np.ndarray) -> np.ndarray:
+    """Test hook (zpx_test_colour): the kernels' colour functions on free-standing samples -> (n, 4) uint8."""
+    a = np.ascontiguousarray(samples, dtype=np.uint8)
+    n = a.shape[0]
+    out = np.empty((n, 4), np.uint8)
+    _check(ctx.handle, lib.zpx_test_colour(ctx.handle, mode, a.ctypes.data, n, out.ctypes.data))
+    return out
+
+
 def _rgba_image(inf: ZpxImageInfo, rgba: np.ndarray) -> _image.Image:
     rect = _image.Rectangle.init(0, 0, inf.width, inf.height)
     flat = rgba.reshape(-1)
@@ -213,6 +241,35 @@ def decodeBatchOneCall(buffers: Sequence[bytes], ctx: Optional[Context] = None):
     return [o if s == 0 else None for o, s in zip(outs, st)], st
 
 
+def decodeBatchNative(buffers: Sequence[bytes], ctx: Optional[Context] = None):
+    """The single C-ABI call `zpx_decode_batch_native`: like decodeBatchOneCall, but every image comes back as the
+    variant jpeg.load returns (Image{.YCbCr} / {.Gray} planes with makeImg's strides, {.RGBA}, {.CMYK}).
+    Returns a list with an Image per input, or a JpegError instance for inputs that failed."""
+    ctx = ctx or default_context()
+    n = len(buffers)
+    keep = [np.frombuffer(b, dtype=np.uint8) for b in buffers]
+    infos = []
+    for a in keep:
+        inf = ZpxImageInfo()
+        lib.zpx_probe(a.ctypes.data if a.size else None, a.size, C.byref(inf))
+        infos.append(inf)
+    outs = [np.empty(i.native_len, np.uint8) if (i.status == 0 and i.width > 0 and i.height > 0) else None for i in infos]
+    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in keep])
+    lens = (C.c_size_t * max(n, 1))(*[a.size for a in keep])
+    optr = (C.c_void_p * max(n, 1))(*[o.ctypes.data if o is not None else None for o in outs])
+    st = (C.c_int32 * max(n, 1))()
+    _check(ctx.handle, lib.zpx_decode_batch_native(ctx.handle, ptrs, lens, n, optr, st))
+    res = []
+    for inf, o, s in zip(infos, outs, list(st)[:n]):
+        if s != 0 or o is None:
+            res.append(JpegError(s if s != 0 else inf.status))
+            continue
+        img = _native_image(inf, o, np.zeros(0, np.uint8))
+        img._device_rgba = None  # rgbaPixels() of these images runs the reference's per-pixel formulas on the host
+        res.append(img)
+    return res
+
+
 def loadBatch(paths: Sequence[str], ctx: Optional[Context] = None, raise_on_error: bool = False):
     bufs = []
     for p in paths:
@@ -242,7 +299,7 @@ def loadFromBuffer(buffer: bytes, ctx: Optional[Context] = None) -> _image.Image
     """src/jpeg/root.zig:10.  Returns the same Image variant the reference returns (.Gray/.YCbCr/.RGBA),
     .CMYK for 4-component frames), planes / interleave computed on the GPU."""
     ctx = ctx or default_context()
-    ctx.set_option(2, 1)  # native planes only exist on the unfused path
+    ctx.set_option(9, 1)  # ZPX_OPT_NATIVE_PLANES: the fused kernel writes the planes beside the RGBA
     try:
         with Batch(ctx, [buffer]) as b:
             inf = b.info(0)
@@ -258,7 +315,7 @@ def loadFromBuffer(buffer: bytes, ctx: Optional[Context] = None) -> _image.Image
                 raise JpegError(st2[0])
             return _native_image(inf, nat[0], outs[0])
     finally:
-        ctx.set_option(2, 0)
+        ctx.set_option(9, 0)
 
 
 def load(path: str, ctx: Optional[Context] = None) -> _image.Image:
