@@ -307,10 +307,16 @@ ms = bench.reduce_max(10.0 + 7.0 * rank, dist, "cpu")
 value = bench.aggregate_value(pixels, world, ms)
 seeds = bench.rank_seed_range(per_rank, rank)
 out = [None] * world
-dist.all_gather_object(out, (rank, ms, value, list(seeds)))
-if rank == 0:
-    print(json.dumps(out))
+dist.all_gather_object(out, (rank, ms, value, list(seeds), bench.host_thread_budget(world)))
+# last phase of bench.py: a host-side (gloo) barrier, then every rank but 0 leaves and rank 0 goes on alone
+# (the library's own multi-GPU scheduler is measured by one process over all devices)
+g = dist.new_group(backend="gloo")
+dist.barrier(group=g)
 dist.destroy_process_group()
+if rank == 0:
+    import time
+    time.sleep(0.5)
+    print(json.dumps(out))
 '''
 
 
@@ -332,3 +338,4 @@ def test_bench_multi_rank_plumbing_gloo(tmp_path):
     want = 2 * 5 * 1920 * 1080 / 1e6 / 0.017
     assert all(abs(x[2] - want) / want < 1e-9 for x in res)
     assert res[0][3] == res[1][3]  # every rank decodes its own copy of the same cfg2 batch
+    assert res[0][4] == max(2, (os.cpu_count() or 1) // 2)  # the ranks of a box share its host cores
