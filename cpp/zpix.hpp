@@ -13,6 +13,7 @@
 // error name (error.UnexpectedEof -> "UnexpectedEof").  Pixel storage is std::vector<uint8_t>
 // (the Zig `pixels: []u8` slice owned by the caller).
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <fstream>
@@ -114,35 +115,53 @@ struct Result {
     image::Image img;
 };
 
-// NEW beside loadFromBuffer: Image{.RGBA} per input holding jpeg.load(..).rgbaPixels() bytes.
-inline std::vector<Result> decodeBatch(Context& ctx, const std::vector<std::pair<const uint8_t*, size_t>>& buffers) {
+enum class Output { rgba, native };
+
+// NEW beside loadFromBuffer, ONE library call (zpx_decode_batch_rgba / zpx_decode_batch_native: header parse, upload,
+// kernels and download pipelined in chunks).  Output::rgba: Image{.RGBA} per input holding jpeg.load(..).rgbaPixels()
+// bytes.  Output::native: the variant jpeg.load itself returns (planes with makeImg's strides, decoder.zig:1708-1783).
+// One corrupt input does not fail the batch: it gets its own status.
+inline std::vector<Result> decodeBatch(Context& ctx, const std::vector<std::pair<const uint8_t*, size_t>>& buffers,
+                                       Output output = Output::rgba) {
     const int n = (int)buffers.size();
     std::vector<const uint8_t*> ptrs(n);
     std::vector<size_t> lens(n);
-    for (int i = 0; i < n; i++) { ptrs[i] = buffers[i].first; lens[i] = buffers[i].second; }
-    zpx_batch* b = nullptr;
-    int rc = zpx_batch_open(ctx.handle(), ptrs.data(), lens.data(), n, &b);
-    if (rc) throw Error(rc);
+    std::vector<zpx_image_info> infos(n);
     std::vector<Result> res(n);
     std::vector<uint8_t*> outs(n, nullptr);
     std::vector<int32_t> st(n, 0);
     for (int i = 0; i < n; i++) {
-        zpx_image_info info;
-        zpx_batch_info(b, i, &info);
+        ptrs[i] = buffers[i].first;
+        lens[i] = buffers[i].second;
+        zpx_image_info& info = infos[i];
+        zpx_probe(ptrs[i], lens[i], &info);  // sizes from the header-only probe (decodeConfig)
         res[i].status = info.status;
         if (info.status) continue;
-        image::RGBAImage m{std::vector<uint8_t>(info.rgba_len), (size_t)4 * info.width, image::Rectangle::init(0, 0, info.width, info.height)};
-        res[i].img.v = std::move(m);
-        outs[i] = std::get<image::RGBAImage>(res[i].img.v).pixels.data();
+        const image::Rectangle rect = image::Rectangle::init(0, 0, info.width, info.height);
+        const size_t w4 = (size_t)4 * info.width;
+        if (output == Output::rgba || info.variant == ZPX_VARIANT_RGBA) {
+            res[i].img.v = image::RGBAImage{std::vector<uint8_t>(output == Output::rgba ? info.rgba_len : info.native_len), w4, rect};
+            outs[i] = std::get<image::RGBAImage>(res[i].img.v).pixels.data();
+        } else if (info.variant == ZPX_VARIANT_GRAY) {
+            res[i].img.v = image::GrayImage{std::vector<uint8_t>(info.native_len), (size_t)info.y_stride, rect};
+            outs[i] = std::get<image::GrayImage>(res[i].img.v).pixels.data();
+        } else if (info.variant == ZPX_VARIANT_CMYK) {
+            res[i].img.v = image::CMYKImage{std::vector<uint8_t>(info.native_len), w4, rect};
+            outs[i] = std::get<image::CMYKImage>(res[i].img.v).pixels.data();
+        } else {
+            res[i].img.v = image::YCbCrImage{0, (size_t)info.native_cb_off, (size_t)info.native_cr_off, (size_t)info.y_stride,
+                                             (size_t)info.c_stride, (image::YCbCrSubsample)info.subsample_ratio, rect,
+                                             std::vector<uint8_t>(info.native_len)};
+            outs[i] = std::get<image::YCbCrImage>(res[i].img.v).pixels.data();
+        }
     }
-    rc = zpx_batch_upload(b);
-    if (!rc) rc = zpx_batch_decode(b, nullptr);
-    if (!rc) rc = zpx_batch_fetch_rgba(b, outs.data(), nullptr, st.data());
-    zpx_batch_close(b);
+    const int rc = output == Output::rgba
+                       ? zpx_decode_batch_rgba(ctx.handle(), ptrs.data(), lens.data(), n, outs.data(), nullptr, st.data())
+                       : zpx_decode_batch_native(ctx.handle(), ptrs.data(), lens.data(), n, outs.data(), st.data());
     if (rc) throw Error(rc);
     for (int i = 0; i < n; i++) {
         res[i].status = st[i];
-        if (!st[i]) res[i].img.rgba = std::get<image::RGBAImage>(res[i].img.v).pixels;
+        if (!st[i] && output == Output::rgba) res[i].img.rgba = std::get<image::RGBAImage>(res[i].img.v).pixels;
     }
     return res;
 }
@@ -166,12 +185,12 @@ inline image::Image load(Context& ctx, const std::string& path) {
     return loadFromBuffer(ctx, d.data(), d.size());
 }
 
-inline std::vector<Result> loadBatch(Context& ctx, const std::vector<std::string>& paths) {
+inline std::vector<Result> loadBatch(Context& ctx, const std::vector<std::string>& paths, Output output = Output::rgba) {
     std::vector<std::vector<uint8_t>> files;
     std::vector<std::pair<const uint8_t*, size_t>> bufs;
     for (auto& p : paths) files.push_back(readFile(p));
     for (auto& f : files) bufs.push_back({f.data(), f.size()});
-    return decodeBatch(ctx, bufs);
+    return decodeBatch(ctx, bufs, output);
 }
 
 // reference src/jpeg/decoder.zig:178-218; host only
@@ -186,4 +205,46 @@ inline image::Config decodeConfig(const uint8_t* data, size_t len) {
 inline bool probeBuffer(const uint8_t* data, size_t len) { return len >= 2 && data[0] == 0xFF && data[1] == 0xD8; }
 
 }  // namespace jpeg
+
+// Batch dispatcher beside zpix.fromBuffer / fromFilePath (reference src/root.zig:24-40): same probing order (PNG,
+// JPEG, QOI, BMP).  JPEGs of the batch are decoded together on the GPU and come back as the native variant; this
+// C++ mirror has no CPU decoders for the other formats (zpix's own stay in charge of them): they, and anything
+// unrecognised, get kUnknownImageFormat.
+enum class Format { png, jpeg, qoi, bmp, unknown };
+constexpr int kUnknownImageFormat = -1;  // error.UnknownImageFormat (src/root.zig:30,39)
+
+inline Format probeBuffer(const uint8_t* d, size_t n) {
+    static const uint8_t png_sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (n >= 8 && std::equal(png_sig, png_sig + 8, d)) return Format::png;
+    if (jpeg::probeBuffer(d, n)) return Format::jpeg;
+    if (n >= 4 && d[0] == 'q' && d[1] == 'o' && d[2] == 'i' && d[3] == 'f') return Format::qoi;
+    if (n >= 2 && d[0] == 'B' && d[1] == 'M') return Format::bmp;
+    return Format::unknown;
+}
+
+inline std::vector<jpeg::Result> fromBuffers(jpeg::Context& ctx, const std::vector<std::pair<const uint8_t*, size_t>>& buffers) {
+    std::vector<jpeg::Result> res(buffers.size());
+    std::vector<std::pair<const uint8_t*, size_t>> jpegs;
+    std::vector<size_t> where;
+    for (size_t i = 0; i < buffers.size(); i++) {
+        if (probeBuffer(buffers[i].first, buffers[i].second) == Format::jpeg) {
+            jpegs.push_back(buffers[i]);
+            where.push_back(i);
+        } else {
+            res[i].status = kUnknownImageFormat;
+        }
+    }
+    if (!jpegs.empty()) {
+        auto r = jpeg::decodeBatch(ctx, jpegs, jpeg::Output::native);
+        for (size_t k = 0; k < r.size(); k++) res[where[k]] = std::move(r[k]);
+    }
+    return res;
+}
+
+inline image::Image fromBuffer(jpeg::Context& ctx, const uint8_t* d, size_t n) {
+    auto r = fromBuffers(ctx, {{d, n}});
+    if (r[0].status == kUnknownImageFormat) throw std::runtime_error("error.UnknownImageFormat");
+    if (r[0].status) throw Error(r[0].status);
+    return std::move(r[0].img);
+}
 }  // namespace zpix

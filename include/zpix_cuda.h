@@ -189,10 +189,16 @@ int32_t zpx_batch_size(const zpx_batch *b);
 int32_t zpx_batch_info(const zpx_batch *b, int32_t i, zpx_image_info *out);
 /* Copy every image's entropy-coded segments (still byte-stuffed) and tables to its device: one H2D per device. */
 int32_t zpx_batch_upload(zpx_batch *b);
-/* Run the entropy + IDCT/colour kernels; results stay in device memory.
- * stream: a cudaStream_t to launch on (single-device contexts only), or NULL
- * for the context's own streams.  Returns after the work is enqueued when a
- * stream is given, after completion otherwise.  May be called repeatedly. */
+/* Run the unstuffing + entropy + IDCT/colour kernels; results stay in device memory.
+ * stream: a cudaStream_t to launch on (single-device contexts only), or NULL for the context's own streams.
+ * With NULL the call returns after completion.  With a stream it returns once the work is enqueued -- with one
+ * exception: batches that take the self-synchronising entropy decoder (no or few restart markers) and hold a
+ * segment longer than 32 sub-sequences read one 4-byte convergence flag back per sweep (usually once), i.e. the
+ * call then waits for the synchronisation passes, never for the kernels that write coefficients or pixels.
+ * Ordering contract: work the caller enqueues on `stream` after this call sees the results.  The library's own
+ * reads (zpx_batch_status, zpx_batch_fetch_*, zpx_batch_fetch_coefficients) run on the context's stream, which
+ * the library orders after the decode's last kernel itself: they may be called right away, without synchronising
+ * `stream`.  May be called repeatedly. */
 int32_t zpx_batch_decode(zpx_batch *b, void *stream);
 /* Copy RGBA (Image.rgbaPixels layout: tight rows unless out_stride says otherwise)
  * to caller memory.  out[i] may be NULL to skip image i.  out_stride may be NULL

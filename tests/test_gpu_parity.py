@@ -655,6 +655,15 @@ def test_cpp_host_layer_end_to_end(fixtures_dir, tmp_path):
             h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
         assert line.split()[1] == f"{want.width}x{want.height}"
         assert line.split()[2] == f"fnv1a={h:016x}", line
+    # the batch dispatcher (zpix::fromBuffers, src/root.zig:24-40): native variants, a PNG signature -> UnknownImageFormat
+    r = subprocess.run([str(exe), "--native"] + paths, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for p, line in zip(paths, r.stdout.strip().splitlines()):
+        want = O.decode(open(p, "rb").read())
+        h = 1469598103934665603
+        for b in want.pixels.tobytes():
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        assert line.split()[1] == f"variant={want.variant}" and line.split()[3] == f"fnv1a={h:016x}", line
 
 
 def test_image_over_the_memory_budget_fails_alone(jpeg, fixtures_dir, monkeypatch):

@@ -22,11 +22,18 @@ const c = @cImport({
 
 pub const BatchOptions = struct {
     /// CUDA device ordinals to spread the batch over (images are independent: the host scheduler
-    /// partitions the batch, there is no collective).  Empty = device 0.
+    /// partitions the batch, there is no collective).  Empty = device 0.  Read by `BatchContext.init`
+    /// and by the context-less convenience functions.
     devices: []const i32 = &.{},
-    /// Allocate the pixel slices from pinned host memory (zpx_host_alloc) instead of `al`.
-    /// Faster D2H; such images must be released with `freePinned`, not `Image.free`.
+    /// Put all pixel data of the batch into ONE pinned host allocation (zpx_host_alloc) instead of one
+    /// `al` allocation per image: the device->host copy then runs at PCIe speed and in few large copies.
+    /// The images of such a batch are views into that slab: release the whole batch with `Decoded.deinit`,
+    /// never with `Image.free`.
     pinned: bool = false,
+    /// What each image is: `.rgba` = `Image{ .RGBA }` holding the bytes `jpeg.load(..).rgbaPixels()` yields;
+    /// `.native` = the variant `jpeg.load` itself returns (`.YCbCr` / `.Gray` planes with makeImg's strides,
+    /// `.RGBA` for RGB-tagged files, `.CMYK`): 1.5 bytes per pixel instead of 4 for 4:2:0 files.
+    output: enum { rgba, native } = .rgba,
 };
 
 /// Every Zig error of src/jpeg/decoder.zig, in the order of the ZPX_E_* codes (1..42).
@@ -103,86 +110,181 @@ pub const Result = union(enum) {
     err: DecodeError,
 };
 
-/// Decode a batch of in-memory JPEGs.  The returned slice and every `.ok` image's pixels are
-/// owned by the caller (`Image.free(al)` each, then `al.free(results)`), exactly like the images
-/// `jpeg.loadFromBuffer` returns.  One corrupt input does not fail the batch.
-pub fn decodeBatch(al: std.mem.Allocator, buffers: []const []const u8, opts: BatchOptions) ![]Result {
-    var ctx: ?*c.zpx_ctx = null;
-    var rc = c.zpx_ctx_create(if (opts.devices.len == 0) null else opts.devices.ptr, @intCast(opts.devices.len), &ctx);
-    if (rc != c.ZPX_OK) return toError(rc);
-    defer c.zpx_ctx_destroy(ctx);
+/// The results of one batch.  `deinit` releases everything (the images too).
+pub const Decoded = struct {
+    results: []Result,
+    slab: ?[]u8 = null, // pinned host memory all pixel slices point into (BatchOptions.pinned)
 
-    const n = buffers.len;
-    const ptrs = try al.alloc([*c]const u8, n);
-    defer al.free(ptrs);
-    const lens = try al.alloc(usize, n);
-    defer al.free(lens);
-    for (buffers, 0..) |buf, i| {
-        ptrs[i] = buf.ptr;
-        lens[i] = buf.len;
-    }
-
-    var batch: ?*c.zpx_batch = null;
-    rc = c.zpx_batch_open(ctx, ptrs.ptr, lens.ptr, @intCast(n), &batch);
-    if (rc != c.ZPX_OK) return toError(rc);
-    defer c.zpx_batch_close(batch);
-
-    // the caller's allocator owns every output slice: size them from the header parse
-    const results = try al.alloc(Result, n);
-    errdefer al.free(results);
-    const outs = try al.alloc([*c]u8, n);
-    defer al.free(outs);
-    const status = try al.alloc(i32, n);
-    defer al.free(status);
-    for (0..n) |i| {
-        var info: c.zpx_image_info = undefined;
-        _ = c.zpx_batch_info(batch, @intCast(i), &info);
-        outs[i] = null;
-        if (info.status != c.ZPX_OK) {
-            results[i] = .{ .err = toError(info.status) };
-            continue;
-        }
-        const rect = image.Rectangle.init(0, 0, info.width, info.height);
-        var img = try image.RGBAImage.init(al, rect); // pixels.len == 4*W*H, stride == 4*W
-        outs[i] = img.pixels.ptr;
-        results[i] = .{ .ok = .{ .RGBA = img } };
-    }
-
-    rc = c.zpx_batch_upload(batch);
-    if (rc == c.ZPX_OK) rc = c.zpx_batch_decode(batch, null);
-    if (rc == c.ZPX_OK) rc = c.zpx_batch_fetch_rgba(batch, outs.ptr, null, status.ptr);
-    if (rc != c.ZPX_OK) {
-        for (results) |r| switch (r) {
-            .ok => |img| img.free(al),
-            .err => {},
-        };
-        return toError(rc);
-    }
-    for (0..n) |i| {
-        if (status[i] != c.ZPX_OK) {
-            switch (results[i]) {
+    pub fn deinit(self: *Decoded, al: std.mem.Allocator) void {
+        if (self.slab) |s| {
+            c.zpx_host_free(s.ptr); // the images are views: nothing else to free
+        } else {
+            for (self.results) |r| switch (r) {
                 .ok => |img| img.free(al),
                 .err => {},
-            }
-            results[i] = .{ .err = toError(status[i]) };
+            };
         }
+        al.free(self.results);
+        self.* = undefined;
     }
-    return results;
+};
+
+/// Owns the zpx_ctx: device buffers, pinned staging, streams, the chunk pipeline's workers.  Create ONE per
+/// calling thread and keep it for the life of the program: the first batch sizes the device buffers (about
+/// 15 GB for 1024 x 1080p), later batches reuse them.  Not thread-safe.
+pub const BatchContext = struct {
+    handle: *c.zpx_ctx,
+
+    pub fn init(devices: []const i32) DecodeError!BatchContext {
+        var h: ?*c.zpx_ctx = null;
+        const rc = c.zpx_ctx_create(if (devices.len == 0) null else devices.ptr, @intCast(devices.len), &h);
+        if (rc != c.ZPX_OK) return toError(rc);
+        return .{ .handle = h.? };
+    }
+
+    pub fn deinit(self: *BatchContext) void {
+        c.zpx_ctx_destroy(self.handle);
+        self.* = undefined;
+    }
+
+    /// Decode a batch of in-memory JPEGs with ONE library call (zpx_decode_batch_rgba / zpx_decode_batch_native:
+    /// header parse, upload, kernels and download, pipelined in chunks so that the device->host link stays busy).
+    /// One corrupt input does not fail the batch: it gets its own `.err`.
+    pub fn decodeBatch(self: *BatchContext, al: std.mem.Allocator, buffers: []const []const u8, opts: BatchOptions) !Decoded {
+        const n = buffers.len;
+        const ptrs = try al.alloc([*c]const u8, n);
+        defer al.free(ptrs);
+        const lens = try al.alloc(usize, n);
+        defer al.free(lens);
+        const infos = try al.alloc(c.zpx_image_info, n);
+        defer al.free(infos);
+        const outs = try al.alloc([*c]u8, n);
+        defer al.free(outs);
+        const status = try al.alloc(i32, n);
+        defer al.free(status);
+
+        // sizes from the header-only probe (decodeConfig); the caller's side owns every output byte
+        var total: usize = 0;
+        for (buffers, 0..) |buf, i| {
+            ptrs[i] = buf.ptr;
+            lens[i] = buf.len;
+            _ = c.zpx_probe(buf.ptr, buf.len, &infos[i]);
+            if (infos[i].status == c.ZPX_OK) total += outLen(infos[i], opts) + 255 & ~@as(usize, 255);
+        }
+        var out = Decoded{ .results = try al.alloc(Result, n) };
+        errdefer al.free(out.results);
+        if (opts.pinned and total > 0) {
+            const p: ?[*]u8 = @ptrCast(c.zpx_host_alloc(total));
+            if (p == null) return error.OutOfMemory;
+            out.slab = p.?[0..total];
+        }
+        errdefer if (out.slab) |s| c.zpx_host_free(s.ptr);
+
+        var off: usize = 0;
+        for (0..n) |i| {
+            outs[i] = null;
+            if (infos[i].status != c.ZPX_OK) {
+                out.results[i] = .{ .err = toError(infos[i].status) };
+                continue;
+            }
+            const len = outLen(infos[i], opts);
+            const pixels: []u8 = if (out.slab) |s| s[off .. off + len] else try al.alloc(u8, len);
+            off += len + 255 & ~@as(usize, 255);
+            outs[i] = pixels.ptr;
+            out.results[i] = .{ .ok = wrap(infos[i], pixels, opts) };
+        }
+
+        const rc = switch (opts.output) {
+            .rgba => c.zpx_decode_batch_rgba(self.handle, ptrs.ptr, lens.ptr, @intCast(n), outs.ptr, null, status.ptr),
+            .native => c.zpx_decode_batch_native(self.handle, ptrs.ptr, lens.ptr, @intCast(n), outs.ptr, status.ptr),
+        };
+        if (rc != c.ZPX_OK) {
+            out.deinit(al);
+            return toError(rc);
+        }
+        for (0..n) |i| {
+            if (status[i] == c.ZPX_OK) continue;
+            switch (out.results[i]) {
+                .ok => |img| if (out.slab == null) img.free(al),
+                .err => {},
+            }
+            out.results[i] = .{ .err = toError(status[i]) };
+        }
+        return out;
+    }
+
+    /// Same, reading the files first (beside `jpeg.load`, reference src/jpeg/root.zig:36).
+    pub fn loadBatch(self: *BatchContext, al: std.mem.Allocator, paths: []const []const u8, opts: BatchOptions) !Decoded {
+        const bufs = try al.alloc([]const u8, paths.len);
+        var loaded: usize = 0;
+        defer {
+            for (bufs[0..loaded]) |b| al.free(b);
+            al.free(bufs);
+        }
+        for (paths, 0..) |p, i| {
+            bufs[i] = try std.fs.cwd().readFileAlloc(al, p, std.math.maxInt(usize));
+            loaded = i + 1;
+        }
+        return self.decodeBatch(al, bufs, opts);
+    }
+
+    /// GPU-resident hand-off: the staged calls, for consumers that take the RGBA where the kernels left it
+    /// (zpx_batch_device_rgba) on their own stream.  See include/zpix_cuda.h for the ordering contract.
+    pub fn raw(self: *BatchContext) *c.zpx_ctx {
+        return self.handle;
+    }
+};
+
+fn outLen(info: c.zpx_image_info, opts: BatchOptions) usize {
+    return @intCast(if (opts.output == .rgba) info.rgba_len else info.native_len);
 }
 
-/// Same, reading the files first (beside `jpeg.load`, reference src/jpeg/root.zig:36).
-pub fn loadBatch(al: std.mem.Allocator, paths: []const []const u8, opts: BatchOptions) ![]Result {
-    const bufs = try al.alloc([]const u8, paths.len);
-    var loaded: usize = 0;
-    defer {
-        for (bufs[0..loaded]) |b| al.free(b);
-        al.free(bufs);
-    }
-    for (paths, 0..) |p, i| {
-        bufs[i] = try std.fs.cwd().readFileAlloc(al, p, std.math.maxInt(usize));
-        loaded = i + 1;
-    }
-    return decodeBatch(al, bufs, opts);
+/// The Image a result slice is: Image{.RGBA} for rgbaPixels bytes, else the variant jpeg.load returns
+/// (decoder.zig:361-370) with makeImg's strides (decoder.zig:1708-1783).
+fn wrap(info: c.zpx_image_info, pixels: []u8, opts: BatchOptions) image.Image {
+    const rect = image.Rectangle.init(0, 0, info.width, info.height);
+    const w4: usize = @intCast(4 * info.width);
+    if (opts.output == .rgba or info.variant == c.ZPX_VARIANT_RGBA)
+        return .{ .RGBA = .{ .pixels = pixels, .stride = w4, .rect = rect } };
+    return switch (info.variant) {
+        c.ZPX_VARIANT_GRAY => .{ .Gray = .{ .pixels = pixels, .stride = @intCast(info.y_stride), .rect = rect } },
+        c.ZPX_VARIANT_CMYK => .{ .CMYK = .{ .pixels = pixels, .stride = w4, .rect = rect } },
+        else => .{ .YCbCr = .{
+            .y = pixels[0..@intCast(info.native_cb_off)],
+            .cb = pixels[@intCast(info.native_cb_off)..@intCast(info.native_cr_off)],
+            .cr = pixels[@intCast(info.native_cr_off)..],
+            .y_stride = @intCast(info.y_stride),
+            .c_stride = @intCast(info.c_stride),
+            .subsample_ratio = @enumFromInt(info.subsample_ratio), // same order as image.YCbCrSubsample
+            .rect = rect,
+            .pixels = pixels,
+        } },
+    };
+}
+
+/// Convenience for a single batch: creates a context, decodes, destroys it.  Costs a device-buffer allocation
+/// per call -- programs that decode more than once keep a `BatchContext`.
+pub fn decodeBatch(al: std.mem.Allocator, buffers: []const []const u8, opts: BatchOptions) !Decoded {
+    var ctx = try BatchContext.init(opts.devices);
+    defer ctx.deinit();
+    return ctx.decodeBatch(al, buffers, opts);
+}
+
+pub fn loadBatch(al: std.mem.Allocator, paths: []const []const u8, opts: BatchOptions) !Decoded {
+    var ctx = try BatchContext.init(opts.devices);
+    defer ctx.deinit();
+    return ctx.loadBatch(al, paths, opts);
+}
+
+/// `jpeg.loadFromBuffer` itself on the GPU path (reference src/jpeg/root.zig:10): one image, the native variant,
+/// pixels owned by `al` exactly as the reference's.
+pub fn loadFromBufferGpu(ctx: *BatchContext, al: std.mem.Allocator, buffer: []const u8) !image.Image {
+    var d = try ctx.decodeBatch(al, &.{buffer}, .{ .output = .native });
+    defer al.free(d.results);
+    return switch (d.results[0]) {
+        .ok => |img| img,
+        .err => |e| e,
+    };
 }
 
 /// Header-only probe (decodeConfig, reference decoder.zig:178) through the same parser the batch
