@@ -21,6 +21,21 @@ constexpr int W1 = 2841, W2 = 2676, W3 = 2408, W5 = 1609, W6 = 1108, W7 = 565;
 constexpr int W1PW7 = W1 + W7, W1MW7 = W1 - W7, W2PW6 = W2 + W6, W2MW6 = W2 - W6, W3PW5 = W3 + W5, W3MW5 = W3 - W5;
 constexpr int R2 = 181;
 
+// Arithmetic right shift by K as a multiply-high: floor(x / 2^K) == (x * 2^(32-K)) >> 32 for every int32 x, so the
+// value is the reference's `>> K` exactly; the instruction (IMAD.HI) goes to the FMA pipe instead of the ALU pipe,
+// which the shifts, adds and packs of the IDCT keep busier (ZPX_SHIFT_VIA_MULHI selects, measured both ways).
+#ifndef ZPX_SHIFT_VIA_MULHI
+#define ZPX_SHIFT_VIA_MULHI 0
+#endif
+template <int K>
+__device__ __forceinline__ int asr(int x) {
+#if ZPX_SHIFT_VIA_MULHI
+    return __mulhi(x, 1 << (32 - K));
+#else
+    return x >> K;
+#endif
+}
+
 // signed halves of a packed pair of int16
 __device__ __forceinline__ int lo16(uint32_t w) { return (int)(short)(w & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t w) { return ((int)w) >> 16; }
@@ -54,14 +69,14 @@ __device__ __forceinline__ void idct_row(int x0, int x4, int x3, int x7, int x1,
     x2 = (R2 * (x4 + x5) + 128) >> 8;
     x4 = (R2 * (x4 - x5) + 128) >> 8;
 
-    o[0] = (x7 + x1) >> 8;
-    o[1] = (x3 + x2) >> 8;
-    o[2] = (x0 + x4) >> 8;
-    o[3] = (x8 + x6) >> 8;
-    o[4] = (x8 - x6) >> 8;
-    o[5] = (x0 - x4) >> 8;
-    o[6] = (x3 - x2) >> 8;
-    o[7] = (x7 - x1) >> 8;
+    o[0] = asr<8>(x7 + x1);
+    o[1] = asr<8>(x3 + x2);
+    o[2] = asr<8>(x0 + x4);
+    o[3] = asr<8>(x8 + x6);
+    o[4] = asr<8>(x8 - x6);
+    o[5] = asr<8>(x0 - x4);
+    o[6] = asr<8>(x3 - x2);
+    o[7] = asr<8>(x7 - x1);
 }
 
 // Column pass on one column (stride 8 inside b), in place.  idct.zig:149-199.
@@ -94,14 +109,14 @@ __device__ __forceinline__ void idct_col(int* b) {
     y2 = (R2 * (y4 + y5) + 128) >> 8;
     y4 = (R2 * (y4 - y5) + 128) >> 8;
 
-    b[8 * 0] = (y7 + y1) >> 14;
-    b[8 * 1] = (y3 + y2) >> 14;
-    b[8 * 2] = (y0 + y4) >> 14;
-    b[8 * 3] = (y8 + y6) >> 14;
-    b[8 * 4] = (y8 - y6) >> 14;
-    b[8 * 5] = (y0 - y4) >> 14;
-    b[8 * 6] = (y3 - y2) >> 14;
-    b[8 * 7] = (y7 - y1) >> 14;
+    b[8 * 0] = asr<14>(y7 + y1);
+    b[8 * 1] = asr<14>(y3 + y2);
+    b[8 * 2] = asr<14>(y0 + y4);
+    b[8 * 3] = asr<14>(y8 + y6);
+    b[8 * 4] = asr<14>(y8 - y6);
+    b[8 * 5] = asr<14>(y0 - y4);
+    b[8 * 6] = asr<14>(y3 - y2);
+    b[8 * 7] = asr<14>(y7 - y1);
 }
 
 // pack four int32 to bytes with signed saturation to [-128,127], then +128 (== ^0x80 on each byte)

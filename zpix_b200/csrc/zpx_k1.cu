@@ -176,6 +176,10 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     const uint32_t total = st.count + (probe ? 1u : 0u);
     uint32_t left = total;  // blocks still to decode (including the current one and the probe)
 
+    // block flush (end of the loop body): this lane stores row (lane & 7) of the blocks of lanes 4 i + (lane >> 3)
+    const uint32_t r16 = (uint32_t)(lane & 7) << 4;
+    const uint32_t sbr = sbw + (uint32_t)(lane >> 3) * K1_BLKB, sir = siw + (uint32_t)(lane >> 3) * 8;
+
     while (__any_sync(0xffffffffu, left != 0)) {
         int k = 64;  // > 63: no block in flight on this lane
         int err = 0;
@@ -270,7 +274,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
             if (more) rd.topup();
         }
         // ---- block end ----
-        // flush record of this lane's block: x = block index (low 32 bits), y = high bits | key << 16 |
+        // flush record of this lane's block: x = destination address (low 32 bits), y = high 16 bits | key << 16 |
         // (store it) << 24 | (zero it) << 25; 0 = nothing to do
         uint32_t fx = 0, fy = 0;
         if (SUB && tail) {
@@ -311,8 +315,9 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                     blk = im->comp_base[comp] + (uint64_t)byn * im->comp_bw[comp] + bx;
                 }
                 const bool keep = !(bi.w & 0x40000u) && !(P.dbg & 1);  // not superseded by a later scan of the same component
-                fx = (uint32_t)blk;
-                fy = (uint32_t)(blk >> 32) | (bx & 7u) << 16 | (keep ? 1u << 24 : 0u) | 1u << 25;
+                const unsigned long long dst = (unsigned long long)(P.coef + blk * 8);  // (device addresses fit 48 bits)
+                fx = (uint32_t)dst;
+                fy = (uint32_t)(dst >> 32) | (bx & 7u) << 16 | (keep ? 1u << 24 : 0u) | 1u << 25;
                 left--;
                 if (interleaved) {
                     if (++c == nblk) {
@@ -341,15 +346,13 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < LPW / 4; i++) {
-                const int s = 4 * i + (lane >> 3);
-                uint32_t ix, iy;
-                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ix), "=r"(iy) : "r"(siw + s * 8));
+                uint32_t ix, iy;  // record of lane 4 i + (lane >> 3): x = address low, y = high | key << 16 | flags << 24
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ix), "=r"(iy) : "r"(sir + i * 32));
                 if (iy >> 24) {
-                    const uint32_t r = lane & 7u;
-                    const uint32_t a = sbw + s * K1_BLKB + ((r ^ ((iy >> 16) & 7u)) << 4);
+                    const uint32_t a = sbr + i * (4 * K1_BLKB) + ((r16 ^ (iy >> 12)) & 0x70u);  // row (r ^ key) of that lane's block
                     if (iy & (1u << 24)) {
-                        const uint64_t blk = (uint64_t)ix | (uint64_t)(iy & 0xffffu) << 32;
-                        P.coef[blk * 8 + r] = lds_u128(a);
+                        uint4* g = reinterpret_cast<uint4*>(((unsigned long long)(iy & 0xffffu) << 32 | ix) + r16);
+                        *g = lds_u128(a);
                     }
                     sts_zero16(a);
                 }

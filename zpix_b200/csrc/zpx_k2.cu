@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
         // native planes (makeImg's layout, decoder.zig:1708-1783), when the launch writes them
         uint64_t poff[3];
         int32_t ystride, cstride;
+        uint32_t magic;   // phase 2: 2^32 / (items per row) + 1, for the exact division of an item index by it
     };
     __shared__ TileCtx ctx[NS];
     __shared__ __align__(16) uint32_t qsm[NS][3 * 32];  // per row four words q[2j] | q[2j+1] << 24 (dp2a operands)
@@ -151,6 +152,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
             c.poff[2] = imn->plane_off[2];
             c.ystride = imn->plane_stride[0];
             c.cstride = imn->plane_stride[1];
+            {
+                constexpr int PXW_ = (V == 2) ? 4 : 8;
+                const uint32_t ipr_ = c.wt * (uint32_t)(Cfg::MCU_W / PXW_);
+                c.magic = ipr_ > 1 ? 0xffffffffu / ipr_ + 1u : 0u;  // exact it / ipr for it, ipr < 2^16
+            }
             ctx[stg] = c;
         }
         if (tid < 32 * NC) {
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
             const int PYt = (NC == 1) ? wt * 8 + 16 : PY;
             const int ipr = wt * (Cfg::MCU_W / PXW);  // items per row(-pair)
             const int items = ipr * ((NC == 1 ? (int)t.nr * 8 : Cfg::YROWS) / RP);
-            const uint32_t magic = ipr > 1 ? 0xffffffffu / (uint32_t)ipr + 1u : 0u;  // exact it/ipr for it, ipr < 2^16
+            const uint32_t magic = t.magic;  // 2^32 / ipr + 1: exact it / ipr for it, ipr < 2^16
             uint8_t* __restrict__ outp = P.out + t.out_off;
             const bool vec_ok = (W & 3) == 0;
             for (int it = tid; it < items; it += NT) {
