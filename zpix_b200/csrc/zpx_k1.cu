@@ -256,27 +256,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                     // decoder.zig:946-969), inline.  Everything else (End-Of-Band runs, values of 13 bits or more,
                     // invalid codes, tables in HBM) takes the general path.
                     uint32_t e2 = 0;
-                    if (SMEM && e0 == 0) {
-                        const uint32_t v16 = hi >> 16, slot = (bi.w >> 24) & 15u;
-                        const uint32_t la = tb + (uint32_t)offsetof(K1Tables, lim) + slot * 64u;
-                        const uint4 la9 = lds_u128(la + 32), la13 = lds_u128(la + 48);  // limit[9..12], limit[13..16]
-                        int len = 0;
-                        if (v16 < la13.w) len = 16;
-                        if (v16 < la13.z) len = 15;
-                        if (v16 < la13.y) len = 14;
-                        if (v16 < la13.x) len = 13;
-                        if (v16 < la9.w) len = 12;
-                        if (v16 < la9.z) len = 11;
-                        if (v16 < la9.y) len = 10;
-                        if (len != 0) {
-                            const int off = (int)lds_u32(tb + (uint32_t)offsetof(K1Tables, valoff) + slot * 64u + (uint32_t)(len - 1) * 4u);
-                            const uint32_t sym = lds_u8(tb + (uint32_t)offsetof(K1Tables, vals) + slot * 256u + (uint32_t)((off + (int)(v16 >> (16 - len))) & 0xff));
-                            const uint32_t r = sym >> 4, s2 = sym & 15u;
-                            if (s2 != 0 && s2 < 13) e2 = ZPX_FE((uint32_t)len + s2, len, s2, r + 1, 0);
-                            else if (sym == 0xf0u) e2 = ZPX_FE(len, len, 0, 16, 0);
-                            else if (sym == 0) e2 = ZPX_FE(len, len, 0, 64, 0);
-                        }
-                    }
+                    if (SMEM && e0 == 0) e2 = k1_long_ac_sm(tb, (bi.w >> 24) & 15u, hi);
                     if (e2 == 0) e2 = k1_rare<SMEM>(P, hi, false, e0, bi, tb, eob_run, err, wide);
                     // End-Of-Band RUN inside a sequential scan: the synchronisation passes do not
                     // model that state

@@ -311,4 +311,31 @@ static __device__ __noinline__ unsigned long long k1_slow_symbol_sm(uint32_t tb,
     return k1_pack_symbol(sym, len, isdc);
 }
 
+// The common rare symbol, inline: an ordinary AC run/size symbol whose code is longer than the first-level table
+// (tables in the CTA's cache).  Canonical search over the cached limits -- first match = the reference's rule,
+// decoder.zig:946-969.  Returns its ZPX_FE entry, or 0 for everything else (End-Of-Band runs, values of 13 bits
+// or more, invalid codes): those take k1_slow_symbol_sm.
+__device__ __forceinline__ uint32_t k1_long_ac_sm(uint32_t tb, uint32_t slot, uint32_t hi) {
+    static_assert(K1_ALB == 9, "the search below starts at length 10");
+    const uint32_t v16 = hi >> 16;
+    const uint32_t la = tb + (uint32_t)offsetof(K1Tables, lim) + slot * 64u;
+    const uint4 la9 = lds_u128(la + 32), la13 = lds_u128(la + 48);  // limit[9..12], limit[13..16]
+    int len = 0;
+    if (v16 < la13.w) len = 16;
+    if (v16 < la13.z) len = 15;
+    if (v16 < la13.y) len = 14;
+    if (v16 < la13.x) len = 13;
+    if (v16 < la9.w) len = 12;
+    if (v16 < la9.z) len = 11;
+    if (v16 < la9.y) len = 10;
+    if (len == 0) return 0;
+    const int off = (int)lds_u32(tb + (uint32_t)offsetof(K1Tables, valoff) + slot * 64u + (uint32_t)(len - 1) * 4u);
+    const uint32_t sym = lds_u8(tb + (uint32_t)offsetof(K1Tables, vals) + slot * 256u + (uint32_t)((off + (int)(v16 >> (16 - len))) & 0xff));
+    const uint32_t r = sym >> 4, s2 = sym & 15u;
+    if (s2 != 0 && s2 < 13) return ZPX_FE((uint32_t)len + s2, len, s2, r + 1, 0);
+    if (sym == 0xf0u) return ZPX_FE(len, len, 0, 16, 0);
+    if (sym == 0) return ZPX_FE(len, len, 0, 64, 0);
+    return 0;
+}
+
 }  // namespace zpx

@@ -155,8 +155,9 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
                 uint32_t e;
                 if (SMEM) e = lds_u32(isdc ? bi.x + ((hi >> (32 - K1_DLB)) << 2) : bi.y + ((hi >> (32 - K1_ALB)) << 2));
                 else e = __ldg((isdc ? fdc : fac) + (hi >> (32 - ZPX_LUT_BITS)));
+                if (SMEM && e == 0 && !isdc) e = k1_long_ac_sm(tb, (bi.w >> 24) & 15u, hi);  // the common rare case, inline
                 if ((int)e <= 0) {
-                    // longer code / invalid code / EOB run / DC category > 16 (about 1 % of the symbols)
+                    // longer code / invalid code / EOB run / DC category > 16
                     unsigned long long r;
                     if (SMEM) r = k1_slow_symbol_sm(tb, isdc ? (bi.w >> 20) & 15u : (bi.w >> 24) & 15u, hi, isdc, e);
                     else r = k1_slow_symbol(&P.huff[isdc ? bi.x : bi.y], hi, isdc, e);
