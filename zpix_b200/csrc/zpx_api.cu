@@ -588,16 +588,16 @@ void build_plan(zpx_batch* b, int di) {
     const int64_t mode = b->ctx->opt_entropy_mode;
     {
         // auto: estimated time of either decoder (measured on B200, cfg2-like data).  One lane per interval is bound
-        // by its longest interval while there are few of them (about 2.3 MB/s per lane) and by instruction issue
-        // once the GPU is full (78 GB/s); the self-synchronising decoder parallelises inside intervals but decodes
-        // everything about twice (25-36 GB/s) and has a fixed cost of a few launches.
+        // by its longest interval while there are few of them (a lane decodes about 2.1 MB/s) and by instruction
+        // issue once the GPU is full (125 GB/s); the self-synchronising decoder parallelises inside intervals but
+        // decodes everything twice (45 GB/s) and has a fixed cost of a few launches.
         uint64_t total = 0, longest = 0;
         for (size_t k = 0; k < pl.n_seq; k++) {
             total += pl.ivs[k].len;
             longest = std::max<uint64_t>(longest, pl.ivs[k].len);
         }
-        const double lane_s = std::max((double)longest / 2.3e6, (double)total / 78e9);
-        const double sub_s = 0.3e-3 + (double)total / (total < (200u << 20) ? 25e9 : 36e9);
+        const double lane_s = std::max((double)longest / 2.1e6, (double)total / 125e9);
+        const double sub_s = 0.3e-3 + (double)total / (total < (100u << 20) ? 38e9 : 45e9);
         pl.sub_mode = mode == 2 || (mode == 0 && sub_s < lane_s);
     }
     pl.n_sub_iv = 0;
@@ -608,10 +608,13 @@ void build_plan(zpx_batch* b, int di) {
         pl.n_sub_iv = keep.size();
         std::copy(keep.begin(), keep.end(), pl.ivs.begin());
         std::copy(lane.begin(), lane.end(), pl.ivs.begin() + (ptrdiff_t)keep.size());
-        const uint32_t submax = b->ctx->opt_subseq > 0 ? (uint32_t)align_up((size_t)b->ctx->opt_subseq, 4) : 256u;
         for (size_t k = 0; k < pl.n_sub_iv; k++) {
             ZpxIntervalDev& d = pl.ivs[k];
             const uint32_t span = d.ulen;
+            // sub-sequence size: long streams re-synchronise more slowly (more blocks per MCU, longer runs past the
+            // boundary) and have lanes to spare: measured on B200, 384 bytes for 512x512 files, 768 for 2160p ones
+            const uint32_t submax = b->ctx->opt_subseq > 0 ? (uint32_t)align_up((size_t)b->ctx->opt_subseq, 4)
+                                    : span < (256u << 10) ? 384u : span < (1u << 20) ? 512u : 768u;
             uint32_t sub = (uint32_t)align_up((span + 31) / 32, 4);
             sub = std::max(32u, std::min(submax, sub));
             d.sub_bytes = sub;

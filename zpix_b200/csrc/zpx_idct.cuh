@@ -248,11 +248,11 @@ __device__ __forceinline__ uint32_t ycc_pixel(int y, int rr, int gg, int bb) {
     return pack4_sat_u8(r >> 16, g >> 16, b >> 16, 255);
 }
 // per-chroma-sample terms, shared by every luma pixel that replicates the sample
+// (cb - 128, cr - 128 of color.zig:92-93 multiplied out: the same integers, one multiply-add per term)
 __device__ __forceinline__ void chroma_terms(int cb, int cr, int& rr, int& gg, int& bb) {
-    const int cb1 = cb - 128, cr1 = cr - 128;
-    rr = 91881 * cr1;
-    gg = -22554 * cb1 - 46802 * cr1;
-    bb = 116130 * cb1;
+    rr = 91881 * cr - 91881 * 128;
+    gg = -22554 * cb + (-46802 * cr + (22554 + 46802) * 128);
+    bb = 116130 * cb - 116130 * 128;
 }
 // CMYK -> RGBA8 (color.zig:115-121, then >>8).  c,m,y,k are the stored (already inverted) bytes.
 __device__ __forceinline__ uint32_t cmyk_pixel(uint32_t c, uint32_t m, uint32_t y, uint32_t k) {
