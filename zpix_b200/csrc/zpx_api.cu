@@ -766,8 +766,8 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         k2.img_flags = img_flags;
         k2.ntiles = (int)g.tiles.size();
         k2.tmax = g.tmax;
-        const int grid = std::min<int>(k2.ntiles, dc.sm_count * (512 / k2_fused_threads(g.h, g.v, g.nc)));
-        CU(ctx, k2_launch_fused(g.h, g.v, g.nc, k2, grid, st));
+        k2.nt = std::max(96, (g.tmax * k2_fused_bpm(g.h, g.v, g.nc) + 31) / 32 * 32);
+        CU(ctx, k2_launch_fused(g.h, g.v, g.nc, k2, dc.sm_count, st));
         k2_launches++;
     }
     CU(ctx, cudaEventRecord(dc.ev[2], st));

@@ -82,8 +82,11 @@ struct K2Cfg {
     }
 };
 
-template <int H, int V, int NC, int NS, int NT>
-__global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
+// NTMAX bounds the registers (512 threads per SM); the launch uses as many threads as the group's largest tile has
+// blocks (K2Params::nt, a multiple of 32), so that phase 1 leaves no thread without a block.
+template <int H, int V, int NC, int NS, int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P) {
+    const int NT = (int)blockDim.x;
     using Cfg = K2Cfg<H, V, NC>;
     constexpr int BPM = Cfg::BPM;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
         uint64_t poff[3];
         int32_t ystride, cstride;
         uint32_t magic;   // phase 2: 2^32 / (items per row) + 1, for the exact division of an item index by it
+        uint32_t interior;  // every pixel of the tile lies inside the image and rows are 16-byte multiples: no bounds tests
     };
     __shared__ TileCtx ctx[NS];
     __shared__ __align__(16) uint32_t qsm[NS][3 * 32];  // per row four words q[2j] | q[2j+1] << 24 (dp2a operands)
@@ -156,6 +160,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
                 constexpr int PXW_ = (V == 2) ? 4 : 8;
                 const uint32_t ipr_ = c.wt * (uint32_t)(Cfg::MCU_W / PXW_);
                 c.magic = ipr_ > 1 ? 0xffffffffu / ipr_ + 1u : 0u;  // exact it / ipr for it, ipr < 2^16
+                const int rows_ = NC == 1 ? (int)c.nr * 8 : Cfg::YROWS;
+                c.interior = ((c.width & 3) == 0 && (int)(c.mx0 + c.wt) * Cfg::MCU_W <= c.width && (int)c.my * Cfg::YROWS + rows_ <= c.height) ? 1u : 0u;
             }
             ctx[stg] = c;
         }
@@ -301,6 +307,59 @@ __global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
             const uint32_t magic = t.magic;  // 2^32 / ipr + 1: exact it / ipr for it, ipr < 2^16
             uint8_t* __restrict__ outp = P.out + t.out_off;
             const bool vec_ok = (W & 3) == 0;
+            if (t.interior) {
+                // tile entirely inside the image (all but the right / bottom edge tiles): no bounds tests, one
+                // 64-bit base address per tile, 32-bit offsets from it
+                uint8_t* __restrict__ ob = outp + ((size_t)y0 * (size_t)W + (size_t)x0) * 4u;
+                const uint32_t rowb = (uint32_t)W * 4u;
+                for (int it = tid; it < items; it += NT) {
+                    const uint32_t rp = ipr > 1 ? __umulhi((uint32_t)it, magic) : (uint32_t)it;
+                    const uint32_t xg = (uint32_t)it - rp * (uint32_t)ipr;
+                    int rr[NCS], gg[NCS], bb[NCS];
+                    if (NC == 3) {
+                        const uint32_t coff = rp * (uint32_t)(V == 2 ? 1 : RP) * (uint32_t)PC + (PXW * xg) / H;
+                        uint32_t cbw[2] = {0, 0}, crw[2] = {0, 0};
+                        if (NCS == 8) {
+                            const uint2 a2 = *reinterpret_cast<const uint2*>(planeCb + coff), b2 = *reinterpret_cast<const uint2*>(planeCr + coff);
+                            cbw[0] = a2.x; cbw[1] = a2.y; crw[0] = b2.x; crw[1] = b2.y;
+                        } else if (NCS == 4) {
+                            cbw[0] = *reinterpret_cast<const uint32_t*>(planeCb + coff);
+                            crw[0] = *reinterpret_cast<const uint32_t*>(planeCr + coff);
+                        } else if (NCS == 2) {
+                            cbw[0] = *reinterpret_cast<const uint16_t*>(planeCb + coff);
+                            crw[0] = *reinterpret_cast<const uint16_t*>(planeCr + coff);
+                        } else {
+                            cbw[0] = planeCb[coff];
+                            crw[0] = planeCr[coff];
+                        }
+#pragma unroll
+                        for (int k = 0; k < NCS; k++)
+                            chroma_terms((int)__byte_perm(cbw[k >> 2], 0, 0x4440 + (k & 3)), (int)__byte_perm(crw[k >> 2], 0, 0x4440 + (k & 3)),
+                                         rr[k], gg[k], bb[k]);
+                    }
+                    const uint8_t* yp = planeY + rp * (uint32_t)(RP * PYt) + PXW * xg;
+                    uint8_t* o = ob + (rp * (uint32_t)RP * rowb + xg * (uint32_t)(PXW * 4));
+#pragma unroll
+                    for (int r = 0; r < RP; r++) {
+#pragma unroll
+                        for (int g = 0; g < PXW / 4; g++) {
+                            const uint32_t yw = *reinterpret_cast<const uint32_t*>(yp + r * PYt + 4 * g);
+                            uint32_t p[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const uint32_t yv = __byte_perm(yw, 0, 0x4440 + j);
+                                if (NC == 1) {
+                                    p[j] = yv * 0x010101u | 0xff000000u;
+                                } else {
+                                    const int ci = (4 * g + j) / H;
+                                    p[j] = ycc_pixel((int)yv, rr[ci], gg[ci], bb[ci]);
+                                }
+                            }
+                            __stcs(reinterpret_cast<uint4*>(o + (uint32_t)r * rowb) + g, make_uint4(p[0], p[1], p[2], p[3]));
+                        }
+                    }
+                }
+            } else
             for (int it = tid; it < items; it += NT) {
                 const int rp = ipr > 1 ? (int)__umulhi((uint32_t)it, magic) : it;
                 const int xg = it - rp * ipr;
@@ -370,36 +429,41 @@ __global__ void __launch_bounds__(NT, 512 / NT) k2_fused(const K2Params P) {
     }
 }
 
-template <int H, int V, int NC, int NS, int NT>
-static cudaError_t launch_fused_ns(const K2Params& P, int grid, cudaStream_t s) {
+template <int H, int V, int NC, int NS, int NTMAX>
+static cudaError_t launch_fused_ns(const K2Params& P, int sms, cudaStream_t s) {
     using Cfg = K2Cfg<H, V, NC>;
     const size_t smem = Cfg::smem_bytes(P.tmax, NS);
-    cudaError_t e = cudaFuncSetAttribute(k2_fused<H, V, NC, NS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k2_fused<H, V, NC, NS, NTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k2_fused<H, V, NC, NS, NT><<<grid, NT, smem, s>>>(P);
+    const int nt = P.nt >= 96 && P.nt <= NTMAX ? P.nt : NTMAX;  // (>= 96: 32 threads per component stage the quantisers)
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_fused<H, V, NC, NS, NTMAX>, nt, smem);
+    if (e != cudaSuccess) return e;
+    const int grid = P.ntiles < sms * occ ? P.ntiles : sms * (occ > 0 ? occ : 1);
+    k2_fused<H, V, NC, NS, NTMAX><<<grid, nt, smem, s>>>(P);
     return cudaGetLastError();
 }
 
 // three stages when all resident CTAs of that size still fit one SM (227 KB), else two
 template <int H, int V, int NC>
-static cudaError_t launch_fused_t(const K2Params& P, int grid, cudaStream_t s) {
+static cudaError_t launch_fused_t(const K2Params& P, int sms, cudaStream_t s) {
     using Cfg = K2Cfg<H, V, NC>;
     constexpr int NT = (NC == 3 && H == 2 && V == 2) ? 256 : 128;  // == k2_fused_threads(H, V, NC)
-    if ((512 / NT) * (Cfg::smem_bytes(P.tmax, 3) + 1024) <= 227 * 1024) return launch_fused_ns<H, V, NC, 3, NT>(P, grid, s);
-    return launch_fused_ns<H, V, NC, 2, NT>(P, grid, s);
+    if ((512 / NT) * (Cfg::smem_bytes(P.tmax, 3) + 1024) <= 227 * 1024) return launch_fused_ns<H, V, NC, 3, NT>(P, sms, s);
+    return launch_fused_ns<H, V, NC, 2, NT>(P, sms, s);
 }
 
 int k2_fused_bpm(int h, int v, int nc) { return nc == 1 ? 1 : h * v + 2; }
 
-cudaError_t k2_launch_fused(int h, int v, int nc, const K2Params& P, int grid, cudaStream_t s) {
-    if (nc == 1) return launch_fused_t<1, 1, 1>(P, grid, s);
+cudaError_t k2_launch_fused(int h, int v, int nc, const K2Params& P, int sms, cudaStream_t s) {
+    if (nc == 1) return launch_fused_t<1, 1, 1>(P, sms, s);
     switch (h << 4 | v) {
-        case 0x11: return launch_fused_t<1, 1, 3>(P, grid, s);
-        case 0x21: return launch_fused_t<2, 1, 3>(P, grid, s);
-        case 0x22: return launch_fused_t<2, 2, 3>(P, grid, s);
-        case 0x12: return launch_fused_t<1, 2, 3>(P, grid, s);
-        case 0x41: return launch_fused_t<4, 1, 3>(P, grid, s);
-        case 0x42: return launch_fused_t<4, 2, 3>(P, grid, s);
+        case 0x11: return launch_fused_t<1, 1, 3>(P, sms, s);
+        case 0x21: return launch_fused_t<2, 1, 3>(P, sms, s);
+        case 0x22: return launch_fused_t<2, 2, 3>(P, sms, s);
+        case 0x12: return launch_fused_t<1, 2, 3>(P, sms, s);
+        case 0x41: return launch_fused_t<4, 1, 3>(P, sms, s);
+        case 0x42: return launch_fused_t<4, 2, 3>(P, sms, s);
     }
     return cudaErrorInvalidValue;
 }

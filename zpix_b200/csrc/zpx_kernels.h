@@ -67,9 +67,11 @@ struct K2Params {
     const uint32_t* img_flags;  // K1Params::img_flags
     int ntiles;
     int tmax;  // largest tile (MCUs): fixes the shared-memory layout
+    int nt;    // threads per CTA: blocks of the largest tile rounded up to a warp (<= k2_fused_threads)
 };
 int k2_fused_bpm(int h, int v, int nc);
-cudaError_t k2_launch_fused(int h, int v, int nc, const K2Params& P, int grid, cudaStream_t s);
+// persistent grid: min(tiles, SMs x resident CTAs)
+cudaError_t k2_launch_fused(int h, int v, int nc, const K2Params& P, int sm_count, cudaStream_t s);
 
 // ---- generic unfused path -------------------------------------------------------
 struct K2GParams {
