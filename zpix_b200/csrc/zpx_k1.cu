@@ -64,13 +64,10 @@ struct K1Start {
     int k;            // 0: at a block start; 1..63: inside a block, next zig-zag index k
     int dc0, dc1, dc2, dc3;  // DC predictors at that point
     uint32_t j0;      // ordinal (inside the interval) of the first block this lane writes
-    uint32_t count;   // blocks this lane writes
-    // SUB: after its last block the lane also decodes the next DC symbol, writing nothing, and reports the error
-    // if there is one.  The synchronisation pass steps over invalid codes bit by bit; when that happens at a block
-    // start, the block it finally finds may start in a later sub-sequence, and no lane would ever decode the
-    // invalid code itself.  The lane that owns the preceding block does, here (reference: BadHuffmanCode at the
-    // block that follows, decoder.zig:947-969).
-    bool probe;
+    uint32_t count;   // blocks this lane writes.  (SUB: the synchronisation pass steps over invalid codes bit by bit
+                      // and counts a block that fails to start as started: the lane that reaches it in the true
+                      // state decodes it here and reports the reference's error, BadHuffmanCode at the block that
+                      // follows, decoder.zig:947-969)
 };
 
 // Block-synchronous main loop: the 32 lanes of a warp decode their k-th block together --
@@ -129,7 +126,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     const ZpxImageDev* __restrict__ im = &P.imgs[sc->img];
 
     RingReader<RS> rd;
-    if (st.count != 0 || (SUB && st.probe)) rd.init(ring_col, P.ublob, iv.ustart, iv.ulen, st.bitpos);
+    if (st.count != 0) rd.init(ring_col, P.ublob, iv.ustart, iv.ulen, st.bitpos);
     else rd.init_idle(ring_col);
     Window<RS> win;
     win.load(rd);  // (top-ups never touch the ring words under the window: it stays valid from block to block)
@@ -160,7 +157,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     }
     // SUB: a lane that starts inside a block first runs that block's remaining AC symbols without storing
     // anything (phase: the one before block j0's)
-    bool tail = SUB && st.k != 0 && (st.count != 0 || st.probe);
+    bool tail = SUB && st.k != 0 && st.count != 0;
     const int c_first = c;
     if (tail) c = c == 0 ? nblk - 1 : c - 1;
     // bi: x = DC table (SMEM: shared address of its LUT; else table index), y = AC likewise,
@@ -172,9 +169,8 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     int dc0 = st.dc0, dc1 = st.dc1, dc2 = st.dc2, dc3 = st.dc3;
     uint32_t eob_run = 0;
     int wide = 0;  // >= 13: some coefficient of the lane lies outside [-4096, 4095]
-    const bool probe = SUB && st.probe;
-    const uint32_t total = st.count + (probe ? 1u : 0u);
-    uint32_t left = total;  // blocks still to decode (including the current one and the probe)
+    const uint32_t total = st.count;
+    uint32_t left = total;  // blocks still to decode (including the current one)
 
     // block flush (end of the loop body): this lane stores row (lane & 7) of the blocks of lanes 4 i + (lane >> 3)
     const uint32_t r16 = (uint32_t)(lane & 7) << 4;
@@ -213,14 +209,6 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
             else if (k == 1 && (bi.w & 0x20000u)) {
                 err = ZPX_E_UninitializedHuffmanTable;
                 k = 64;
-            }
-            if (SUB && probe && left == 1) {
-                // probe block: only the DC symbol counts, and only if it is an error (a valid one belongs to the
-                // next lane's block); nothing is stored
-                k = 64;
-                sts_u16(sb, 0);
-                if (err == ZPX_E_UninitializedHuffmanTable && !(bi.w & 0x10000u)) err = 0;
-                if (!err && !rd.overrun()) left = 0;
             }
         }
         // ---- AC (decoder.zig:1383-1411): one symbol per lane per vote ----
@@ -440,7 +428,6 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 ? (LPW <= 20 ? 4 : 3) 
     st.dc0 = st.dc1 = st.dc2 = st.dc3 = 0;
     st.j0 = 0;
     st.count = live ? iv.n_blocks : 0;
-    st.probe = false;
     k1_cta_run<LPW, WARPS, false>(P, iv, st);
 }
 
@@ -471,8 +458,6 @@ __global__ void __launch_bounds__(K1S_WWARPS * 32, 4) k1s_write(const K1SParams 
     st.dc3 = dc.w;
     st.j0 = excl;
     st.count = valid && next > excl ? next - excl : 0;
-    // probe the symbol after the lane's last block if the lane skipped an invalid code and a block follows
-    st.probe = valid && P.s_bad[t] != 0 && st.j0 + st.count < iv.n_blocks;
     k1_cta_run<32, K1S_WWARPS, true>(P.k1, iv, st);
 }
 

@@ -103,10 +103,9 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
     uint4 bi = SMEM ? lds_u128(sdesc + c * 16) : bpack[c];
     const uint32_t* __restrict__ fdc = SMEM ? nullptr : P.huff[bi.x].fast;
     const uint32_t* __restrict__ fac = SMEM ? nullptr : P.huff[bi.y].fast;
-    bool go = true, merged = false;
+    bool go = true, merged = false, skipping = false;
     int bad = 0;  // an invalid code was skipped (one bit further).  If this decode started in the true state, the
-                  // reference fails there; a skipped code at a block start is seen by no write-pass lane unless the
-                  // lane that owns the preceding block probes the symbol after it (k1s_write)
+                  // reference fails there (diagnostic only: see `skipping` below for how the write pass finds it)
     int it = 0;
     while (__any_sync(mask, go)) {
         if (it == K1_TOPUP) {  // uniform over the lanes in mask
@@ -165,6 +164,15 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
                     if ((int)(r >> 32) == ZPX_E_BadHuffmanCode) {
                         bad = 1;
                         e = 1u | 32u << 16;  // invalid: one bit further, same state (tot = 1, no value bits, adv = 0)
+                        // An invalid code where a block should start: the block that fails to start is counted (once
+                        // per run of skipped bits), so that the lane that reaches it in the true state decodes it in
+                        // the write pass -- and reports the reference's error there -- and every block found
+                        // further on gets a strictly larger ordinal: nothing decoded after the first error of the
+                        // reference's order can tie with it in the status key.
+                        if (k == 0 && !skipping) {
+                            skipping = true;
+                            n++;
+                        }
                     } else if (e >> 31) {
                         // EOB run: r more bits belong to the symbol
                         const uint32_t len = (e >> 8) & 0xffu, rr = (e >> 16) & 0xffu;
@@ -174,6 +182,7 @@ __device__ __forceinline__ unsigned long long sync_decode(const K1Params& P, con
                 const int len = fe_len(e), s32 = fe_s32(e);
                 int tot = fe_tot(e);
                 const int adv = fe_adv(e);
+                if (adv) skipping = false;  // a valid symbol
                 if (isdc && adv) {
                     const int v = fe_extend(hi << len, s32);
                     const int comp = rotate ? c : (int)(bi.z & 0xff);
