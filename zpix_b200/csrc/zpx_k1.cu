@@ -338,18 +338,24 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
         if (__any_sync(0xffffffffu, fy != 0)) {
             if (lane < LPW) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(siw + lane * 8), "r"(fx), "r"(fy) : "memory");
             __syncwarp();
+            // all records first, then all rows, then the stores: independent loads back to back instead of eight
+            // dependent load -> load -> store chains
+            uint32_t ix[LPW / 4], iy[LPW / 4];  // record of lane 4 i + (lane >> 3): x = address low, y = high | key << 16 | flags << 24
+#pragma unroll
+            for (int i = 0; i < LPW / 4; i++)
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ix[i]), "=r"(iy[i]) : "r"(sir + i * 32));
+            uint4 row[LPW / 4];
+            uint32_t ra[LPW / 4];
 #pragma unroll
             for (int i = 0; i < LPW / 4; i++) {
-                uint32_t ix, iy;  // record of lane 4 i + (lane >> 3): x = address low, y = high | key << 16 | flags << 24
-                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ix), "=r"(iy) : "r"(sir + i * 32));
-                if (iy >> 24) {
-                    const uint32_t a = sbr + i * (4 * K1_BLKB) + ((r16 ^ (iy >> 12)) & 0x70u);  // row (r ^ key) of that lane's block
-                    if (iy & (1u << 24)) {
-                        uint4* g = reinterpret_cast<uint4*>(((unsigned long long)(iy & 0xffffu) << 32 | ix) + r16);
-                        *g = lds_u128(a);
-                    }
-                    sts_zero16(a);
-                }
+                ra[i] = sbr + i * (4 * K1_BLKB) + ((r16 ^ (iy[i] >> 12)) & 0x70u);  // row (r ^ key) of that lane's block
+                row[i] = lds_u128(ra[i]);  // (a valid shared address whatever the record holds)
+            }
+#pragma unroll
+            for (int i = 0; i < LPW / 4; i++) {
+                if (iy[i] & (1u << 24))
+                    *reinterpret_cast<uint4*>(((unsigned long long)(iy[i] & 0xffffu) << 32 | ix[i]) + r16) = row[i];
+                if (iy[i] >> 24) sts_zero16(ra[i]);
             }
             __syncwarp();
         }
