@@ -247,3 +247,27 @@ def test_every_chroma_pair_through_the_fused_kernel(jpeg, ctx, name):
     assert np.array_equal(got, rgba)
     # and the planes really hold the intended values: spot check through the colour formula
     assert tuple(got[0, 0]) == tuple(O.ycbcr_to_rgba8_batch(np.array([[0, 0, 0]], np.uint8))[0])
+
+
+@pytest.mark.parametrize("name", sorted(SAMPLINGS))
+def test_every_sampling_interior_and_edge_tiles(jpeg, ctx, name):
+    """deterministic sweep (the hypothesis test above draws samplings at random): every sampling at a size whose tiles
+    all lie inside the image (the fused kernel's bounds-test-free path) and at sizes with partial MCUs on the right and
+    bottom edges, widths that are and are not multiples of four"""
+    rng = np.random.default_rng(hash(name) & 0xffff)
+    mode, comp_hv = SAMPLINGS[name]
+    for width, height in ((256, 64), (640, 32), (253, 61), (36, 130)):
+        mxx, myy = _geometry(width, height, comp_hv)
+        n = mxx * myy * sum(h * v for h, v in comp_hv)
+        blocks = _random_blocks(rng, n, "dense" if width == 256 else "sparse")
+        quant = rng.integers(1, 64, (len(comp_hv), 64))
+        planes, rgba = _expected(width, height, comp_hv, quant, mode, blocks)
+        got, nat, _ = _run(jpeg, ctx, width, height, comp_hv, quant, mode, blocks, False, mode in (MODE_GRAY, MODE_YCBCR))
+        assert np.array_equal(got, rgba), (name, width, height, np.argwhere(got != rgba)[:3])
+        if nat is not None:
+            ylen = planes[0].size
+            assert np.array_equal(nat[:ylen].reshape(planes[0].shape), planes[0]), (name, width, height)
+            if mode == MODE_YCBCR:
+                clen = planes[1].size
+                assert np.array_equal(nat[ylen:ylen + clen].reshape(planes[1].shape), planes[1])
+                assert np.array_equal(nat[ylen + clen:].reshape(planes[2].shape), planes[2])

@@ -737,3 +737,49 @@ def test_native_batch_one_call(jpeg, fixtures_dir):
             else:
                 assert np.array_equal(img.payload.pixels.reshape(-1), ref.pix.reshape(-1))
         c.close()
+
+
+def test_full_size_batches_every_image(jpeg):
+    """The BASELINE.json batches at FULL size, every output image checked (no sampling): cfg2 = 1024 distinct 1080p
+    4:2:0 files with DRI, each compared with the oracle on all host threads; cfg3 = 4096 x 512x512 (gray + 4:4:4, no
+    DRI) and cfg4 = 512 x 2160p 4:2:2 with and without DRI, built from 64 / 16 distinct files: the first copy of each
+    against the oracle, every other copy against that one on the GPU.  Size-independent check on top: the number of
+    pixels and the per-image status of every output."""
+    import ctypes as C
+    import bench
+
+    c = jpeg.Context([0])
+    # cfg2 through the one-call API into one pinned buffer
+    datas = S.make_batch(2, 1024, 1920, 1080, cache_dir=bench.CACHE, subsampling="4:2:0", restart_rows=1)
+    n, out_bytes = len(datas), 4 * 1920 * 1080
+    pinned = jpeg.lib.zpx_host_alloc(out_bytes * n)
+    assert pinned
+    try:
+        outs = (C.c_void_p * n)(*[pinned + i * out_bytes for i in range(n)])
+        keep = [np.frombuffer(d, np.uint8) for d in datas]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in keep])
+        lens = (C.c_size_t * n)(*[a.size for a in keep])
+        st = (C.c_int32 * n)()
+        assert jpeg.lib.zpx_decode_batch_rgba(c.handle, ptrs, lens, n, outs, None, st) == 0
+        assert not any(st)
+        par = bench.parity_host(datas, pinned, out_bytes, os.cpu_count() or 1)
+        assert par == {"images": 1024, "mismatch": 0, "against": par["against"]}
+    finally:
+        jpeg.lib.zpx_host_free(pinned)
+
+    def rep(base, k):
+        return [base[i % len(base)] for i in range(k)]
+
+    g = S.make_batch(3, 32, 512, 512, cache_dir=bench.CACHE, mode="L")
+    y = S.make_batch(3, 32, 512, 512, cache_dir=bench.CACHE, first=5000, mode="YCbCr", subsampling="4:4:4")
+    cfg3 = rep([x for pair in zip(g, y) for x in pair], 4096)
+    cfg4a = rep(S.make_batch(4, 16, 3840, 2160, cache_dir=bench.CACHE, mode="YCbCr", subsampling="4:2:2", restart_rows=1), 512)
+    cfg4b = rep(S.make_batch(4, 16, 3840, 2160, cache_dir=bench.CACHE, mode="YCbCr", subsampling="4:2:2"), 512)
+    for batch_data, distinct in ((cfg3, 64), (cfg4a, 16), (cfg4b, 16)):
+        with jpeg.Batch(c, batch_data) as b:
+            b.upload()
+            b.decode()
+            assert not any(b.status())
+            par = bench.parity_device(b, batch_data, distinct)
+        assert par["images"] == len(batch_data) and par["distinct"] == distinct and par["mismatch"] == 0, par
+    c.close()
