@@ -304,6 +304,72 @@ def test_damaged_progressive_streams_match_oracle(jpeg, ctx, fixtures_dir):
     _assert_same(jpeg, ctx, datas)
 
 
+def test_progressive_warp_per_scan_kernel(jpeg, fixtures_dir):
+    """Progressive frames take one lane per scan by default (zpx_k3l.cu); frames whose scan script is not an ordinary
+    successive approximation fall back to one warp per scan (zpx_k3.cu).  ZPX_OPT_PROGRESSIVE_MODE = 1 sends every
+    frame there: same fixtures, same damaged files, same oracle."""
+    c = jpeg.Context()
+    c.set_option(10, 1)
+    try:
+        datas = [_read(fixtures_dir, n) for n in PROGRESSIVE_FIXTURES]
+        _assert_same(jpeg, c, datas, PROGRESSIVE_FIXTURES)
+        datas = []
+        for name, seed in [("video-001.q50.420.progressive.jpeg", 1), ("video-005.gray.q50.progressive.jpeg", 2)]:
+            datas += _damaged(_read(fixtures_dir, name), seed, 12, 40)
+        datas += [S.encode(50012, 333, 211, subsampling="4:2:2", progressive=True, restart_rows=1),
+                  S.encode(50013, 97, 64, subsampling="4:2:0", progressive=True, restart_blocks=3)]
+        _assert_same(jpeg, c, datas)
+    finally:
+        c.close()
+
+
+def _scan_script_variants(data: bytes):
+    """Rewrites of the SOS headers of a progressive file that keep it decodable by the reference but leave the ordinary
+    successive-approximation order: a refinement pass turned into a second first pass of its band, a refinement that
+    repeats the previous Al, a first pass whose Al is raised."""
+    out = []
+    pos, sos = 2, []
+    while pos + 4 <= len(data):
+        assert data[pos] == 0xFF
+        m = data[pos + 1]
+        ln = int.from_bytes(data[pos + 2:pos + 4], "big")
+        if m == 0xDA:
+            sos.append(pos)
+            nxt = pos + 2 + ln
+            while not (data[nxt] == 0xFF and data[nxt + 1] not in (0, 0xD0, 0xD1, 0xD2, 0xD3, 0xD4, 0xD5, 0xD6, 0xD7)):
+                nxt += 1
+            pos = nxt
+            continue
+        if m == 0xD9:
+            break
+        pos += 2 + ln
+    for p in sos:
+        ln = int.from_bytes(data[p + 2:p + 4], "big")
+        q = p + 2 + ln - 1  # the Ah/Al byte
+        ah, al = data[q] >> 4, data[q] & 15
+        ss = data[q - 2]
+        for nah, nal in ((0, al), (al + 2, al + 1), (0, al + 1), (ah, al)):
+            if (nah, nal) == (ah, al) or (nah != 0 and nah != nal + 1) or nal > 13:
+                continue
+            d = bytearray(data)
+            d[q] = nah << 4 | nal
+            out.append((bytes(d), f"sos@{p} ss={ss} ah/al {ah}/{al} -> {nah}/{nal}"))
+    return out
+
+
+def test_unusual_scan_scripts(jpeg, ctx, fixtures_dir):
+    """Progressive files whose scan scripts are legal for the reference's parser but not an ordinary successive
+    approximation (repeated first passes, refinements that do not lower Al): the lane-per-scan kernels must hand
+    them to the kernel that works on the coefficients themselves; results as the oracle's either way."""
+    datas, names = [], []
+    for name in ["video-001.q50.420.progressive.jpeg", "video-005.gray.q50.progressive.jpeg"]:
+        for d, tag in _scan_script_variants(_read(fixtures_dir, name)):
+            datas.append(d)
+            names.append(f"{name} {tag}")
+    assert len(datas) > 20
+    _assert_same(jpeg, ctx, datas, names)
+
+
 def test_header_fuzz_decodes_like_oracle(jpeg, ctx, fixtures_dir):
     """Seeded damage in the marker segments: odd-but-legal sampling factors, table assignments, scan scripts,
     restart intervals ... must decode to the oracle's pixels, everything else must fail with its error."""

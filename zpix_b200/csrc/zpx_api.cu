@@ -142,7 +142,12 @@ struct DevicePlan {
     std::vector<ZpxQuantDev> quant;
     std::vector<FusedGroup> groups;
     std::vector<ZpxIntervalDev> ivs_prog;            // intervals of progressive scans (appended after the sequential ones)
-    std::vector<std::vector<uint32_t>> prog_lists;   // per dependency level: indices (into the final interval array)
+    // progressive scans: work lists of interval indices (into the final interval array), launched in order.
+    // List 3 * level + kind; kind 0: one warp per interval (zpx_k3.cu), 1: one lane per interval, grouped by pass type
+    // and padded with ~0 (k3l_level), 2: DC refinement passes (k3l_dc_refine)
+    std::vector<std::vector<uint32_t>> prog_lists;
+    struct AcRefine { uint32_t first = 0, count = 0, max_blocks = 0; };  // the AC refinement group inside list 3 * level + 1
+    std::vector<AcRefine> prog_acr;                                      // per level
     std::vector<size_t> prog_off;                    // byte offsets of those lists in the descriptor buffer
     std::vector<std::pair<uint64_t, uint64_t>> prog_zero;  // (first block, blocks) of progressive images: zeroed before the scans
     size_t n_seq = 0;                                // sequential intervals = ivs[0, n_seq)
@@ -179,7 +184,7 @@ struct zpx_ctx {
     std::string last_cuda_str;
     std::atomic<uint64_t> launches{0};
     int64_t opt_entropy_mode = 0, opt_force_generic = 0, opt_subseq = 0, opt_pipeline_chunk = 0;
-    int64_t opt_pipeline_ramp = 1, opt_pipeline_workers = 3, opt_test_wide = 0, opt_native = 0;
+    int64_t opt_pipeline_ramp = 1, opt_pipeline_workers = 3, opt_test_wide = 0, opt_native = 0, opt_progressive_mode = 0;
     bool busy = false;
     const zpx_batch* resident = nullptr;  // the batch whose data currently occupies the device buffers
     std::vector<zpx_ctx*> shadows;  // further sets of device buffers/streams for the chunk pipeline of zpx_decode_batch_rgba
@@ -268,6 +273,27 @@ struct TableDedup {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Can the lane-per-interval progressive kernels (zpx_k3l.cu) decode this frame?  They never read a coefficient back:
+// an AC refinement pass learns which coefficients are non-zero (and their signs) from per-block bit maps and applies a
+// correction bit as a blind add of +-2^Al.  That is exact when the scan script is an ordinary successive
+// approximation: every band position of a component is coded by at most one first pass, before any refinement of it,
+// and refined with strictly falling Al (the bit being added is clear, the magnitude stays below 2^15).  Anything else
+// (only hand-made or damaged files) takes the warp-per-interval kernel, which works on the coefficients themselves.
+bool lane_script_ok(const ZpxParsed& p) {
+    int8_t gran[ZPX_MAX_COMP][64];  // lowest bit position coded so far; 127: untouched
+    memset(gran, 127, sizeof(gran));
+    for (const ZpxScanHost& s : p.scans) {
+        if (s.al > 13) return false;
+        if (s.ss == 0) continue;  // DC passes: a store or an OR
+        const int c = s.comp[0];
+        for (int z = s.ss; z <= s.se; z++) {
+            if (s.ah == 0 ? gran[c][z] != 127 : (gran[c][z] != 127 && s.al >= gran[c][z])) return false;
+            gran[c][z] = (int8_t)s.al;
+        }
+    }
+    return true;
+}
+
 // Build everything one device needs for its share of the batch.
 void build_plan(zpx_batch* b, int di) {
     DevicePlan& pl = b->plans[di];
@@ -275,6 +301,7 @@ void build_plan(zpx_batch* b, int di) {
     const bool force_generic = b->ctx->opt_force_generic != 0;
     pl.native = (int)b->ctx->opt_native;
     std::map<int, int> group_ix;  // (h<<8|v<<4|nc) -> index
+    std::vector<std::vector<uint32_t>> lane_groups;  // progressive, lane per interval: [3 * level + pass type]
     for (size_t k = 0; k < pl.images.size(); k++) {
         const int bi = pl.images[k];
         const ZpxParsed& p = b->parsed[bi];
@@ -329,6 +356,8 @@ void build_plan(zpx_batch* b, int di) {
             cb += (uint64_t)im.comp_bw[c] * im.comp_bh[c];
         }
         pl.coef_blocks += nblocks;
+        bool lanep = false;       // progressive frame on the lane-per-interval kernels (zpx_k3l.cu), decided below
+        uint64_t map_blocks = 0;  // its non-zero / sign maps, zeroed together with the coefficients
         // quantisers: sequential frames use the tables in force at the component's SOS,
         // progressive frames those at EOI
         for (int c = 0; c < p.ncomp; c++) {
@@ -443,6 +472,41 @@ void build_plan(zpx_batch* b, int di) {
                 }
             }
         }
+        // Progressive frames with an ordinary scan script take the lane-per-interval kernels.  Their scratch lives
+        // right after the coefficients: 16 bytes of non-zero / sign maps per block; per AC refinement scan one 32-bit
+        // stream position per coded block (+ one progress counter per interval); per coded block of the AC refinement
+        // scans of one level an 80-byte list of zero positions (levels reuse the space).
+        std::vector<uint32_t> pos_off(p.scans.size(), 0), zl_off(p.scans.size(), 0);
+        auto coded_w = [&](int c) { return std::min(im.comp_bw[c], (p.width + 7) / 8); };
+        auto coded_h = [&](int c) { return std::min(im.comp_bh[c], (p.height + 7) / 8); };
+        if (p.progressive && b->ctx->opt_progressive_mode == 0 && lane_script_ok(p)) {
+            uint64_t pos_entries = 0, zl_max = 0;
+            std::vector<uint64_t> zl_level;
+            bool fits = true;
+            for (size_t a = 0; a < p.scans.size(); a++) {
+                const ZpxScanHost& s = p.scans[a];
+                for (const ZpxIntervalHost& iv : s.intervals) fits = fits && iv.limit - iv.start < (1u << 27);  // bit positions in 31 bits
+                if (s.ss == 0 || s.ah == 0) continue;
+                const uint64_t coded = (uint64_t)coded_w(s.comp[0]) * coded_h(s.comp[0]);
+                pos_off[a] = (uint32_t)pos_entries;
+                pos_entries += coded + s.intervals.size();
+                if (zl_level.size() <= (size_t)level[a]) zl_level.resize(level[a] + 1, 0);
+                zl_off[a] = (uint32_t)zl_level[level[a]];
+                zl_level[level[a]] += coded;
+                zl_max = std::max(zl_max, zl_level[level[a]]);
+            }
+            const uint64_t pos_blocks = (pos_entries * 4 + 127) / 128, zl_blocks = (zl_max * 80 + 127) / 128;
+            // (zpx_batch_open budgets 128 bytes of scratch per block; scripts that refine many bands side by side
+            // go to the warp-per-interval kernel)
+            if (fits && pos_blocks + zl_blocks <= nblocks + 16 && pos_entries < (1ull << 31)) {
+                lanep = true;
+                map_blocks = (nblocks + 7) / 8;
+                im.pmask_base = pl.coef_blocks;
+                im.ppos_base = im.pmask_base + map_blocks;
+                im.pzl_base = im.ppos_base + pos_blocks;
+                pl.coef_blocks += map_blocks + pos_blocks + zl_blocks;
+            }
+        }
         int scan_index = 0;
         for (const ZpxScanHost& s : p.scans) {
             ZpxScanDev sd;
@@ -456,6 +520,8 @@ void build_plan(zpx_batch* b, int di) {
             sd.al = s.al;
             sd.total_mcu = p.mxx * p.myy;
             sd.restart_interval = s.restart_interval;
+            sd.pos_off = pos_off[scan_index];
+            sd.zl_off = zl_off[scan_index];
             sd.scan_index = scan_index++;
             // A sequential frame may code a component in more than one scan (only broken files do): the reference
             // reconstructs every scan as it comes, so the last one wins.  Here all scans of an image decode side by
@@ -494,8 +560,8 @@ void build_plan(zpx_batch* b, int di) {
             }
             if (s.ncomp == 1) {
                 const int c = s.comp[0];
-                sd.cw = std::min(im.comp_bw[c], (p.width + 7) / 8);
-                sd.ch = std::min(im.comp_bh[c], (p.height + 7) / 8);
+                sd.cw = coded_w(c);
+                sd.ch = coded_h(c);
             }
             // An AC table that holds a symbol (r, 0) with 0 < r < 15 can start an End-Of-Band run inside a
             // sequential scan; the self-synchronising decoder does not model that state, so such
@@ -546,7 +612,7 @@ void build_plan(zpx_batch* b, int di) {
                 d.sub_first = d.nsub = d.sub_bytes = 0;
                 d.ulen = 0;
                 d.ustart = 0;
-                if (!p.progressive) {
+                if (!p.progressive || lanep) {
                     // the interval's place in the unstuffed blob and the pieces k0_unstuff works on
                     d.ulen = d.len - iv.n_stuffed;
                     d.ustart = pl.ublob_bytes;
@@ -560,28 +626,52 @@ void build_plan(zpx_batch* b, int di) {
                         sgd.flags = q + 1 == iv.n_segs ? 1u : 0u;
                         pl.segs.push_back(sgd);
                     }
-                    pl.iv_lane_only.push_back(eob_capable ? 1 : 0);
+                    if (!p.progressive) pl.iv_lane_only.push_back(eob_capable ? 1 : 0);
                 }
                 if (p.progressive) {
                     const size_t lv = (size_t)level[sd.scan_index];
-                    if (pl.prog_lists.size() <= lv) pl.prog_lists.resize(lv + 1);
-                    pl.prog_lists[lv].push_back((uint32_t)pl.ivs_prog.size());  // fixed up below
+                    if (pl.prog_lists.size() < 3 * (lv + 1)) pl.prog_lists.resize(3 * (lv + 1));
+                    if (lane_groups.size() < 3 * (lv + 1)) lane_groups.resize(3 * (lv + 1));
+                    const uint32_t self = (uint32_t)pl.ivs_prog.size();  // (indices are fixed up below)
+                    if (!lanep) pl.prog_lists[3 * lv].push_back(self);
+                    else if (s.ss == 0 && s.ah != 0) pl.prog_lists[3 * lv + 2].push_back(self);
+                    else lane_groups[3 * lv + (s.ss == 0 ? 0 : s.ah == 0 ? 1 : 2)].push_back(self);
                     pl.ivs_prog.push_back(d);
                 } else {
                     pl.ivs.push_back(d);
                 }
             }
         }
-        if (p.progressive) pl.prog_zero.push_back({im.coef_base, nblocks});
+        if (p.progressive) pl.prog_zero.push_back({im.coef_base, nblocks + map_blocks});
         pl.imgs.push_back(im);
     }
     // progressive intervals go after the sequential ones
     pl.n_seq = pl.ivs.size();
     // longest scans first: a launch is as long as its slowest warp, so the big ones must not start last
+    auto by_len = [&](uint32_t a, uint32_t b) { return pl.ivs_prog[a].len > pl.ivs_prog[b].len; };
+    for (auto& l : pl.prog_lists) std::stable_sort(l.begin(), l.end(), by_len);
+    // lane-per-interval lists: the level's DC-first, AC-first and AC-refinement intervals, each group sorted the same
+    // way (the 32 lanes of a warp then finish together) and padded to whole warps
+    for (size_t g = 0; g < lane_groups.size(); g++) {
+        std::vector<uint32_t>& l = lane_groups[g];
+        if (l.empty()) continue;
+        std::stable_sort(l.begin(), l.end(), by_len);
+        l.resize(align_up(l.size(), 32), 0xffffffffu);
+        std::vector<uint32_t>& dst = pl.prog_lists[g / 3 * 3 + 1];
+        if (g % 3 == 2) {
+            if (pl.prog_acr.size() <= g / 3) pl.prog_acr.resize(g / 3 + 1);
+            DevicePlan::AcRefine& a = pl.prog_acr[g / 3];
+            a.first = (uint32_t)dst.size();
+            a.count = (uint32_t)l.size();
+            for (uint32_t ix : l)
+                if (ix != 0xffffffffu) a.max_blocks = std::max(a.max_blocks, pl.ivs_prog[ix].n_blocks);
+        }
+        dst.insert(dst.end(), l.begin(), l.end());
+    }
+    pl.prog_acr.resize(pl.prog_lists.size() / 3);
     for (auto& l : pl.prog_lists)
-        std::stable_sort(l.begin(), l.end(), [&](uint32_t a, uint32_t b) { return pl.ivs_prog[a].len > pl.ivs_prog[b].len; });
-    for (auto& l : pl.prog_lists)
-        for (uint32_t& ix : l) ix += (uint32_t)pl.n_seq;
+        for (uint32_t& ix : l)
+            if (ix != 0xffffffffu) ix += (uint32_t)pl.n_seq;
     pl.ivs.insert(pl.ivs.end(), pl.ivs_prog.begin(), pl.ivs_prog.end());
     // entropy mode: with enough restart intervals to fill the GPU, one lane per interval decodes each
     // once, serially; otherwise the self-synchronising decoder parallelises inside the intervals
@@ -744,12 +834,30 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         CU(ctx, k1s_launch_write(ks, st));
         k1_launches += 2;
     }
-    // ---- K3: progressive frames, one launch per scan ordinal over zeroed coefficient grids ----
+    // ---- K3: progressive frames, launches by dependency level over zeroed coefficient grids (and bit maps) ----
     for (const auto& z : pl.prog_zero)
         CU(ctx, cudaMemsetAsync((uint8_t*)dc.coef.p + z.first * 128, 0, z.second * 128, st));
     for (size_t k = 0; k < pl.prog_lists.size(); k++) {
         if (pl.prog_lists[k].empty()) continue;
-        CU(ctx, k3_launch_progressive(k1, (const uint32_t*)(desc + pl.prog_off[k]), (int)pl.prog_lists[k].size(), st));
+        const uint32_t* list = (const uint32_t*)(desc + pl.prog_off[k]);
+        const int nl = (int)pl.prog_lists[k].size();
+        if (k % 3 == 0) {
+            CU(ctx, k3_launch_progressive(k1, list, nl, st));
+        } else if (k % 3 == 1) {
+            // AC refinement passes: zero-position lists first, the writes after the serial part
+            const DevicePlan::AcRefine& a = pl.prog_acr[k / 3];
+            if (a.count) {
+                CU(ctx, k3l_launch_refine_prep(k1, list + a.first, (int)a.count, a.max_blocks, st));
+                k1_launches++;
+            }
+            CU(ctx, k3l_launch_level(k1, list, nl, st));
+            if (a.count) {
+                CU(ctx, k3l_launch_refine_apply(k1, list + a.first, (int)a.count, a.max_blocks, st));
+                k1_launches++;
+            }
+        } else {
+            CU(ctx, k3l_launch_dc_refine(k1, list, nl, st));
+        }
         k1_launches++;
     }
     CU(ctx, cudaEventRecord(dc.ev[1], st));
@@ -1032,6 +1140,7 @@ int32_t zpx_ctx_set_option(zpx_ctx* c, int32_t option, int64_t value) {
         case ZPX_OPT_PIPELINE_CHUNK: c->opt_pipeline_chunk = value; return ZPX_OK;
         case ZPX_OPT_PIPELINE_RAMP: c->opt_pipeline_ramp = value; return ZPX_OK;
         case ZPX_OPT_TEST_WIDE: c->opt_test_wide = value; return ZPX_OK;
+        case ZPX_OPT_PROGRESSIVE_MODE: c->opt_progressive_mode = value; return ZPX_OK;
         case ZPX_OPT_NATIVE_PLANES:
             if (value < 0 || value > 2) return ZPX_E_INVALID_ARG;
             c->opt_native = value;
@@ -1087,7 +1196,8 @@ int32_t zpx_batch_open(zpx_ctx* ctx, const uint8_t* const* bufs, const size_t* l
             uint64_t bpm = 0;
             for (int c = 0; c < p.ncomp; c++) bpm += (uint64_t)p.h[c] * p.v[c];
             const uint64_t blocks = (uint64_t)p.mxx * p.myy * bpm;
-            need_of[i] = blocks * (128 + 64) + (uint64_t)4 * p.width * p.height;  // coefficients + planes + RGBA
+            // coefficients (+ a progressive frame's bit maps and scratch) + planes + RGBA
+            need_of[i] = blocks * (128 + 64 + (p.progressive ? 16 + 128 : 0)) + (p.progressive ? 8192 : 0) + (uint64_t)4 * p.width * p.height;
             if (need_of[i] > image_budget) p.status = ZPX_E_OutOfMemory;
         }
     });
@@ -1636,6 +1746,7 @@ static int32_t decode_batch_pipelined(zpx_ctx* ctx, const uint8_t* const* bufs, 
         sh->opt_force_generic = ctx->opt_force_generic;
         sh->opt_subseq = ctx->opt_subseq;
         sh->opt_native = ctx->opt_native;
+        sh->opt_progressive_mode = ctx->opt_progressive_mode;
     }
     // chunk list: the first two chunks are a quarter and a half of the regular size, so that the first
     // device->host copy starts early (the pipeline is bound by that copy; its fill time is pure loss)

@@ -72,6 +72,12 @@ struct ZpxImageDev {
     int32_t qidx[4];          // index into the quant table array, per component
     uint32_t blk_off[4];      // interleaved: index of the component's first block inside an MCU
     uint64_t coef_base;       // first block of the image in the coefficient buffer (block units)
+    uint64_t pmask_base;      // progressive frames on the lane-per-interval kernels (zpx_k3l.cu): where the per-block
+                              // non-zero / sign maps start in the coefficient buffer (block units; 16 bytes per block,
+                              // indexed like the coefficient blocks relative to coef_base); else 0
+    uint64_t ppos_base;       // the same frames: block start positions found by the serial part of the AC refinement
+                              // passes (32-bit entries, ZpxScanDev::pos_off) ...
+    uint64_t pzl_base;        // ... and the zero-position lists they read (80-byte records, ZpxScanDev::zl_off)
     uint64_t comp_base[4];    // planar: first block of each component's grid (block units, absolute)
     int32_t comp_bw[4];       // planar: grid width in blocks = mxx*h
     int32_t comp_bh[4];       //         grid height in blocks = myy*v
@@ -102,7 +108,9 @@ struct ZpxScanDev {
     // parsing does not depend on the block phase, so the self-synchronising decoder leaves it out of
     // its state and attributes DC sums by phase relative to the sub-sequence start (zpx_k1s.cu)
     int32_t rotate;
-    int32_t pad1[3];
+    uint32_t pos_off, zl_off;  // AC refinement scans on the lane-per-interval kernels: the scan's first entry / record
+                               // in the image's position and list areas (ZpxImageDev::ppos_base, pzl_base)
+    int32_t pad1;
     // per block inside one MCU of this scan
     uint8_t blk_comp[ZPX_MAX_BLK_PER_MCU]; // frame component index
     uint8_t blk_hx[ZPX_MAX_BLK_PER_MCU];
@@ -205,7 +213,7 @@ struct ZpxScanHost {
     ZpxHuffHost dc[ZPX_MAX_COMP], ac[ZPX_MAX_COMP];  // snapshot of the tables this scan uses
     int32_t quant[ZPX_MAX_COMP][64];                 // snapshot of quant[tq] (zig-zag order) per scan component
     std::vector<ZpxIntervalHost> intervals;
-    std::vector<ZpxSegHost> segs;  // sequential scans only
+    std::vector<ZpxSegHost> segs;
     // error the reference raises after `err_after_interval` intervals decoded fine (findRst / EOF)
     int pending_err = 0;
     int err_after_interval = -1;

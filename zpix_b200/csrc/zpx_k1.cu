@@ -82,29 +82,7 @@ struct K1Start {
 // three ring words in registers -- the word under the bit position and the two after it -- so the 32 bits of a
 // step come from one funnel shift; when a step crosses a word boundary the registers move up and the third is
 // reloaded from the ring, a load nothing waits for until the step after the next.
-template <int RS>
-struct Window {
-    uint32_t w0, w1, w2;
-    uint32_t a2;  // shared address of w2's ring word
-    __device__ __forceinline__ void load(const RingReader<RS>& rd) {
-        w0 = lds_u32(rd.word_addr(0));
-        w1 = lds_u32(rd.word_addr(1));
-        a2 = rd.word_addr(2);
-        w2 = lds_u32(a2);
-    }
-    __device__ __forceinline__ uint32_t peek(uint32_t bitpos) const { return __funnelshift_l(w1, w0, bitpos); }
-    // the position moves from `from` by tot <= 32 bits.  Branch-free: m is all ones when it enters the next word
-    // (then the registers move up and w2 is the next ring word; otherwise w2 is simply read again)
-    __device__ __forceinline__ void advance(const RingReader<RS>& rd, uint32_t from, uint32_t tot) {
-        const uint32_t t = (from & 31u) + tot;
-        const uint32_t m = (uint32_t)((int)(t << 26) >> 31);
-        w0 = (w1 & m) | (w0 & ~m);
-        w1 = (w2 & m) | (w1 & ~m);
-        a2 += m & (uint32_t)RS;
-        if (a2 == rd.ring + K1_RW * RS) a2 = rd.ring;
-        w2 = lds_u32(a2);
-    }
-};
+// (Window<RS>: zpx_k1_common.cuh)
 
 // what a lane that idles (its block is complete) or takes the rare path sees in the common code of a step:
 // no bits, no value, no advance

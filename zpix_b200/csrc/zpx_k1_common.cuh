@@ -81,8 +81,8 @@ __device__ __forceinline__ int fe_extend(uint32_t t, int s32) {
 // ---------------------------------------------------------------------------
 // reader
 // ---------------------------------------------------------------------------
-template <int RS>  // bytes between consecutive ring words of one lane = 4 * (lanes with a stream per CTA)
-struct RingReader {
+template <int RS, int RW = K1_RW>  // RS: bytes between consecutive ring words of one lane = 4 * (lanes with a stream
+struct RingReader {                //     per CTA); RW: ring words per lane
     uint32_t ring;       // shared address of this lane's column: word slot s at ring + s * RS
     const uint8_t* src;  // first byte of the interval in the unstuffed blob (16-byte aligned)
     uint32_t bitpos;     // next unread bit, from src
@@ -98,8 +98,8 @@ struct RingReader {
     }
     // chunks can be added as long as the one that holds the read position stays in the ring
     __device__ __forceinline__ void topup() {
-        while (wbyte - ((bitpos >> 7) << 4) <= (uint32_t)(4 * K1_RW - 16)) {
-            const uint32_t a = ring + ((wbyte >> 2) & (uint32_t)(K1_RW - 1)) * (uint32_t)RS;
+        while (wbyte - ((bitpos >> 7) << 4) <= (uint32_t)(4 * RW - 16)) {
+            const uint32_t a = ring + ((wbyte >> 2) & (uint32_t)(RW - 1)) * (uint32_t)RS;
             sts_u32(a, __byte_perm(nxt.x, 0, 0x0123));
             sts_u32(a + RS, __byte_perm(nxt.y, 0, 0x0123));
             sts_u32(a + 2 * RS, __byte_perm(nxt.z, 0, 0x0123));
@@ -123,18 +123,46 @@ struct RingReader {
         ring = ring_col;
         src = nullptr;
         endbits = lim16 = bitpos = 0;
-        wbyte = 4 * K1_RW;
+        wbyte = 4 * RW;
         nxt = make_uint4(0u, 0u, 0u, 0u);
     }
     // shared address of ring word (bitpos >> 5) + d
     __device__ __forceinline__ uint32_t word_addr(uint32_t d) const {
-        return ring + (((bitpos >> 5) + d) & (uint32_t)(K1_RW - 1)) * (uint32_t)RS;
+        return ring + (((bitpos >> 5) + d) & (uint32_t)(RW - 1)) * (uint32_t)RS;
     }
     // the next 32 bits
     __device__ __forceinline__ uint32_t peek() const {
         return __funnelshift_l(lds_u32(word_addr(1)), lds_u32(word_addr(0)), bitpos);
     }
     __device__ __forceinline__ bool overrun() const { return bitpos > endbits; }
+};
+
+// The stream window of the write kernels (zpx_k1.cu, zpx_k3l.cu): three ring words in registers -- the word under the
+// bit position and the two after it -- so the 32 bits of a step come from one funnel shift; when a step crosses a
+// word boundary the registers move up and the third is reloaded from the ring, a load nothing waits for until the
+// step after the next.
+template <int RS>
+struct Window {
+    uint32_t w0, w1, w2;
+    uint32_t a2;  // shared address of w2's ring word
+    __device__ __forceinline__ void load(const RingReader<RS>& rd) {
+        w0 = lds_u32(rd.word_addr(0));
+        w1 = lds_u32(rd.word_addr(1));
+        a2 = rd.word_addr(2);
+        w2 = lds_u32(a2);
+    }
+    __device__ __forceinline__ uint32_t peek(uint32_t bitpos) const { return __funnelshift_l(w1, w0, bitpos); }
+    // the position moves from `from` by tot <= 32 bits.  Branch-free: m is all ones when it enters the next word
+    // (then the registers move up and w2 is the next ring word; otherwise w2 is simply read again)
+    __device__ __forceinline__ void advance(const RingReader<RS>& rd, uint32_t from, uint32_t tot) {
+        const uint32_t t = (from & 31u) + tot;
+        const uint32_t m = (uint32_t)((int)(t << 26) >> 31);
+        w0 = (w1 & m) | (w0 & ~m);
+        w1 = (w2 & m) | (w1 & ~m);
+        a2 += m & (uint32_t)RS;
+        if (a2 == rd.ring + K1_RW * RS) a2 = rd.ring;
+        w2 = lds_u32(a2);
+    }
 };
 
 // ---------------------------------------------------------------------------

@@ -12,8 +12,9 @@ struct K1Params {
     const uint8_t* blob;          // entropy-coded bytes of the whole device batch, still byte-stuffed (progressive scans
                                   // read it directly, zpx_k3.cu)
     int dbg;                      // experiments only (ZPX_K1_DBG): bit 0 = skip the coefficient stores
-    const uint8_t* ublob;         // sequential scans: the same bytes with the stuffing removed (k0_unstuff), one
-                                  // 16-byte aligned run per restart interval (ZpxIntervalDev::ustart / ulen)
+    const uint8_t* ublob;         // the same bytes with the stuffing removed (k0_unstuff), one 16-byte aligned run per
+                                  // restart interval (ZpxIntervalDev::ustart / ulen): sequential scans and the
+                                  // progressive ones of zpx_k3l.cu
     const ZpxIntervalDev* ivs;
     int n_iv;
     const ZpxScanDev* scans;
@@ -50,6 +51,15 @@ cudaError_t k1s_launch_write(const K1SParams& P, cudaStream_t s);
 
 // progressive scans (zpx_k3.cu): one lane per listed interval, read-modify-write of the coefficient grids
 cudaError_t k3_launch_progressive(const K1Params& P, const uint32_t* list, int n_list, cudaStream_t s);
+// progressive scans of frames with an ordinary successive-approximation script (zpx_k3l.cu): one LANE per listed
+// interval.  list = the level's intervals grouped by pass type (DC first / AC first / AC refinement), each group
+// padded to a multiple of 32 with 0xffffffff; DC refinement passes have a kernel of their own (one warp per interval)
+cudaError_t k3l_launch_level(const K1Params& P, const uint32_t* list, int n_padded, cudaStream_t s);
+cudaError_t k3l_launch_dc_refine(const K1Params& P, const uint32_t* list, int n_list, cudaStream_t s);
+// AC refinement passes: before k3l_launch_level, the zero-position lists of every block; after it, the writes.  list =
+// the level's AC refinement intervals, max_blocks = the most coded blocks any of them has
+cudaError_t k3l_launch_refine_prep(const K1Params& P, const uint32_t* list, int n_list, uint32_t max_blocks, cudaStream_t s);
+cudaError_t k3l_launch_refine_apply(const K1Params& P, const uint32_t* list, int n_list, uint32_t max_blocks, cudaStream_t s);
 
 // ---- K2: fused dequant + IDCT + upsample + colour ------------------------------
 // Threads per CTA of the fused kernel (= blocks a tile can hold) for a sampling; 512 / threads CTAs are resident

@@ -368,7 +368,7 @@ struct Parser {
             ZpxIntervalHost iv;
             iv.start = p;
             iv.seg_first = (uint32_t)sc.segs.size();
-            iv.limit = find_limit(p, &iv.eof_limit, &iv.n_stuffed, o.progressive ? nullptr : &sc.segs);
+            iv.limit = find_limit(p, &iv.eof_limit, &iv.n_stuffed, &sc.segs);
             iv.n_segs = (uint32_t)sc.segs.size() - iv.seg_first;
             iv.first_mcu = ri > 0 ? k * ri : 0;
             iv.n_mcu = ri > 0 ? (total_mcu - iv.first_mcu < ri ? total_mcu - iv.first_mcu : ri) : total_mcu;
