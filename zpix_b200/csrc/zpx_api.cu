@@ -146,8 +146,8 @@ struct DevicePlan {
     // List 3 * level + kind; kind 0: one warp per interval (zpx_k3.cu), 1: one lane per interval, grouped by pass type
     // and padded with ~0 (k3l_level), 2: DC refinement passes (k3l_dc_refine)
     std::vector<std::vector<uint32_t>> prog_lists;
-    struct AcRefine { uint32_t first = 0, count = 0, max_blocks = 0; };  // the AC refinement group inside list 3 * level + 1
-    std::vector<AcRefine> prog_acr;                                      // per level
+    struct LaneGroup { uint32_t first = 0, count = 0, max_blocks = 0; };  // a pass type's group inside list 3 * level + 1
+    std::vector<LaneGroup> prog_grp;                                      // [3 * level + pass type]
     std::vector<size_t> prog_off;                    // byte offsets of those lists in the descriptor buffer
     std::vector<std::pair<uint64_t, uint64_t>> prog_zero;  // (first block, blocks) of progressive images: zeroed before the scans
     size_t n_seq = 0;                                // sequential intervals = ivs[0, n_seq)
@@ -357,7 +357,8 @@ void build_plan(zpx_batch* b, int di) {
         }
         pl.coef_blocks += nblocks;
         bool lanep = false;       // progressive frame on the lane-per-interval kernels (zpx_k3l.cu), decided below
-        uint64_t map_blocks = 0;  // its non-zero / sign maps, zeroed together with the coefficients
+        uint64_t map_blocks = 0, zero_pos_blocks = 0;  // its non-zero / sign maps and block positions, zeroed together
+                                                       // with the coefficients
         // quantisers: sequential frames use the tables in force at the component's SOS,
         // progressive frames those at EOI
         for (int c = 0; c < p.ncomp; c++) {
@@ -473,9 +474,9 @@ void build_plan(zpx_batch* b, int di) {
             }
         }
         // Progressive frames with an ordinary scan script take the lane-per-interval kernels.  Their scratch lives
-        // right after the coefficients: 16 bytes of non-zero / sign maps per block; per AC refinement scan one 32-bit
-        // stream position per coded block (+ one progress counter per interval); per coded block of the AC refinement
-        // scans of one level an 80-byte list of zero positions (levels reuse the space).
+        // right after the coefficients: 16 bytes of non-zero / sign maps per block; per AC scan one 32-bit stream
+        // position per coded block (+ one progress counter per interval); per coded block of the AC refinement scans
+        // of one level a 64-byte list of zero positions (levels reuse the space).
         std::vector<uint32_t> pos_off(p.scans.size(), 0), zl_off(p.scans.size(), 0);
         auto coded_w = [&](int c) { return std::min(im.comp_bw[c], (p.width + 7) / 8); };
         auto coded_h = [&](int c) { return std::min(im.comp_bh[c], (p.height + 7) / 8); };
@@ -486,20 +487,22 @@ void build_plan(zpx_batch* b, int di) {
             for (size_t a = 0; a < p.scans.size(); a++) {
                 const ZpxScanHost& s = p.scans[a];
                 for (const ZpxIntervalHost& iv : s.intervals) fits = fits && iv.limit - iv.start < (1u << 27);  // bit positions in 31 bits
-                if (s.ss == 0 || s.ah == 0) continue;
+                if (s.ss == 0) continue;
                 const uint64_t coded = (uint64_t)coded_w(s.comp[0]) * coded_h(s.comp[0]);
                 pos_off[a] = (uint32_t)pos_entries;
                 pos_entries += coded + s.intervals.size();
+                if (s.ah == 0) continue;
                 if (zl_level.size() <= (size_t)level[a]) zl_level.resize(level[a] + 1, 0);
                 zl_off[a] = (uint32_t)zl_level[level[a]];
                 zl_level[level[a]] += coded;
                 zl_max = std::max(zl_max, zl_level[level[a]]);
             }
-            const uint64_t pos_blocks = (pos_entries * 4 + 127) / 128, zl_blocks = (zl_max * 80 + 127) / 128;
+            const uint64_t pos_blocks = (pos_entries * 4 + 127) / 128, zl_blocks = (zl_max * 64 + 127) / 128;
             // (zpx_batch_open budgets 128 bytes of scratch per block; scripts that refine many bands side by side
             // go to the warp-per-interval kernel)
             if (fits && pos_blocks + zl_blocks <= nblocks + 16 && pos_entries < (1ull << 31)) {
                 lanep = true;
+                zero_pos_blocks = pos_blocks;  // (a first pass leaves the entries of blocks without bits at zero)
                 map_blocks = (nblocks + 7) / 8;
                 im.pmask_base = pl.coef_blocks;
                 im.ppos_base = im.pmask_base + map_blocks;
@@ -642,7 +645,7 @@ void build_plan(zpx_batch* b, int di) {
                 }
             }
         }
-        if (p.progressive) pl.prog_zero.push_back({im.coef_base, nblocks + map_blocks});
+        if (p.progressive) pl.prog_zero.push_back({im.coef_base, nblocks + map_blocks + zero_pos_blocks});
         pl.imgs.push_back(im);
     }
     // progressive intervals go after the sequential ones
@@ -658,17 +661,15 @@ void build_plan(zpx_batch* b, int di) {
         std::stable_sort(l.begin(), l.end(), by_len);
         l.resize(align_up(l.size(), 32), 0xffffffffu);
         std::vector<uint32_t>& dst = pl.prog_lists[g / 3 * 3 + 1];
-        if (g % 3 == 2) {
-            if (pl.prog_acr.size() <= g / 3) pl.prog_acr.resize(g / 3 + 1);
-            DevicePlan::AcRefine& a = pl.prog_acr[g / 3];
-            a.first = (uint32_t)dst.size();
-            a.count = (uint32_t)l.size();
-            for (uint32_t ix : l)
-                if (ix != 0xffffffffu) a.max_blocks = std::max(a.max_blocks, pl.ivs_prog[ix].n_blocks);
-        }
+        if (pl.prog_grp.size() <= g) pl.prog_grp.resize(g + 1);
+        DevicePlan::LaneGroup& a = pl.prog_grp[g];
+        a.first = (uint32_t)dst.size();
+        a.count = (uint32_t)l.size();
+        for (uint32_t ix : l)
+            if (ix != 0xffffffffu) a.max_blocks = std::max(a.max_blocks, pl.ivs_prog[ix].n_blocks);
         dst.insert(dst.end(), l.begin(), l.end());
     }
-    pl.prog_acr.resize(pl.prog_lists.size() / 3);
+    pl.prog_grp.resize(pl.prog_lists.size());
     for (auto& l : pl.prog_lists)
         for (uint32_t& ix : l)
             if (ix != 0xffffffffu) ix += (uint32_t)pl.n_seq;
@@ -844,13 +845,18 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         if (k % 3 == 0) {
             CU(ctx, k3_launch_progressive(k1, list, nl, st));
         } else if (k % 3 == 1) {
-            // AC refinement passes: zero-position lists first, the writes after the serial part
-            const DevicePlan::AcRefine& a = pl.prog_acr[k / 3];
+            // the serial lanes only find where the blocks of an AC pass start; the writes follow in parallel.  AC
+            // refinement passes: zero-position lists first
+            const DevicePlan::LaneGroup &f = pl.prog_grp[k / 3 * 3 + 1], &a = pl.prog_grp[k / 3 * 3 + 2];
             if (a.count) {
                 CU(ctx, k3l_launch_refine_prep(k1, list + a.first, (int)a.count, a.max_blocks, st));
                 k1_launches++;
             }
             CU(ctx, k3l_launch_level(k1, list, nl, st));
+            if (f.count) {
+                CU(ctx, k3l_launch_first_apply(k1, list + f.first, (int)f.count, f.max_blocks, st));
+                k1_launches++;
+            }
             if (a.count) {
                 CU(ctx, k3l_launch_refine_apply(k1, list + a.first, (int)a.count, a.max_blocks, st));
                 k1_launches++;

@@ -45,7 +45,7 @@ namespace {
 constexpr int L_ALB = 9;             // first-level bits of a lane's AC table
 constexpr int L_DLB = 7;             //                    of each of its DC tables
 constexpr int L_RS = 128;            // bytes between ring words of a lane: 32 lanes x 4
-constexpr int L_ZLB = 80;            // bytes of a zero-position list: up to 63 entries, 0xff from the last one on, [79] = their number
+constexpr int L_ZLB = 64;            // bytes of a zero-position list: up to 63 entries, [63] = their number
 constexpr uint32_t SM_RING = 0;                             // [ring words][32] u32: 16 words, 32 in the refinement pass
 constexpr uint32_t SM_LUT = SM_RING + 32 * 128;             // [512][32] u16 (AC) / [4][128][32] u16 (DC)
 constexpr uint32_t SM_AUX = SM_LUT + (1u << L_ALB) * 64;    // AC: lim [32][8] u32, valoff [32][8] i32, vals [32][256] u8
@@ -236,37 +236,39 @@ __device__ __forceinline__ void run_dc_first(const K1Params& P, const Work& w, c
 constexpr int L_STEPS = 8;  // a symbol takes at most 31 bits: 8 of them 31 bytes, the window reaches 12 further, a
                             // topped-up ring holds 49
 
+__device__ __forceinline__ uint32_t* scan_pos(const K1Params& P, const ZpxImageDev* im, const ZpxScanDev* sc) {
+    return reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(P.coef) + im->ppos_base * 128ull) + sc->pos_off;
+}
+__device__ __forceinline__ uint8_t* scan_lists(const K1Params& P, const ZpxImageDev* im, const ZpxScanDev* sc) {
+    return reinterpret_cast<uint8_t*>(P.coef) + im->pzl_base * 128ull + (uint64_t)sc->zl_off * L_ZLB;
+}
+
+// The serial part: where every block that has bits starts (pos[b] = bit position + 1; blocks inside an End-Of-Band run
+// keep the 0 the area was cleared to).  k3l_first_apply decodes the blocks.
 __device__ __forceinline__ void run_ac_first(const K1Params& P, const Work& w, const uint32_t sm, const int lane) {
     const ZpxScanDev* sc = w.sc;
     const ZpxImageDev* im = w.im;
     Lane L;
     L.init(w.active, sm, lane, P, w.iv);
     const uint32_t n = w.active ? w.iv.n_blocks : 0u;
-    int ss = 1, se = 63, al = 0, comp = 0;
+    int ss = 1, se = 63;
     bool undef = false;
-    uint32_t cw = 1, bw = 1, bx = 0, row = 0;  // row = by * bw
+    uint32_t* pos = nullptr;
+    uint32_t* done = nullptr;
     if (w.active) {
         ss = sc->ss;
         se = sc->se;
-        al = sc->al;
-        comp = sc->blk_comp[0];
         undef = ((sc->blk_pack[0][3] >> 17) & 1u) != 0;
-        cw = (uint32_t)sc->cw;
-        bw = (uint32_t)im->comp_bw[comp];
-        const uint32_t by = w.iv.first_block / cw;
-        bx = w.iv.first_block - by * cw;
-        row = by * bw;
+        pos = scan_pos(P, im, sc);
+        done = pos + (uint32_t)sc->cw * (uint32_t)sc->ch + w.iv.ordinal;
+        pos += w.iv.first_block;
     }
-    const uint64_t rel = w.active ? im->comp_base[comp] - im->coef_base : 0ull;
-    short* const cgrid = reinterpret_cast<short*>(P.coef) + (w.active ? im->comp_base[comp] * 64ull : 0ull);
-    unsigned long long* const maps =
-        reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(P.coef) + (w.active ? im->pmask_base * 128ull + rel * 16ull : 0ull));
     const uint32_t lut = sm + SM_LUT + (uint32_t)lane * 2u;
     uint32_t j = 0, eob = 0;
     int zig = ss, err = 0;
-    uint32_t nzl = 0, nzh = 0, sgl = 0, sgh = 0;
     if (undef && n) err = ZPX_E_UninitializedHuffmanTable;
     bool act = n != 0 && !err;
+    if (act) pos[0] = 1u;
     while (__any_sync(0xffffffffu, act)) {
         L.rd.topup();
 #pragma unroll
@@ -277,61 +279,31 @@ __device__ __forceinline__ void run_ac_first(const K1Params& P, const Work& w, c
                 e = ac_long(false, sm, lane, hi);
                 if (e == 0) { L.rd.bitpos += 16; err = ZPX_E_BadHuffmanCode; act = false; }
             }
-            if (!act) e = 0;  // null symbol: no bits, no coefficient, no block end
+            if (!act) e = 0;  // null symbol: no bits, no block end
             const uint32_t tot = e & 31u, len = (e >> 5) & 31u, r = (e >> 10) & 15u, nx = tot - len;
-            const uint32_t t = hi << len;
-            const uint32_t raw = shr_clamp(t, 32u - nx);  // the bits after the code: a value, or the low bits of a run length
             const bool iseob = (e & 0x8000u) != 0, iscoef = (e & 0x4000u) != 0;
             const int zc = zig + (int)r;
-            const bool inband = zc <= se;
-            uint32_t used = tot;
-            if (iscoef) {
-                if (inband) {
-                    const int v = (int)(((int)t < 0 ? raw : raw - shr_clamp(0xffffffffu, 32u - nx)) << al);
-                    if ((uint32_t)(v + 32768) > 65535u) {
-                        err = ZPX_E_COEF_RANGE;  // (the symbol's bits are consumed below, as zpx_k3.cu does)
-                    } else {
-                        const uint32_t nat = lds_u8(sm + SM_UNZIG + (uint32_t)zc);
-                        cgrid[(uint64_t)(row + bx) * 64u + cslot(bx & 7u, nat)] = (short)v;
-                        const uint32_t bit = 1u << (zc & 31), neg = v < 0 ? bit : 0u;
-                        if (zc < 32) { nzl |= bit; sgl |= neg; }
-                        else { nzh |= bit; sgh |= neg; }
-                    }
-                } else {
-                    used = len;  // the value bits stay unread, decoding goes on (decoder.zig:1392-1394)
-                }
-            }
+            // a coefficient past the band's end: its value bits stay unread and the block is over (decoder.zig:1392-1394)
+            L.consume(iscoef && zc > se ? len : tot);
             // EOBn: the rest of the band of this block and of the next eob blocks (decoder.zig:1399-1407)
-            if (iseob) eob = (1u << nx) + raw - 1u;
-            L.consume(used);
+            if (iseob) eob = (1u << nx) + shr_clamp(hi << len, 32u - nx) - 1u;
             zig = iseob ? 64 : zc + (act ? 1 : 0);
-            if (err) act = false;
             if (act && zig > se) {
                 if (L.rd.overrun()) {
                     act = false;
                 } else {
-                    if (nzl | nzh) {
-                        unsigned long long* m = maps + 2ull * (row + bx);
-                        atomicOr(m, (unsigned long long)nzh << 32 | nzl);
-                        if (sgl | sgh) atomicOr(m + 1, (unsigned long long)sgh << 32 | sgl);
-                        nzl = nzh = sgl = sgh = 0;
-                    }
                     const uint32_t skip = min(eob, n - j - 1u);
                     eob -= skip;
                     j += 1u + skip;
-                    bx += 1u + skip;
-                    if (bx >= cw) {
-                        const uint32_t q = bx - cw < cw ? 1u : bx / cw;
-                        bx -= q * cw;
-                        row += q * bw;
-                    }
-                    zig = ss;
                     act = j < n;
+                    if (act) pos[j] = L.rd.bitpos + 1u;
+                    zig = ss;
                 }
             }
         }
     }
     if (w.active) {
+        *done = j;
         if (L.rd.overrun()) err = eof_code(w.iv);
         if (err) report(P.status, im->status_slot, sc->scan_index, (uint64_t)w.iv.first_block + j, err);
         // an End-Of-Band run still open at the end of a scan: see zpx_k3.cu (the reference carries it into the next scan)
@@ -346,15 +318,8 @@ __device__ __forceinline__ void run_ac_first(const K1Params& P, const Work& w, c
 //   pos[b]     bit position of the block's first bit in its interval's stream, bit 31 = the block lies inside an
 //              End-Of-Band run (it has no symbols)
 //   pos[B + i] B = coded blocks of the scan, i = interval ordinal: blocks of interval i the serial pass got through
-//   list[b]    L_ZLB bytes: zig-zag positions of the band's zero coefficients, ascending, 0xff after the last one;
-//              [79] = their number
+//   list[b]    L_ZLB bytes: zig-zag positions of the band's zero coefficients, ascending; [63] = their number
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t* scan_pos(const K1Params& P, const ZpxImageDev* im, const ZpxScanDev* sc) {
-    return reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(P.coef) + im->ppos_base * 128ull) + sc->pos_off;
-}
-__device__ __forceinline__ uint8_t* scan_lists(const K1Params& P, const ZpxImageDev* im, const ZpxScanDev* sc) {
-    return reinterpret_cast<uint8_t*>(P.coef) + im->pzl_base * 128ull + (uint64_t)sc->zl_off * L_ZLB;
-}
 // asynchronous copy of one list into a lane's shared-memory slot (no registers, nothing waits until wait_lists)
 __device__ __forceinline__ void copy_list(uint32_t dst, const uint8_t* src) {
 #pragma unroll
@@ -433,8 +398,8 @@ __device__ __forceinline__ void run_ac_refine(const K1Params& P, const Work& w, 
                     adv = 0;
                 } else {
                     // the (r + 1)-th zero coefficient at or after zig; the non-zero ones passed on the way take a bit each
-                    const uint32_t t = lds_u8(zl + zi + r);
-                    if (t > (uint32_t)se) {
+                    const uint32_t t = lds_u8(zl + min(zi + r, (uint32_t)L_ZLB - 2u));
+                    if (zi + r >= nzeros) {
                         err = ZPX_E_TooManyCoefficients;  // (after the block's remaining correction bits, as the reference)
                     } else {
                         adv = tot + (t - (uint32_t)zig - r);
@@ -573,9 +538,80 @@ __global__ void __launch_bounds__(128) k3l_refine_prep(const K1Params P, const u
         const uint32_t clo = (uint32_t)__popc(zlo), nzeros = clo + (uint32_t)__popc(zhi);
         if (zlo >> lane & 1u) out[__popc(zlo & lt)] = (uint8_t)lane;
         if (zhi >> lane & 1u) out[clo + (uint32_t)__popc(zhi & lt)] = (uint8_t)(lane + 32u);
-        for (uint32_t i = nzeros + lane; i < (uint32_t)L_ZLB - 1u; i += 32u) out[i] = 0xff;
-        if (lane == 0) out[L_ZLB - 1] = (uint8_t)nzeros;
+        if (lane == 0) out[L_ZLB - 1] = (uint8_t)nzeros;  // (entries past the last zero are never read)
         if (++bx == cw) { bx = 0; by++; }
+    }
+}
+
+// AC first pass, after the serial pass: every block that has bits decoded from its start, one thread per block:
+// coefficients and the non-zero / sign maps (decoder.zig:1378-1411).  Grid as k3l_refine_prep
+__global__ void __launch_bounds__(128) k3l_first_apply(const K1Params P, const uint32_t* __restrict__ list) {
+    __shared__ uint16_t s_lut[1 << L_ALB];  // sym << 8 | len, 0 = longer
+    __shared__ uint8_t s_unzig[64];
+    const uint32_t ix = list[blockIdx.y];
+    if (ix == 0xffffffffu) return;
+    const ZpxIntervalDev& iv = P.ivs[ix];
+    if (blockIdx.x * 128u >= iv.n_blocks) return;
+    const ZpxScanDev* __restrict__ sc = &P.scans[iv.scan];
+    const ZpxImageDev* __restrict__ im = &P.imgs[sc->img];
+    const ZpxHuffDev* __restrict__ tab = &P.huff[sc->blk_ac[0]];
+    for (int i = threadIdx.x; i < (1 << L_ALB); i += 128) {
+        const uint32_t e = __ldg(&tab->lut[i << (ZPX_LUT_BITS - L_ALB)]);
+        s_lut[i] = (e & 0xffu) <= (uint32_t)L_ALB ? (uint16_t)e : (uint16_t)0;
+    }
+    if (threadIdx.x < 64) s_unzig[threadIdx.x] = c_unzig[threadIdx.x];
+    __syncthreads();
+    const uint32_t* pos = scan_pos(P, im, sc);
+    const uint32_t done = pos[(uint32_t)sc->cw * (uint32_t)sc->ch + iv.ordinal];
+    const uint32_t j = blockIdx.x * 128u + threadIdx.x;
+    if (j >= done) return;
+    const uint32_t p0 = pos[iv.first_block + j];
+    if (p0 == 0) return;  // inside an End-Of-Band run: nothing coded
+    const int se = sc->se, al = sc->al, comp = sc->blk_comp[0];
+    const uint32_t cw = (uint32_t)sc->cw, bw = (uint32_t)im->comp_bw[comp];
+    const uint32_t q = iv.first_block + j, by = q / cw, bx = q - by * cw;
+    const uint64_t blkix = (uint64_t)by * bw + bx;
+    short* const blk = reinterpret_cast<short*>(P.coef) + (im->comp_base[comp] + blkix) * 64ull;
+    const uint8_t* __restrict__ src = P.ublob + iv.ustart;
+    const uint32_t key = bx & 7u;
+    unsigned long long nz = 0, sg = 0;
+    uint32_t p = p0 - 1u;
+    int zig = sc->ss;
+    while (zig <= se) {
+        const uint32_t hi = bits_at(src, p);
+        uint32_t e = s_lut[hi >> (32 - L_ALB)];
+        if (e == 0) {
+            const HuffSym hs = huff_decode(tab, hi);
+            if (hs.len == 0) break;
+            e = hs.sym << 8 | (uint32_t)hs.len;
+        }
+        const uint32_t len = e & 0xffu, r = e >> 12, s = (e >> 8) & 15u;
+        if (s == 0) {
+            if (r != 15u) break;  // EOBn
+            zig += 16;
+            p += len;
+            continue;
+        }
+        zig += (int)r;
+        if (zig > se) break;
+        const uint32_t t = hi << len;
+        const int v = (int)((uint32_t)((int)t < 0 ? (int)(t >> (32 - s)) : (int)(t >> (32 - s)) - (int)((1u << s) - 1u)) << al);
+        if (v < -32768 || v > 32767) {
+            // hard error, as in zpx_k3.cu: later scans parse according to which coefficients are non-zero
+            report(P.status, im->status_slot, sc->scan_index, (uint64_t)q, ZPX_E_COEF_RANGE);
+            break;
+        }
+        blk[cslot(key, s_unzig[zig])] = (short)v;
+        nz |= 1ull << zig;
+        if (v < 0) sg |= 1ull << zig;
+        p += len + s;
+        zig++;
+    }
+    if (nz) {
+        unsigned long long* m = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(P.coef) + im->pmask_base * 128ull +
+                                                                      (im->comp_base[comp] - im->coef_base + blkix) * 16ull);
+        atomicOr(m, nz);
+        if (sg) atomicOr(m + 1, sg);
     }
 }
 
@@ -732,6 +768,14 @@ cudaError_t k3l_launch_refine_prep(const K1Params& P, const uint32_t* list, int 
     for (int y0 = 0; y0 < n_list; y0 += 65535) {
         const dim3 grid((max_blocks + 127) / 128, (unsigned)std::min(65535, n_list - y0));
         k3l_refine_prep<<<grid, 128, 0, s>>>(P, list + y0);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t k3l_launch_first_apply(const K1Params& P, const uint32_t* list, int n_list, uint32_t max_blocks, cudaStream_t s) {
+    for (int y0 = 0; y0 < n_list; y0 += 65535) {
+        const dim3 grid((max_blocks + 127) / 128, (unsigned)std::min(65535, n_list - y0));
+        k3l_first_apply<<<grid, 128, 0, s>>>(P, list + y0);
     }
     return cudaGetLastError();
 }

@@ -58,6 +58,8 @@ cudaError_t k3l_launch_level(const K1Params& P, const uint32_t* list, int n_padd
 cudaError_t k3l_launch_dc_refine(const K1Params& P, const uint32_t* list, int n_list, cudaStream_t s);
 // AC refinement passes: before k3l_launch_level, the zero-position lists of every block; after it, the writes.  list =
 // the level's AC refinement intervals, max_blocks = the most coded blocks any of them has
+// AC first passes: after k3l_launch_level, the coefficient writes (list = the level's AC first-pass intervals)
+cudaError_t k3l_launch_first_apply(const K1Params& P, const uint32_t* list, int n_list, uint32_t max_blocks, cudaStream_t s);
 cudaError_t k3l_launch_refine_prep(const K1Params& P, const uint32_t* list, int n_list, uint32_t max_blocks, cudaStream_t s);
 cudaError_t k3l_launch_refine_apply(const K1Params& P, const uint32_t* list, int n_list, uint32_t max_blocks, cudaStream_t s);
 
