@@ -259,13 +259,15 @@ typedef struct zpx_parse_report {
     int32_t fused;         /* 1 if the image takes the fused IDCT/colour kernel */
     int32_t mode;          /* colour exit: 0 gray, 1 YCbCr, 2 RGB-tagged, 3 CMYK, 4 YCbCrK */
     uint64_t entropy_bytes;
-    /* sequential scans: what the unstuffing pass (k0_unstuff) is handed */
+    /* what the unstuffing pass (k0_unstuff) is handed */
     uint64_t stuffed_bytes;    /* FF 00 pairs inside the restart intervals */
     uint64_t unstuffed_bytes;  /* bytes of the intervals once the stuffing is removed */
     int32_t n_pieces;          /* work units of the unstuffing kernel */
     int32_t max_piece;         /* largest one, raw bytes */
     int32_t pieces_ok;         /* 1: the pieces tile every interval and none starts on the 0x00 of a pair */
-    int32_t reserved;
+    int32_t lane_script;       /* progressive frames: 1 = the scan script is an ordinary successive approximation (every
+                                * band of a component coded once, then refined with falling Al): the frame can take the
+                                * lane-per-scan kernels (ZPX_OPT_PROGRESSIVE_MODE) */
 } zpx_parse_report;
 int32_t zpx_parse_report_of(const uint8_t *buf, size_t len, zpx_image_info *info, zpx_parse_report *rep);
 

@@ -234,6 +234,51 @@ def test_unstuffing_plan_covers_every_interval(zlib, fixtures_dir):
         assert rep.pieces_ok == 1
 
 
+def test_progressive_scan_script_classification(zlib, fixtures_dir):
+    """Which progressive frames may take the lane-per-scan kernels (they apply correction bits as blind adds and keep
+    the non-zero history in bit maps): every reference fixture (libjpeg's scripts) does; a frame whose script repeats a
+    first pass over a band, or refines without lowering Al, does not -- and its unstuffing plan is still complete."""
+    L = zlib.lib
+
+    def report(d):
+        a = np.frombuffer(d, np.uint8)
+        info, rep = zlib.ZpxImageInfo(), zlib.ZpxParseReport()
+        assert L.zpx_parse_report_of(a.ctypes.data, a.size, C.byref(info), C.byref(rep)) == 0
+        return rep
+
+    names = [n for n in sorted(os.listdir(fixtures_dir)) if "progressive" in n]
+    assert len(names) >= 8
+    for n in names:
+        rep = report(_read(fixtures_dir, n))
+        assert rep.status == 0 and rep.lane_script == 1 and rep.pieces_ok == 1, n
+    assert report(_read(fixtures_dir, "video-001.jpeg")).lane_script == 0  # not progressive
+    data = _read(fixtures_dir, "video-001.q50.420.progressive.jpeg")
+    # walk the SOS headers: (offset of the Ah/Al byte, Ss, Ah, Al)
+    pos, sos = 2, []
+    while data[pos + 1] != 0xD9:
+        ln = int.from_bytes(data[pos + 2:pos + 4], "big")
+        if data[pos + 1] == 0xDA:
+            q = pos + 2 + ln - 1
+            sos.append((q, data[q - 2], data[q] >> 4, data[q] & 15))
+            pos = q + 1
+            while not (data[pos] == 0xFF and data[pos + 1] not in (0, *range(0xD0, 0xD8))):
+                pos += 1
+        else:
+            pos += 2 + ln
+    refinements = [s for s in sos if s[1] > 0 and s[2] > 0]
+    assert refinements
+    q, ss, ah, al = refinements[0]
+    d = bytearray(data)
+    d[q] = 0 << 4 | al  # the refinement becomes a second first pass over its band
+    assert report(bytes(d)).lane_script == 0
+    d[q] = (al + 2) << 4 | (al + 1)  # a refinement that repeats the Al of the first pass
+    assert report(bytes(d)).lane_script == 0
+    dc = [s for s in sos if s[1] == 0][0]
+    d = bytearray(data)
+    d[dc[0]] = 14  # Al = 14: a DC value shifted out of int16 range is the old kernel's business
+    assert report(bytes(d)).lane_script == 0
+
+
 def test_partition_rule(zlib):
     rng = np.random.default_rng(0)
     for n, nd in [(0, 1), (1, 8), (7, 2), (1024, 1), (1024, 2), (1024, 4), (1024, 8), (513, 8)]:

@@ -24,6 +24,8 @@ ap.add_argument("--mode", type=int, default=0)
 ap.add_argument("--native", type=int, default=0, help="1: also compare the native variant (planes / interleave) byte for byte")
 ap.add_argument("--structural", type=int, default=0, help="N more files per base with marker-level damage")
 ap.add_argument("--synth", type=int, default=0, help="1: synthetic base files (other shapes, DRI, CMYK, YCbCrK) instead of the fixtures")
+ap.add_argument("--prog-only", type=int, default=0, help="1: progressive base files only")
+ap.add_argument("--prog-mode", type=int, default=0, help="ZPX_OPT_PROGRESSIVE_MODE: 0 lane per scan where the script allows, 1 warp per scan")
 a = ap.parse_args()
 os.makedirs(a.out, exist_ok=True)
 FX = os.path.join(ROOT, "tests", "golden", "ref_fixtures")
@@ -68,7 +70,7 @@ def bases():
     return out
 
 
-BASES = bases()
+BASES = [b for b in bases() if not a.prog_only or b"\xff\xc2" in b[:4096]]
 def structural_damage(data, rng, count):
     """Marker-level damage: stray / missing / renumbered RSTn, inserted and deleted bytes, a scan played twice,
     a segment moved, a changed restart interval."""
@@ -108,6 +110,7 @@ def structural_damage(data, rng, count):
 
 ctx = jpeg.Context([0])
 ctx.set_option(1, a.mode)
+ctx.set_option(10, a.prog_mode)
 if a.native:
     ctx.set_option(2, 1)  # planes only exist on the unfused path
 bad = total = 0

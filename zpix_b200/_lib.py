@@ -29,7 +29,7 @@ class ZpxParseReport(C.Structure):
         ("status", C.c_int32), ("n_scans", C.c_int32), ("n_intervals", C.c_int32), ("pending_err", C.c_int32),
         ("pending_after_interval", C.c_int32), ("trailing_err", C.c_int32), ("fused", C.c_int32),
         ("mode", C.c_int32), ("entropy_bytes", C.c_uint64), ("stuffed_bytes", C.c_uint64), ("unstuffed_bytes", C.c_uint64),
-        ("n_pieces", C.c_int32), ("max_piece", C.c_int32), ("pieces_ok", C.c_int32), ("reserved", C.c_int32),
+        ("n_pieces", C.c_int32), ("max_piece", C.c_int32), ("pieces_ok", C.c_int32), ("lane_script", C.c_int32),
     ]
 
 

@@ -862,7 +862,9 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
                 k1_launches++;
             }
         } else {
-            CU(ctx, k3l_launch_dc_refine(k1, list, nl, st));
+            uint32_t mb = 0;
+            for (uint32_t ix : pl.prog_lists[k]) mb = std::max(mb, pl.ivs[ix].n_blocks);
+            CU(ctx, k3l_launch_dc_refine(k1, list, nl, mb, st));
         }
         k1_launches++;
     }
@@ -1017,6 +1019,7 @@ int32_t zpx_parse_report_of(const uint8_t* buf, size_t len, zpx_image_info* info
     rep->status = p.status;
     rep->n_scans = (int32_t)p.scans.size();
     rep->pending_after_interval = -1;
+    rep->lane_script = p.progressive && !p.scans.empty() && lane_script_ok(p) ? 1 : 0;
     for (const ZpxScanHost& s : p.scans) {
         rep->n_intervals += (int32_t)s.intervals.size();
         if (s.pending_err) {
@@ -1024,7 +1027,6 @@ int32_t zpx_parse_report_of(const uint8_t* buf, size_t len, zpx_image_info* info
             rep->pending_after_interval = s.err_after_interval;
         }
         if (!s.intervals.empty()) rep->entropy_bytes += s.intervals.back().limit - s.intervals.front().start;
-        if (p.progressive) continue;
         rep->pieces_ok = 1;
         for (const ZpxIntervalHost& iv : s.intervals) {
             rep->stuffed_bytes += iv.n_stuffed;

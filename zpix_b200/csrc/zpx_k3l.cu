@@ -715,11 +715,13 @@ __global__ void __launch_bounds__(128) k3l_refine_apply(const K1Params P, const 
     }
 }
 
-// DC refinement (decoder.zig:1461-1468): block j of the interval takes bit j of its stream.  One warp per interval.
-__global__ void __launch_bounds__(128) k3l_dc_refine(const K1Params P, const uint32_t* __restrict__ list, const int n_list) {
-    const int gw = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (gw >= n_list) return;
-    const ZpxIntervalDev iv = P.ivs[list[gw]];
+// DC refinement (decoder.zig:1461-1468): block j of the interval takes bit j of its stream.  blockIdx.y = entry of the
+// list of intervals, blockIdx.x = group of DCR_CHUNK blocks of the interval, a warp takes 32 blocks at a time.
+constexpr uint32_t DCR_CHUNK = 2048;
+__global__ void __launch_bounds__(128) k3l_dc_refine(const K1Params P, const uint32_t* __restrict__ list) {
+    const int lane = threadIdx.x & 31;
+    const ZpxIntervalDev iv = P.ivs[list[blockIdx.y]];
+    if (blockIdx.x * DCR_CHUNK >= iv.n_blocks) return;
     const ZpxScanDev* __restrict__ sc = &P.scans[iv.scan];
     const ZpxImageDev* __restrict__ im = &P.imgs[sc->img];
     const bool inter = sc->interleaved != 0;
@@ -729,7 +731,8 @@ __global__ void __launch_bounds__(128) k3l_dc_refine(const K1Params P, const uin
     const uint8_t* __restrict__ src = P.ublob + iv.ustart;
     const unsigned int orv = (unsigned int)((1 << sc->al) & 0xffff);
     short* const cbase = reinterpret_cast<short*>(P.coef);
-    for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+    const uint32_t c0 = blockIdx.x * DCR_CHUNK, c1 = min(n, c0 + DCR_CHUNK);
+    for (uint32_t j0 = c0 + (threadIdx.x >> 5) * 32u; j0 < c1; j0 += 128) {
         const uint32_t j = j0 + (uint32_t)lane;
         // 32 bits of the stream: one word per warp iteration, read by every lane (j0 is a multiple of 32)
         const uint32_t word = __byte_perm(__ldg(reinterpret_cast<const uint32_t*>(src + (j0 >> 3))), 0, 0x0123);
@@ -752,7 +755,7 @@ __global__ void __launch_bounds__(128) k3l_dc_refine(const K1Params P, const uin
             atomicOr(reinterpret_cast<unsigned int*>(a & ~(uintptr_t)3), orv << ((a & 2) ? 16 : 0));
         }
     }
-    if (lane == 0 && iv.n_blocks > bits)  // block `bits` is the first one without a bit
+    if (threadIdx.x == 0 && blockIdx.x == 0 && iv.n_blocks > bits)  // block `bits` is the first one without a bit
         report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + bits, eof_code(iv));
 }
 
@@ -788,9 +791,11 @@ cudaError_t k3l_launch_refine_apply(const K1Params& P, const uint32_t* list, int
     return cudaGetLastError();
 }
 
-cudaError_t k3l_launch_dc_refine(const K1Params& P, const uint32_t* list, int n_list, cudaStream_t s) {
-    if (n_list <= 0) return cudaSuccess;
-    k3l_dc_refine<<<(n_list + 3) / 4, 128, 0, s>>>(P, list, n_list);
+cudaError_t k3l_launch_dc_refine(const K1Params& P, const uint32_t* list, int n_list, uint32_t max_blocks, cudaStream_t s) {
+    for (int y0 = 0; y0 < n_list; y0 += 65535) {
+        const dim3 grid((max_blocks + DCR_CHUNK - 1) / DCR_CHUNK, (unsigned)std::min(65535, n_list - y0));
+        k3l_dc_refine<<<grid, 128, 0, s>>>(P, list + y0);
+    }
     return cudaGetLastError();
 }
 

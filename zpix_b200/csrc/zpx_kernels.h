@@ -55,7 +55,7 @@ cudaError_t k3_launch_progressive(const K1Params& P, const uint32_t* list, int n
 // interval.  list = the level's intervals grouped by pass type (DC first / AC first / AC refinement), each group
 // padded to a multiple of 32 with 0xffffffff; DC refinement passes have a kernel of their own (one warp per interval)
 cudaError_t k3l_launch_level(const K1Params& P, const uint32_t* list, int n_padded, cudaStream_t s);
-cudaError_t k3l_launch_dc_refine(const K1Params& P, const uint32_t* list, int n_list, cudaStream_t s);
+cudaError_t k3l_launch_dc_refine(const K1Params& P, const uint32_t* list, int n_list, uint32_t max_blocks, cudaStream_t s);
 // AC refinement passes: before k3l_launch_level, the zero-position lists of every block; after it, the writes.  list =
 // the level's AC refinement intervals, max_blocks = the most coded blocks any of them has
 // AC first passes: after k3l_launch_level, the coefficient writes (list = the level's AC first-pass intervals)
