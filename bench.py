@@ -293,11 +293,15 @@ def other_configs(jpeg, ctx, peak):
             base += [cmyk[i], ycck[i], prog[2 * i], prog[2 * i + 1]]
         return rep(base, 512), 32
 
+    def prog2048():
+        return rep(S.make_batch(5, 16, 1920, 1080, cache_dir=CACHE, first=4000, mode="YCbCr", subsampling="4:2:0", progressive=True), 2048), 16
+
     work = [
         ("cfg3: 4096 x 512x512, half gray + half 4:4:4, baseline, no DRI (self-synchronising entropy decoder)", cfg3),
         ("cfg4: 512 x 3840x2160 4:2:2, baseline, DRI = one MCU row", lambda: cfg4(True)),
         ("cfg4 without DRI: 512 x 3840x2160 4:2:2, baseline (self-synchronising entropy decoder)", lambda: cfg4(False)),
         ("cfg5: 512 x 1920x1080 mixed, 1/4 Adobe CMYK + 1/4 YCbCrK + 1/2 progressive 4:2:0", cfg5),
+        ("progressive: 2048 x 1920x1080 4:2:0 progressive (libjpeg's 10-scan script), one lane per scan", prog2048),
     ]
     out = []
     for desc, make in work:

@@ -372,68 +372,78 @@ __device__ __forceinline__ void run_ac_refine(const K1Params& P, const Work& w, 
     if (n) pos[0] = 0;
     if (undef && n) err = ZPX_E_UninitializedHuffmanTable;  // (the first block of a scan starts with a symbol)
     bool act = n != 0 && !err;
+    const uint32_t endbits = rd.endbits;
     while (__any_sync(0xffffffffu, act)) {
         rd.topup();
+        // One step = one symbol, or one whole block inside an End-Of-Band run.  Straight-line code: everything a step
+        // may do (the block end included) is predicated, only the rare cases branch.
 #pragma unroll
         for (int u = 0; u < R_STEPS; u++) {
-            // correction bits of the block's rest: its non-zero coefficients at or after zig
-            const uint32_t tail = (uint32_t)(se + 1 - zig) - (nzeros - zi);
-            const bool inrun = eob > 0;
             const uint32_t hi = rd.peek();
             uint32_t e = lds_u16(lut + (hi >> (32 - L_ALB)) * 64u);
-            if (act && !inrun && e == 0) {
+            if (act && eob == 0 && e == 0) {
                 e = ac_long(true, sm, lane, hi);
                 if (e == 0) { rd.bitpos += 16; err = ZPX_E_BadHuffmanCode; act = false; }
             }
-            if (!act || inrun) e = 0;
+            if (!act || eob != 0) e = 0;  // no symbol: a lane that is done, or a block inside a run
             const uint32_t tot = e & 31u, len = (e >> 5) & 31u, r = (e >> 10) & 15u, nx = tot - len;
             const bool iseob = (e & 0x8000u) != 0, iscoef = (e & 0x4000u) != 0;
-            const bool target = act && !inrun && !iseob;  // a run of r zeros, then a new coefficient (or ZRL's 16th zero)
-            uint32_t adv = tot + tail;
-            bool fin = true;
-            if (target) {
+            // correction bits of the block's rest: its non-zero coefficients at or after zig
+            const uint32_t tail = (uint32_t)(se + 1 - zig) - (nzeros - zi);
+            // a run of r zeros, then a new coefficient (or ZRL's 16th zero): the (r + 1)-th zero coefficient at or after
+            // zig; the non-zero ones passed on the way take a bit each
+            bool target = e != 0 && !iseob;
+            const uint32_t zr = zi + r;
+            const uint32_t t = lds_u8(zl + min(zr, (uint32_t)L_ZLB - 2u));
+            if (target && ((!iscoef && r != 15u) || zr >= nzeros)) {
                 if (!iscoef && r != 15u) {
                     rd.bitpos += len;
                     err = ZPX_E_UnexpectedHuffmanCode;
-                    adv = 0;
                 } else {
-                    // the (r + 1)-th zero coefficient at or after zig; the non-zero ones passed on the way take a bit each
-                    const uint32_t t = lds_u8(zl + min(zi + r, (uint32_t)L_ZLB - 2u));
-                    if (zi + r >= nzeros) {
-                        err = ZPX_E_TooManyCoefficients;  // (after the block's remaining correction bits, as the reference)
-                    } else {
-                        adv = tot + (t - (uint32_t)zig - r);
-                        zi += r + 1u;
-                        zig = (int)t + 1;
-                        fin = zig > se;
-                    }
+                    rd.bitpos += tot + tail;  // (after the block's remaining correction bits, as the reference)
+                    err = ZPX_E_TooManyCoefficients;
                 }
+                act = false;
+                target = false;
             }
             // EOBn (decoder.zig:1480-1488): this block's rest and the next eob - 1 blocks
             if (iseob) eob = (1u << nx) + shr_clamp(hi << len, 32u - nx);
-            if (!act) adv = 0;
-            rd.bitpos += adv;
-            if (err) act = false;
-            if (act && fin) {
-                if (inrun || iseob) eob--;
-                if (rd.overrun()) {
-                    act = false;
-                } else {
-                    j++;
-                    if (j < n) pos[j] = rd.bitpos | (eob ? 0x80000000u : 0u);
-                    // the slot just finished takes the list of block j + 2; block j's own copy was issued two blocks ago
-                    if (j + 2 < n) copy_list(zl, lp);
-                    commit_lists();
-                    lp += L_ZLB;
-                    zl += 32u * L_ZLB;
-                    if (zl == zl_end) zl = zl0;
-                    wait_lists();
-                    nzeros = lds_u8(zl + L_ZLB - 1);
-                    zig = ss;
-                    zi = 0;
-                    act = j < n;
-                }
-            }
+            rd.bitpos += !act ? 0u : target ? tot + (t - (uint32_t)zig - r) : tot + tail;
+            zi = target ? zr + 1u : zi;
+            zig = target ? (int)t + 1 : zig;
+            const bool fin = act && (!target || zig > se);
+            eob -= (fin && !target) ? 1u : 0u;
+            const bool be = fin && rd.bitpos <= endbits;  // block end (a block that ran past the stream's end fails below)
+            j += be ? 1u : 0u;
+            act = act && (!fin || be) && j < n;
+            // ---- block end ----
+            const uint32_t bq = be ? 1u : 0u, more = (be && act) ? 1u : 0u, cp = (be && j + 2 < n) ? 1u : 0u;
+            asm volatile(
+                "{\n\t.reg .pred pm, pc, pb;\n\t"
+                "setp.ne.u32 pm, %0, 0;\n\t"
+                "setp.ne.u32 pc, %1, 0;\n\t"
+                "setp.ne.u32 pb, %2, 0;\n\t"
+                "@pm st.global.u32 [%3], %4;\n\t"
+                // the slot just finished takes the list of block j + 2; block j's own copy was issued two blocks ago
+                "@pc cp.async.ca.shared.global [%5], [%6], 16;\n\t"
+                "@pc cp.async.ca.shared.global [%5+16], [%6+16], 16;\n\t"
+                "@pc cp.async.ca.shared.global [%5+32], [%6+32], 16;\n\t"
+                "@pc cp.async.ca.shared.global [%5+48], [%6+48], 16;\n\t"
+                "@pb cp.async.commit_group;\n\t"
+                "}" ::"r"(more), "r"(cp), "r"(bq), "l"(pos + j), "r"(rd.bitpos | (eob ? 0x80000000u : 0u)), "r"(zl), "l"(lp)
+                : "memory");
+            lp += be ? L_ZLB : 0;
+            uint32_t zn = zl + 32u * L_ZLB;
+            if (zn == zl_end) zn = zl0;
+            zl = be ? zn : zl;
+            asm volatile(
+                "{\n\t.reg .pred pb;\n\t"
+                "setp.ne.u32 pb, %1, 0;\n\t"
+                "@pb cp.async.wait_group 2;\n\t"
+                "@pb ld.shared.u8 %0, [%2];\n\t"
+                "}" : "+r"(nzeros) : "r"(bq), "r"(zl + (uint32_t)L_ZLB - 1u) : "memory");
+            zig = be ? ss : zig;
+            zi = be ? 0u : zi;
         }
     }
     if (w.active) {
