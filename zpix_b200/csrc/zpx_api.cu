@@ -659,6 +659,15 @@ void build_plan(zpx_batch* b, int di) {
         std::vector<uint32_t>& l = lane_groups[g];
         if (l.empty()) continue;
         std::stable_sort(l.begin(), l.end(), by_len);
+        if (g % 3 == 1) {
+            // AC first passes: 16 streams per warp (k3l_level keeps a 10-bit table per lane for them)
+            std::vector<uint32_t> w;
+            for (size_t i = 0; i < l.size(); i += 16) {
+                w.insert(w.end(), l.begin() + (ptrdiff_t)i, l.begin() + (ptrdiff_t)std::min(i + 16, l.size()));
+                w.resize(align_up(w.size(), 32), 0xffffffffu);
+            }
+            l.swap(w);
+        }
         l.resize(align_up(l.size(), 32), 0xffffffffu);
         std::vector<uint32_t>& dst = pl.prog_lists[g / 3 * 3 + 1];
         if (pl.prog_grp.size() <= g) pl.prog_grp.resize(g + 1);

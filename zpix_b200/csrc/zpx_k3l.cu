@@ -42,12 +42,17 @@ namespace zpx {
 
 namespace {
 
-constexpr int L_ALB = 9;             // first-level bits of a lane's AC table
+constexpr int L_ALB = 9;             // first-level bits of a lane's AC table (refinement passes: 32 lanes per warp)
+constexpr int L_FLB = 10;            // ... in an AC first pass, whose warps carry 16 lanes: optimised tables of full
+                                     // run/size alphabets have enough 10-bit codes for one lane in 32 to miss a
+                                     // 9-bit table at nearly every step (and the canonical search then stalls all)
+constexpr int L_FLANES = 16;
 constexpr int L_DLB = 7;             //                    of each of its DC tables
 constexpr int L_RS = 128;            // bytes between ring words of a lane: 32 lanes x 4
 constexpr int L_ZLB = 64;            // bytes of a zero-position list: up to 63 entries, [63] = their number
 constexpr uint32_t SM_RING = 0;                             // [ring words][32] u32: 16 words, 32 in the refinement pass
-constexpr uint32_t SM_LUT = SM_RING + 32 * 128;             // [512][32] u16 (AC) / [4][128][32] u16 (DC)
+constexpr uint32_t SM_LUT = SM_RING + 32 * 128;             // [512][32] u16 (AC refinement) / [1024][16] u16 (AC first) /
+                                                            // [4][128][32] u16 (DC)
 constexpr uint32_t SM_AUX = SM_LUT + (1u << L_ALB) * 64;    // AC: lim [32][8] u32, valoff [32][8] i32, vals [32][256] u8
 constexpr uint32_t SM_LIM = SM_AUX, SM_VOFF = SM_AUX + 1024, SM_VALS = SM_AUX + 2048;
 constexpr uint32_t SM_DESC = SM_AUX;                        // DC: [3][ZPX_MAX_BLK_PER_MCU][32] u32
@@ -113,7 +118,8 @@ struct Lane {
 
 // the lane's AC symbol at the top of hi when the first level has no entry: canonical search over the lane's limits,
 // first match = the reference's rule (decoder.zig:946-969).  0 = no code matches
-__device__ __forceinline__ uint32_t ac_long(bool refine, uint32_t sm, int lane, uint32_t hi) {
+__device__ __forceinline__ uint32_t ac_long(bool refine, uint32_t sm, int lane, uint32_t hi) {  // (lengths 10..16: a
+    // 10-bit code that a 10-bit first level would have held is simply never asked for)
     const uint32_t v16 = hi >> 16;
     const uint4 a = lds_u128(sm + SM_LIM + (uint32_t)lane * 32u), b = lds_u128(sm + SM_LIM + (uint32_t)lane * 32u + 16u);
     int len = 0;
@@ -263,7 +269,7 @@ __device__ __forceinline__ void run_ac_first(const K1Params& P, const Work& w, c
         done = pos + (uint32_t)sc->cw * (uint32_t)sc->ch + w.iv.ordinal;
         pos += w.iv.first_block;
     }
-    const uint32_t lut = sm + SM_LUT + (uint32_t)lane * 2u;
+    const uint32_t lut = sm + SM_LUT + (uint32_t)(lane & (L_FLANES - 1)) * 2u;  // (lanes 16..31 never have a stream)
     uint32_t j = 0, eob = 0;
     int zig = ss, err = 0;
     if (undef && n) err = ZPX_E_UninitializedHuffmanTable;
@@ -274,7 +280,7 @@ __device__ __forceinline__ void run_ac_first(const K1Params& P, const Work& w, c
 #pragma unroll
         for (int u = 0; u < L_STEPS; u++) {
             const uint32_t hi = L.peek();
-            uint32_t e = lds_u16(lut + (hi >> (32 - L_ALB)) * 64u);
+            uint32_t e = lds_u16(lut + (hi >> (32 - L_FLB)) * (2u * L_FLANES));
             if (act && e == 0) {
                 e = ac_long(false, sm, lane, hi);
                 if (e == 0) { L.rd.bitpos += 16; err = ZPX_E_BadHuffmanCode; act = false; }
@@ -407,7 +413,10 @@ __device__ __forceinline__ void run_ac_refine(const K1Params& P, const Work& w, 
                 target = false;
             }
             // EOBn (decoder.zig:1480-1488): this block's rest and the next eob - 1 blocks
-            if (iseob) eob = (1u << nx) + shr_clamp(hi << len, 32u - nx);
+            {
+                const uint32_t run = (1u << nx) + shr_clamp(hi << len, 32u - nx);
+                asm("{.reg .pred p; setp.ne.u32 p, %1, 0; selp.u32 %0, %2, %0, p;}" : "+r"(eob) : "r"((uint32_t)iseob), "r"(run));
+            }
             rd.bitpos += !act ? 0u : target ? tot + (t - (uint32_t)zig - r) : tot + tail;
             zi = target ? zr + 1u : zi;
             zig = target ? (int)t + 1 : zig;
@@ -416,34 +425,20 @@ __device__ __forceinline__ void run_ac_refine(const K1Params& P, const Work& w, 
             const bool be = fin && rd.bitpos <= endbits;  // block end (a block that ran past the stream's end fails below)
             j += be ? 1u : 0u;
             act = act && (!fin || be) && j < n;
-            // ---- block end ----
-            const uint32_t bq = be ? 1u : 0u, more = (be && act) ? 1u : 0u, cp = (be && j + 2 < n) ? 1u : 0u;
-            asm volatile(
-                "{\n\t.reg .pred pm, pc, pb;\n\t"
-                "setp.ne.u32 pm, %0, 0;\n\t"
-                "setp.ne.u32 pc, %1, 0;\n\t"
-                "setp.ne.u32 pb, %2, 0;\n\t"
-                "@pm st.global.u32 [%3], %4;\n\t"
+            // ---- block end: the only common branch of a step ----
+            if (be) {
+                if (act) pos[j] = rd.bitpos | (eob ? 0x80000000u : 0u);
                 // the slot just finished takes the list of block j + 2; block j's own copy was issued two blocks ago
-                "@pc cp.async.ca.shared.global [%5], [%6], 16;\n\t"
-                "@pc cp.async.ca.shared.global [%5+16], [%6+16], 16;\n\t"
-                "@pc cp.async.ca.shared.global [%5+32], [%6+32], 16;\n\t"
-                "@pc cp.async.ca.shared.global [%5+48], [%6+48], 16;\n\t"
-                "@pb cp.async.commit_group;\n\t"
-                "}" ::"r"(more), "r"(cp), "r"(bq), "l"(pos + j), "r"(rd.bitpos | (eob ? 0x80000000u : 0u)), "r"(zl), "l"(lp)
-                : "memory");
-            lp += be ? L_ZLB : 0;
-            uint32_t zn = zl + 32u * L_ZLB;
-            if (zn == zl_end) zn = zl0;
-            zl = be ? zn : zl;
-            asm volatile(
-                "{\n\t.reg .pred pb;\n\t"
-                "setp.ne.u32 pb, %1, 0;\n\t"
-                "@pb cp.async.wait_group 2;\n\t"
-                "@pb ld.shared.u8 %0, [%2];\n\t"
-                "}" : "+r"(nzeros) : "r"(bq), "r"(zl + (uint32_t)L_ZLB - 1u) : "memory");
-            zig = be ? ss : zig;
-            zi = be ? 0u : zi;
+                if (j + 2 < n) copy_list(zl, lp);
+                commit_lists();
+                lp += L_ZLB;
+                zl += 32u * L_ZLB;
+                if (zl == zl_end) zl = zl0;
+                wait_lists();
+                nzeros = lds_u8(zl + (uint32_t)L_ZLB - 1u);
+                zig = ss;
+                zi = 0;
+            }
         }
     }
     if (w.active) {
@@ -458,11 +453,11 @@ __device__ __forceinline__ void run_ac_refine(const K1Params& P, const Work& w, 
 // one lane's first-level table into shared memory, written by the whole warp.  Source: the 10-bit table of ZpxHuffDev
 template <typename F>
 __device__ __forceinline__ void stage_lut(uint32_t dst /* shared address of entry 0 of the lane's column */, const ZpxHuffDev* __restrict__ t,
-                                          int bits, int lane, F entry) {
+                                          int bits, uint32_t stride /* bytes between entries */, int lane, F entry) {
     for (int i = lane; i < (1 << bits); i += 32) {
         const uint32_t e = __ldg(&t->lut[i << (ZPX_LUT_BITS - bits)]);
         const uint32_t len = e & 0xffu;
-        sts_u16(dst + (uint32_t)i * 64u, (len == 0 || len > (uint32_t)bits) ? 0 : (int)entry(e >> 8, len));
+        sts_u16(dst + (uint32_t)i * stride, (len == 0 || len > (uint32_t)bits) ? 0 : (int)entry(e >> 8, len));
     }
 }
 
@@ -474,7 +469,8 @@ __device__ __forceinline__ uint32_t bits_at(const uint8_t* __restrict__ src, uin
 
 }  // namespace
 
-// one warp per CTA; list: interval indices grouped by pass type, every group padded to a multiple of 32 with ~0
+// one warp per CTA; list: interval indices grouped by pass type, every group padded to a multiple of 32 with ~0 (AC
+// first passes: 16 intervals and 16 x ~0 per warp)
 __global__ void __launch_bounds__(32) k3l_level(const K1Params P, const uint32_t* __restrict__ list) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     const uint32_t sm = smem_addr(s_raw);
@@ -500,13 +496,15 @@ __global__ void __launch_bounds__(32) k3l_level(const K1Params P, const uint32_t
                 const uint32_t comp = sc->blk_comp[c];
                 if (done >> comp & 1u) continue;
                 done |= 1u << comp;
-                stage_lut(sm + SM_LUT + (comp * (1u << L_DLB) * 32u + (uint32_t)l) * 2u, &P.huff[sc->blk_dc[c]], L_DLB, lane,
+                stage_lut(sm + SM_LUT + (comp * (1u << L_DLB) * 32u + (uint32_t)l) * 2u, &P.huff[sc->blk_dc[c]], L_DLB, 64u, lane,
                           [](uint32_t sym, uint32_t len) { return dc_entry(sym, len); });
             }
         } else {
             const ZpxHuffDev* __restrict__ t = &P.huff[sc->blk_ac[0]];
             const bool refine = type == T_ACR;
-            stage_lut(sm + SM_LUT + (uint32_t)l * 2u, t, L_ALB, lane, [refine](uint32_t sym, uint32_t len) { return ac_entry(refine, sym, len); });
+            // (an AC first pass keeps streams in lanes 0..15 only: the host pads its list that way)
+            stage_lut(sm + SM_LUT + (uint32_t)l * 2u, t, refine ? L_ALB : L_FLB, refine ? 64u : 2u * L_FLANES, lane,
+                      [refine](uint32_t sym, uint32_t len) { return ac_entry(refine, sym, len); });
             if (lane < 7) {
                 sts_u32(sm + SM_LIM + (uint32_t)l * 32u + (uint32_t)lane * 4u, __ldg(&t->limit[10 + lane]));
                 sts_u32(sm + SM_VOFF + (uint32_t)l * 32u + (uint32_t)lane * 4u, (uint32_t)__ldg(&t->valoff[10 + lane]));
@@ -516,6 +514,8 @@ __global__ void __launch_bounds__(32) k3l_level(const K1Params P, const uint32_t
         }
     }
     __syncwarp();
+    if ((P.dbg & 2) && type == T_DCF) return;  // experiments only (ZPX_K1_DBG): time a level without one pass type
+    if ((P.dbg & 4) && type == T_ACF) return;
     if (type == T_DCF) run_dc_first(P, w, sm, lane);
     else if (type == T_ACF) run_ac_first(P, w, sm, lane);
     else run_ac_refine(P, w, sm, lane);
