@@ -290,6 +290,8 @@ int32_t zpx_partition(const uint64_t *weights, int32_t n, int32_t n_devices, int
 #define ZPX_OPT_PROGRESSIVE_MODE 10 /* 0 (default): progressive frames whose scan script is an ordinary successive
                                     * approximation decode one lane per scan (zpx_k3l.cu), the others one warp per scan
                                     * (zpx_k3.cu); 1: always one warp per scan */
+#define ZPX_OPT_K2_DENSE 11 /* 1: the fused kernel never takes its sparse-block IDCT (warps whose 32 blocks have no
+                             * coefficient outside the top-left 4x4 corner); results are identical either way */
 #define ZPX_OPT_TEST_WIDE 8  /* test hook: 1 = frames filled by zpx_batch_set_coefficients take the kernels' exact
                                 all-AC-zero-row IDCT variant whatever their coefficients */
 int32_t zpx_ctx_set_option(zpx_ctx *ctx, int32_t option, int64_t value);

@@ -184,7 +184,7 @@ struct zpx_ctx {
     std::string last_cuda_str;
     std::atomic<uint64_t> launches{0};
     int64_t opt_entropy_mode = 0, opt_force_generic = 0, opt_subseq = 0, opt_pipeline_chunk = 0;
-    int64_t opt_pipeline_ramp = 1, opt_pipeline_workers = 3, opt_test_wide = 0, opt_native = 0, opt_progressive_mode = 0;
+    int64_t opt_pipeline_ramp = 1, opt_pipeline_workers = 3, opt_test_wide = 0, opt_native = 0, opt_progressive_mode = 0, opt_k2_dense = 0;
     bool busy = false;
     const zpx_batch* resident = nullptr;  // the batch whose data currently occupies the device buffers
     std::vector<zpx_ctx*> shadows;  // further sets of device buffers/streams for the chunk pipeline of zpx_decode_batch_rgba
@@ -891,6 +891,7 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         k2.img_flags = img_flags;
         k2.ntiles = (int)g.tiles.size();
         k2.tmax = g.tmax;
+        k2.dense_only = ctx->opt_k2_dense != 0;
         k2.nt = std::max(96, (g.tmax * k2_fused_bpm(g.h, g.v, g.nc) + 31) / 32 * 32);
         CU(ctx, k2_launch_fused(g.h, g.v, g.nc, k2, dc.sm_count, st));
         k2_launches++;
@@ -1158,6 +1159,7 @@ int32_t zpx_ctx_set_option(zpx_ctx* c, int32_t option, int64_t value) {
         case ZPX_OPT_PIPELINE_RAMP: c->opt_pipeline_ramp = value; return ZPX_OK;
         case ZPX_OPT_TEST_WIDE: c->opt_test_wide = value; return ZPX_OK;
         case ZPX_OPT_PROGRESSIVE_MODE: c->opt_progressive_mode = value; return ZPX_OK;
+        case ZPX_OPT_K2_DENSE: c->opt_k2_dense = value; return ZPX_OK;
         case ZPX_OPT_NATIVE_PLANES:
             if (value < 0 || value > 2) return ZPX_E_INVALID_ARG;
             c->opt_native = value;
@@ -1764,6 +1766,7 @@ static int32_t decode_batch_pipelined(zpx_ctx* ctx, const uint8_t* const* bufs, 
         sh->opt_subseq = ctx->opt_subseq;
         sh->opt_native = ctx->opt_native;
         sh->opt_progressive_mode = ctx->opt_progressive_mode;
+        sh->opt_k2_dense = ctx->opt_k2_dense;
     }
     // chunk list: the first two chunks are a quarter and a half of the regular size, so that the first
     // device->host copy starts early (the pipeline is bound by that copy; its fill time is pure loss)

@@ -176,6 +176,34 @@ __device__ __forceinline__ void dequant_idct_block_q8(LoadRow ld, const uint32_t
     }
 }
 
+// Same values as dequant_idct_block_q8 for a block whose coefficients outside the top-left 4x4 corner are all zero
+// (rows 4..7 and columns 4..7 of the natural-order block): the zero inputs are constants, so the multiplications
+// by them, the row pass of rows 4..7 (every output of an all-zero row is (0 + 128) >> 8 = 0) and the column terms
+// they feed fold away at compile time; every surviving operation is the one the general code performs, on the same
+// operands (wrapping 32-bit), hence bit-identical.  The caller takes this variant only when EVERY block of the warp
+// qualifies (a warp vote), which chroma blocks of photographs usually do.
+template <typename LoadRow>
+__device__ __forceinline__ void dequant_idct_block_q8_lo4(LoadRow ld, const uint32_t* __restrict__ qp, uint32_t (&px)[16]) {
+    int b[64];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const uint4 c = ld(r);
+        const uint2 q = *reinterpret_cast<const uint2*>(qp + r * 4);
+        const int s0 = dp2a_lo_su(c.x, q.x) << 11, s1 = dp2a_hi_su(c.x, q.x);
+        const int s2 = dp2a_lo_su(c.y, q.y), s3 = dp2a_hi_su(c.y, q.y);
+        idct_row(s0, s1, s2, s3, 0, 0, 0, 0, &b[r * 8]);
+    }
+#pragma unroll
+    for (int k = 32; k < 64; k++) b[k] = 0;
+#pragma unroll
+    for (int x = 0; x < 8; x++) idct_col(&b[x]);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        px[2 * r + 0] = pack4_level_shift(b[r * 8 + 0], b[r * 8 + 1], b[r * 8 + 2], b[r * 8 + 3]);
+        px[2 * r + 1] = pack4_level_shift(b[r * 8 + 4], b[r * 8 + 5], b[r * 8 + 6], b[r * 8 + 7]);
+    }
+}
+
 // The same block the reference's way where it matters: a row whose dequantised AC are all zero yields s0 << 3
 // in every column (idct.zig:84-97), which differs from the general row once s0 << 11 wraps (|s0| >= 2^20; only
 // garbage streams).  Out of line and self-contained (reads the block from shared memory again, stores the 8x8

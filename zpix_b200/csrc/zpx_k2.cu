@@ -241,18 +241,34 @@ __global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P)
             }
         };
         if (!t.wide) {
-            for (int i = tid; i < nblk; i += NT) {
+            // (warp-uniform trip count: the vote below needs every lane)
+            for (int i = tid; (i & ~31) < nblk; i += NT) {
+                const bool valid = i < nblk;
                 int slot, bxa, pitch;
                 uint8_t* dst;
                 const uint32_t* q;
-                locate(i, slot, bxa, dst, pitch, q);
+                locate(valid ? i : nblk - 1, slot, bxa, dst, pitch, q);
                 const uint4* blk = st + slot * 8;
                 const int key = bxa & 7;
-                uint32_t px[16];
-                dequant_idct_block_q8([&](int r) { return blk[r ^ key]; }, q, px);
+                uint4 c[8];
 #pragma unroll
-                for (int r = 0; r < 8; r++)
-                    *reinterpret_cast<uint2*>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+                for (int r = 0; r < 8; r++) c[r] = blk[r ^ key];
+                // Sparse blocks: when all 32 blocks of the warp have nothing outside their top-left 4x4 corner (chroma
+                // blocks mostly: a tile's threads are ordered luma, Cb, Cr), the IDCT with those zeros folded in
+                // (zpx_idct.cuh: the same operations on the same operands, minus the ones on constants)
+                uint32_t hi = 0;
+#pragma unroll
+                for (int r = 0; r < 4; r++) hi |= c[r].z | c[r].w | c[r + 4].x | c[r + 4].y | c[r + 4].z | c[r + 4].w;
+                uint32_t px[16];
+                if (P.dense_only || __any_sync(0xffffffffu, valid && hi != 0))
+                    dequant_idct_block_q8([&](int r) { return c[r]; }, q, px);
+                else
+                    dequant_idct_block_q8_lo4([&](int r) { return c[r]; }, q, px);
+                if (valid) {
+#pragma unroll
+                    for (int r = 0; r < 8; r++)
+                        *reinterpret_cast<uint2*>(dst + r * pitch) = make_uint2(px[2 * r], px[2 * r + 1]);
+                }
             }
         } else {
             // the image has coefficients outside [-4096, 4095] (garbage streams only): rows whose AC are all zero the

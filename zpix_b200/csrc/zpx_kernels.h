@@ -80,6 +80,7 @@ struct K2Params {
     int ntiles;
     int tmax;  // largest tile (MCUs): fixes the shared-memory layout
     int nt;    // threads per CTA: blocks of the largest tile rounded up to a warp (<= k2_fused_threads)
+    int dense_only;  // 1: never take the sparse-block IDCT (ZPX_OPT_K2_DENSE, measurements and tests)
 };
 int k2_fused_bpm(int h, int v, int nc);
 // persistent grid: min(tiles, SMs x resident CTAs)
