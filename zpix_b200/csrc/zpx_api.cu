@@ -228,14 +228,40 @@ const char* const kErrNames[] = {
     "InvalidImageType", "ConfigOnly", "OutOfMemory",
 };
 
-bool fused_eligible(const ZpxParsed& p) {
-    if (p.progressive || p.scans.size() != 1) return false;
+// Components some scan covers.  Progressive frames allocate their coefficient arrays by looping the FRAME's
+// component count over the scan's component list (entries past the scan's own count read as
+// component 0), and only allocated components are reconstructed (decoder.zig:1272-1279, :1644).
+// bits 4-7: the component is coded by some INTERLEAVED scan of a sequential frame, which visits every block
+// of the MCU grid; a component that only has scans of its own is reconstructed where 8*bx < width and
+// 8*by < height (decoder.zig:1331-1336) and keeps zeros in the rest of its padded plane
+uint32_t recon_mask_of(const ZpxParsed& p) {
+    uint32_t m = 0;
+    for (const ZpxScanHost& sc : p.scans) {
+        for (int i = 0; i < sc.ncomp; i++) {
+            m |= 1u << sc.comp[i];
+            if (sc.ncomp > 1) m |= 16u << sc.comp[i];
+        }
+        if (p.progressive && sc.ncomp < p.ncomp) m |= 1u;
+    }
+    return m;
+}
+
+// Frames the fused kernel takes: gray, or YCbCr with full-resolution luma sampling factors it has an instantiation
+// for.  A frame made of ONE interleaved scan keeps its coefficients MCU by MCU (one bulk copy per tile); every other
+// scan script (components in scans of their own, several scans, progressive) keeps one block grid per component and
+// the kernel gathers a tile with one copy per block row.  Those frames are fused only for RGBA output: in their native
+// planes the reference leaves blocks it never reconstructs at zero (decoder.zig:1331-1336, :1644-1651), which only
+// the unfused kernels reproduce -- and only when every component is covered by some scan (same reason).
+bool fused_eligible(const ZpxParsed& p, uint32_t recon_mask, int native) {
     if ((uint64_t)p.width * (uint64_t)p.height >= (1ull << 30)) return false;  // the fused kernel keeps 32-bit pixel offsets
-    const ZpxScanHost& s = p.scans[0];
-    if (p.ncomp == 1) return p.mode == ZPX_MODE_GRAY && s.ncomp == 1;
-    if (p.ncomp != 3 || p.mode != ZPX_MODE_YCBCR || s.ncomp != 3) return false;
-    for (int i = 0; i < 3; i++)
-        if (s.comp[i] != i) return false;
+    if (p.scans.empty()) return false;
+    bool single = !p.progressive && p.scans.size() == 1 && p.scans[0].ncomp == p.ncomp;
+    if (single)
+        for (int i = 0; i < p.ncomp; i++) single = single && p.scans[0].comp[i] == i;
+    if (!single && native != 0) return false;
+    if (p.ncomp == 1) return p.mode == ZPX_MODE_GRAY && (single || (recon_mask & 1u));
+    if (p.ncomp != 3 || p.mode != ZPX_MODE_YCBCR) return false;
+    if (!single && (recon_mask & 7u) != 7u) return false;
     if (p.h[1] != 1 || p.v[1] != 1 || p.h[2] != 1 || p.v[2] != 1) return false;
     const int hv = p.h[0] << 4 | p.v[0];
     return hv == 0x11 || hv == 0x21 || hv == 0x22 || hv == 0x12 || hv == 0x41 || hv == 0x42;
@@ -320,17 +346,7 @@ void build_plan(zpx_batch* b, int di) {
         // components some scan covers.  Progressive frames allocate their coefficient arrays by looping the FRAME's
         // component count over the scan's component list (entries past the scan's own count read as
         // component 0), and only allocated components are reconstructed (decoder.zig:1272-1279, :1644).
-        im.recon_mask = 0;
-        // bits 4-7: the component is coded by some INTERLEAVED scan of a sequential frame, which visits every block
-        // of the MCU grid; a component that only has scans of its own is reconstructed where 8*bx < width and
-        // 8*by < height (decoder.zig:1331-1336) and keeps zeros in the rest of its padded plane
-        for (const ZpxScanHost& sc : p.scans) {
-            for (int i = 0; i < sc.ncomp; i++) {
-                im.recon_mask |= 1u << sc.comp[i];
-                if (sc.ncomp > 1) im.recon_mask |= 16u << sc.comp[i];
-            }
-            if (p.progressive && sc.ncomp < p.ncomp) im.recon_mask |= 1u;
-        }
+        im.recon_mask = recon_mask_of(p);
         int bpm = 0;
         for (int c = 0; c < p.ncomp; c++) {
             im.h[c] = (uint8_t)p.h[c];
@@ -346,7 +362,7 @@ void build_plan(zpx_batch* b, int di) {
             for (int i = 0; i < p.ncomp; i++) single = single && p.scans[0].comp[i] == i;
         im.layout = single ? ZPX_LAYOUT_INTERLEAVED : ZPX_LAYOUT_PLANAR;
         im.bpm = bpm;
-        im.fused = (!force_generic && fused_eligible(p)) ? 1 : 0;
+        im.fused = (!force_generic && fused_eligible(p, im.recon_mask, pl.native)) ? 1 : 0;
         // coefficient storage
         const uint64_t nblocks = (uint64_t)p.mxx * p.myy * bpm;
         im.coef_base = pl.coef_blocks;
@@ -1061,7 +1077,7 @@ int32_t zpx_parse_report_of(const uint8_t* buf, size_t len, zpx_image_info* info
         }
     }
     rep->trailing_err = p.trailing_err;
-    rep->fused = (p.status == 0 && fused_eligible(p)) ? 1 : 0;
+    rep->fused = (p.status == 0 && fused_eligible(p, recon_mask_of(p), 0)) ? 1 : 0;  // (for RGBA output, 8-bit quantisers)
     rep->mode = p.mode;
     return ZPX_OK;
 }

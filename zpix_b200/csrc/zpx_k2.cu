@@ -126,6 +126,8 @@ __global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P)
         int32_t ystride, cstride;
         uint32_t magic;   // phase 2: 2^32 / (items per row) + 1, for the exact division of an item index by it
         uint32_t interior;  // every pixel of the tile lies inside the image and rows are 16-byte multiples: no bounds tests
+        uint32_t planar;    // the image keeps one block grid per component (multi-scan and progressive frames): the stage
+                            // then holds the tile's blocks component by component, in phase 1's own thread order
     };
     __shared__ TileCtx ctx[NS];
     __shared__ __align__(16) uint32_t qsm[NS][3 * 32];  // per row four words q[2j] | q[2j+1] << 24 (dp2a operands)
@@ -136,11 +138,30 @@ __global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P)
     auto fetch = [&](const ZpxTileDev tn, int stg) {
         const ZpxImageDev* __restrict__ imn = &P.imgs[tn.img];
         if (tid == 0) {
-            const uint64_t blk0 = imn->coef_base + ((uint64_t)tn.my * imn->mxx + tn.mx0) * BPM;
             const uint32_t bytes = (uint32_t)tn.n * BPM * 128;
+            const bool planar = NC == 3 && imn->layout == ZPX_LAYOUT_PLANAR;
+            uint8_t* const sdst = stage0 + (size_t)stg * stage_bytes;
             mbar_arrive_expect_tx(&bars[stg], bytes);
-            bulk_g2s(stage0 + (size_t)stg * stage_bytes, coef + blk0 * 8, bytes, &bars[stg]);
+            if (!planar) {
+                const uint64_t blk0 = imn->coef_base + ((uint64_t)tn.my * imn->mxx + tn.mx0) * BPM;
+                bulk_g2s(sdst, coef + blk0 * 8, bytes, &bars[stg]);
+            } else {
+                // V runs of n*H luma blocks (one per block row of the MCU row), then n Cb and n Cr blocks: block i of
+                // phase 1 lands in slot i
+                const uint32_t yb = (uint32_t)tn.n * H * 128, cb = (uint32_t)tn.n * 128;
+#pragma unroll
+                for (int vy = 0; vy < V; vy++) {
+                    const uint64_t b0 = imn->comp_base[0] + ((uint64_t)tn.my * V + vy) * (uint32_t)imn->comp_bw[0] + (uint64_t)tn.mx0 * H;
+                    bulk_g2s(sdst + vy * yb, coef + b0 * 8, yb, &bars[stg]);
+                }
+#pragma unroll
+                for (int cc = 1; cc <= 2; cc++) {
+                    const uint64_t b0 = imn->comp_base[cc] + (uint64_t)tn.my * (uint32_t)imn->comp_bw[cc] + tn.mx0;
+                    bulk_g2s(sdst + V * yb + (cc - 1) * cb, coef + b0 * 8, cb, &bars[stg]);
+                }
+            }
             TileCtx c;
+            c.planar = planar ? 1u : 0u;
             c.n = tn.n;
             c.mx0 = tn.mx0;
             c.my = tn.my;
@@ -150,7 +171,8 @@ __global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P)
             c.out_off = imn->out_off;
             c.nr = tn.pad & 0xffu ? tn.pad & 0xffu : 1u;
             c.wt = tn.pad >> 16 ? tn.pad >> 16 : tn.n;
-            c.wide = P.img_flags[imn->status_slot] & 1u;
+            // (progressive scans do not track the coefficient range: their frames always take the exact rows)
+            c.wide = (P.img_flags[imn->status_slot] & 1u) | (imn->progressive ? 1u : 0u);
             c.poff[0] = imn->plane_off[0];
             c.poff[1] = imn->plane_off[1];
             c.poff[2] = imn->plane_off[2];
@@ -224,7 +246,7 @@ __global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P)
                 const int vy = (V == 2 && i >= nH) ? 1 : 0;
                 const int bx = i - vy * nH;
                 const int m = bx / H, hx = bx % H;
-                slot = m * BPM + vy * H + hx;
+                slot = t.planar ? i : m * BPM + vy * H + hx;
                 bxa = (int)t.mx0 * H + bx;
                 dst = planeY + (vy * 8) * PY + bx * 8;
                 pitch = PY;
@@ -233,7 +255,7 @@ __global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P)
                 const int j = i - nY;
                 const int c = j >= n ? 1 : 0;
                 const int m = j - c * n;
-                slot = m * BPM + H * V + c;
+                slot = t.planar ? i : m * BPM + H * V + c;
                 bxa = (int)t.mx0 + m;
                 dst = (c ? planeCr : planeCb) + m * 8;
                 pitch = PC;
