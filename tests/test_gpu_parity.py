@@ -434,9 +434,46 @@ def _multiscan_cases():
 def test_multi_scan_sequential_frames(jpeg, ctx):
     """Sequential frames whose components arrive in separate scans (non-interleaved block order, restart
     intervals counted in the scan's own MCU iterations; decoder.zig:1294-1336).  Pillow cannot write
-    them: tools/multiscan.py re-codes single-scan files.  These take the planar coefficient layout and the
-    unfused reconstruction kernels."""
+    them: tools/multiscan.py re-codes single-scan files.  These take the planar coefficient layout (one block grid per
+    component), which the fused kernel gathers tile by tile."""
     _assert_same(jpeg, ctx, _multiscan_cases())
+
+
+def test_planar_layout_frames_fused_equal_generic_equal_oracle(jpeg, fixtures_dir):
+    """Frames that keep one block grid per component (multi-scan sequential, progressive) through the fused kernel
+    (default, RGBA output) and through the unfused kernels (ZPX_OPT_FORCE_GENERIC): both == oracle.  Every sampling
+    the fused kernel has, sizes with several tiles per MCU row and partial MCUs at the edges."""
+    import ctypes as C
+    from tools.multiscan import recode
+    from zpix_b200 import _lib as zl
+    datas = []
+    for n in ["video-001.q50.410.jpeg", "video-001.q50.411.jpeg", "video-001.q50.440.jpeg", "video-001.q50.444.jpeg",
+              "video-001.q50.422.jpeg", "video-001.q50.420.jpeg"]:
+        datas.append(recode(_read(fixtures_dir, n), [[0], [1], [2]], 0))
+        datas.append(recode(_read(fixtures_dir, n), [[2], [0, 1]], 0))
+    datas.append(recode(_read(fixtures_dir, "video-005.gray.q50.jpeg"), [[0]], 2))
+    for seed, (w, h), kw in [(61000, (1920, 136), dict(subsampling="4:2:0")), (61001, (1363, 77), dict(subsampling="4:2:2")),
+                             (61002, (1000, 40), dict(subsampling="4:4:4")), (61003, (1100, 33), dict(mode="L"))]:
+        datas.append(S.encode(seed, w, h, progressive=True, **kw))
+        datas.append(recode(S.encode(seed + 10, w, h, **kw), [[0]] if kw.get("mode") == "L" else [[0], [1], [2]], 0))
+    c1, c2 = jpeg.Context(), jpeg.Context()
+    c2.set_option(2, 1)
+    try:
+        for d in datas:  # the host parser's report: these frames are the fused kernel's
+            a8 = np.frombuffer(d, np.uint8)
+            inf, rep = zl.ZpxImageInfo(), zl.ZpxParseReport()
+            assert zl.lib.zpx_parse_report_of(a8.ctypes.data, a8.size, C.byref(inf), C.byref(rep)) == 0
+            assert rep.status == 0 and rep.fused == 1
+        _assert_same(jpeg, c1, datas)
+        a, sa, ta = _gpu_batch(jpeg, c1, datas)
+        b, sb, tb = _gpu_batch(jpeg, c2, datas)
+        assert sa == sb == [0] * len(datas)
+        assert ta["idct_fused_bytes"] > 0 and tb["idct_fused_bytes"] == 0
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    finally:
+        c1.close()
+        c2.close()
 
 
 def test_files_found_by_fuzzing(jpeg, ctx, golden_dir):

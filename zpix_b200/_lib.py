@@ -11,7 +11,7 @@ import os
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libzpixcuda.so")
+SO_PATH = os.environ.get("ZPX_LIB_PATH") or os.path.join(_HERE, "libzpixcuda.so")  # (override: kernel experiments)
 
 
 class ZpxImageInfo(C.Structure):

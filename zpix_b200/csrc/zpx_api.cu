@@ -908,7 +908,10 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         k2.ntiles = (int)g.tiles.size();
         k2.tmax = g.tmax;
         k2.dense_only = ctx->opt_k2_dense != 0;
-        k2.nt = std::max(96, (g.tmax * k2_fused_bpm(g.h, g.v, g.nc) + 31) / 32 * 32);
+        // at least four warps: phase 2 hands whole item rows to warps, eight row(-pair)s per MCU row (measured: 4:4:4
+        // tiles of 32 MCUs, 96 blocks, +3.6 % with a fourth warp that idles in phase 1); ZPX_K2_MIN_NT: experiments
+        static const int min_nt = getenv("ZPX_K2_MIN_NT") ? atoi(getenv("ZPX_K2_MIN_NT")) : 128;
+        k2.nt = std::max(std::max(96, min_nt), (g.tmax * k2_fused_bpm(g.h, g.v, g.nc) + 31) / 32 * 32);
         CU(ctx, k2_launch_fused(g.h, g.v, g.nc, k2, dc.sm_count, st));
         k2_launches++;
     }

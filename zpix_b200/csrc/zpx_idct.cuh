@@ -275,12 +275,42 @@ __device__ __forceinline__ uint32_t ycc_pixel(int y, int rr, int gg, int bb) {
     const int r = y * 0x10101 + rr, g = y * 0x10101 + gg, b = y * 0x10101 + bb;
     return pack4_sat_u8(r >> 16, g >> 16, b >> 16, 255);
 }
+// The same pixel with the ">> 16" of the first NW channels done by the multiplier: (y << 8) * (0x10101 << 8) + (t << 16)
+// as a 64-bit multiply-add is (y * 0x10101 + t) * 2^16 exactly (no 32-bit intermediate, |y * 0x10101 + t| < 2^31), whose
+// high word is floor((y * 0x10101 + t) / 2^16) == the reference's arithmetic shift.  One IMAD.WIDE (FMA pipe) instead
+// of IMAD + SHF (FMA + ALU pipe).  ZPX_YCC_WIDE selects how many channels take it (measured).
+#ifndef ZPX_YCC_WIDE
+#define ZPX_YCC_WIDE 0
+#endif
+__device__ __forceinline__ int madw_hi(int a, int b, long long c) {
+    long long d;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return (int)(d >> 32);
+}
+struct ChromaTerms {
+    int rr, gg, bb;
+    long long rr64, gg64, bb64;  // the terms << 16 (only the ones ZPX_YCC_WIDE uses are ever computed)
+};
+template <int NW>
+__device__ __forceinline__ uint32_t ycc_pixel_w(int y, const ChromaTerms& t) {
+    const int y8 = y << 8;
+    const int r = NW >= 1 ? madw_hi(y8, 0x10101 << 8, t.rr64) : (y * 0x10101 + t.rr) >> 16;
+    const int b = NW >= 2 ? madw_hi(y8, 0x10101 << 8, t.bb64) : (y * 0x10101 + t.bb) >> 16;
+    const int g = NW >= 3 ? madw_hi(y8, 0x10101 << 8, t.gg64) : (y * 0x10101 + t.gg) >> 16;
+    return pack4_sat_u8(r, g, b, 255);
+}
 // per-chroma-sample terms, shared by every luma pixel that replicates the sample
 // (cb - 128, cr - 128 of color.zig:92-93 multiplied out: the same integers, one multiply-add per term)
 __device__ __forceinline__ void chroma_terms(int cb, int cr, int& rr, int& gg, int& bb) {
     rr = 91881 * cr - 91881 * 128;
     gg = -22554 * cb + (-46802 * cr + (22554 + 46802) * 128);
     bb = 116130 * cb - 116130 * 128;
+}
+__device__ __forceinline__ void chroma_terms_w(int cb, int cr, ChromaTerms& t) {
+    chroma_terms(cb, cr, t.rr, t.gg, t.bb);
+    t.rr64 = (long long)t.rr << 16;
+    t.gg64 = (long long)t.gg << 16;
+    t.bb64 = (long long)t.bb << 16;
 }
 // CMYK -> RGBA8 (color.zig:115-121, then >>8).  c,m,y,k are the stored (already inverted) bytes.
 __device__ __forceinline__ uint32_t cmyk_pixel(uint32_t c, uint32_t m, uint32_t y, uint32_t k) {

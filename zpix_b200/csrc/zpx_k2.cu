@@ -347,15 +347,24 @@ __global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P)
             const bool vec_ok = (W & 3) == 0;
             if (t.interior) {
                 // tile entirely inside the image (all but the right / bottom edge tiles): no bounds tests, one
-                // 64-bit base address per tile, 32-bit offsets from it
+                // 64-bit base address per tile, 32-bit offsets from it.  A warp takes whole item rows (row = warp,
+                // warp + warps, ...; items lane, lane + 32, ... of it), so that an item's addresses are its row's
+                // plus constant steps: no division of an item index by the row length.
                 uint8_t* __restrict__ ob = outp + ((size_t)y0 * (size_t)W + (size_t)x0) * 4u;
                 const uint32_t rowb = (uint32_t)W * 4u;
-                for (int it = tid; it < items; it += NT) {
-                    const uint32_t rp = ipr > 1 ? __umulhi((uint32_t)it, magic) : (uint32_t)it;
-                    const uint32_t xg = (uint32_t)it - rp * (uint32_t)ipr;
-                    int rr[NCS], gg[NCS], bb[NCS];
+                const int nrp = (NC == 1 ? (int)t.nr * 8 : Cfg::YROWS) / RP;
+                const int lane = tid & 31;
+                for (int rp = tid >> 5; rp < nrp; rp += NT >> 5) {
+                    const uint8_t* const yrow = planeY + (uint32_t)rp * (uint32_t)(RP * PYt);
+                    const uint32_t crow = (uint32_t)rp * (uint32_t)(V == 2 ? 1 : RP) * (uint32_t)PC;
+                    uint8_t* const orow = ob + (uint32_t)rp * (uint32_t)RP * rowb;
+                    // (explicit induction variables: the addresses of item xg + 32 are those of item xg plus constants)
+                    const uint8_t* yp = yrow + PXW * lane;
+                    uint32_t coff = crow + (uint32_t)(PXW * lane) / H;
+                    uint8_t* o = orow + (uint32_t)lane * (uint32_t)(PXW * 4);
+                    for (int xg = lane; xg < ipr; xg += 32, yp += 32 * PXW, coff += 32 * PXW / H, o += 32 * PXW * 4) {
+                    ChromaTerms ct[NCS];
                     if (NC == 3) {
-                        const uint32_t coff = rp * (uint32_t)(V == 2 ? 1 : RP) * (uint32_t)PC + (PXW * xg) / H;
                         uint32_t cbw[2] = {0, 0}, crw[2] = {0, 0};
                         if (NCS == 8) {
                             const uint2 a2 = *reinterpret_cast<const uint2*>(planeCb + coff), b2 = *reinterpret_cast<const uint2*>(planeCr + coff);
@@ -372,11 +381,8 @@ __global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P)
                         }
 #pragma unroll
                         for (int k = 0; k < NCS; k++)
-                            chroma_terms((int)__byte_perm(cbw[k >> 2], 0, 0x4440 + (k & 3)), (int)__byte_perm(crw[k >> 2], 0, 0x4440 + (k & 3)),
-                                         rr[k], gg[k], bb[k]);
+                            chroma_terms_w((int)__byte_perm(cbw[k >> 2], 0, 0x4440 + (k & 3)), (int)__byte_perm(crw[k >> 2], 0, 0x4440 + (k & 3)), ct[k]);
                     }
-                    const uint8_t* yp = planeY + rp * (uint32_t)(RP * PYt) + PXW * xg;
-                    uint8_t* o = ob + (rp * (uint32_t)RP * rowb + xg * (uint32_t)(PXW * 4));
 #pragma unroll
                     for (int r = 0; r < RP; r++) {
 #pragma unroll
@@ -389,12 +395,12 @@ __global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P)
                                 if (NC == 1) {
                                     p[j] = yv * 0x010101u | 0xff000000u;
                                 } else {
-                                    const int ci = (4 * g + j) / H;
-                                    p[j] = ycc_pixel((int)yv, rr[ci], gg[ci], bb[ci]);
+                                    p[j] = ycc_pixel_w<ZPX_YCC_WIDE>((int)yv, ct[(4 * g + j) / H]);
                                 }
                             }
                             __stcs(reinterpret_cast<uint4*>(o + (uint32_t)r * rowb) + g, make_uint4(p[0], p[1], p[2], p[3]));
                         }
+                    }
                     }
                 }
             } else
