@@ -13,10 +13,10 @@ from zpix_b200 import jpeg  # noqa: E402
 
 CACHE = os.environ.get("ZPX_SYNTH_CACHE", "/tmp/zpx_synth")
 ctx = jpeg.Context([0])
-work = [("cfg2 420", S.make_batch(2, 32, 1920, 1080, cache_dir=CACHE, subsampling="4:2:0", restart_rows=1), 256),
-        ("444 512", S.make_batch(3, 32, 512, 512, cache_dir=CACHE, first=5000, mode="YCbCr", subsampling="4:4:4"), 1024),
-        ("gray 512", S.make_batch(3, 32, 512, 512, cache_dir=CACHE, mode="L"), 1024),
-        ("422 2160", S.make_batch(4, 16, 3840, 2160, cache_dir=CACHE, mode="YCbCr", subsampling="4:2:2", restart_rows=1), 64)]
+work = [("cfg2 420", S.make_batch(2, 32, 1920, 1080, cache_dir=CACHE, subsampling="4:2:0", restart_rows=1), 512),
+        ("444 512", S.make_batch(3, 32, 512, 512, cache_dir=CACHE, first=5000, mode="YCbCr", subsampling="4:4:4"), 2048),
+        ("gray 512", S.make_batch(3, 32, 512, 512, cache_dir=CACHE, mode="L"), 2048),
+        ("422 2160", S.make_batch(4, 16, 3840, 2160, cache_dir=CACHE, mode="YCbCr", subsampling="4:2:2", restart_rows=1), 256)]
 for name, base, n in work:
     datas = [base[i % len(base)] for i in range(n)]
     with jpeg.Batch(ctx, datas) as b:

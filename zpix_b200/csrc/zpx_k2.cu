@@ -345,7 +345,11 @@ __global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P)
             const uint32_t magic = t.magic;  // 2^32 / ipr + 1: exact it / ipr for it, ipr < 2^16
             uint8_t* __restrict__ outp = P.out + t.out_off;
             const bool vec_ok = (W & 3) == 0;
-            if (t.interior) {
+            // interior tiles, two mappings of items to threads (measured on B200, same box, K2 time): gray -2.7 % with
+            // whole item rows per warp (no index division, constant address steps: 15 % fewer instructions per item);
+            // colour 0 % (4:2:0) to +2.6 % (4:2:2, 4:4:4) that way, so colour keeps the flat item index
+            constexpr bool P2_ROWS = NC == 1;
+            if (t.interior && P2_ROWS) {
                 // tile entirely inside the image (all but the right / bottom edge tiles): no bounds tests, one
                 // 64-bit base address per tile, 32-bit offsets from it.  A warp takes whole item rows (row = warp,
                 // warp + warps, ...; items lane, lane + 32, ... of it), so that an item's addresses are its row's
@@ -401,6 +405,58 @@ __global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P)
                             __stcs(reinterpret_cast<uint4*>(o + (uint32_t)r * rowb) + g, make_uint4(p[0], p[1], p[2], p[3]));
                         }
                     }
+                    }
+                }
+            } else if (t.interior) {
+                // tile entirely inside the image (all but the right / bottom edge tiles): no bounds tests, one
+                // 64-bit base address per tile, 32-bit offsets from it
+                uint8_t* __restrict__ ob = outp + ((size_t)y0 * (size_t)W + (size_t)x0) * 4u;
+                const uint32_t rowb = (uint32_t)W * 4u;
+                for (int it = tid; it < items; it += NT) {
+                    const uint32_t rp = ipr > 1 ? __umulhi((uint32_t)it, magic) : (uint32_t)it;
+                    const uint32_t xg = (uint32_t)it - rp * (uint32_t)ipr;
+                    int rr[NCS], gg[NCS], bb[NCS];
+                    if (NC == 3) {
+                        const uint32_t coff = rp * (uint32_t)(V == 2 ? 1 : RP) * (uint32_t)PC + (PXW * xg) / H;
+                        uint32_t cbw[2] = {0, 0}, crw[2] = {0, 0};
+                        if (NCS == 8) {
+                            const uint2 a2 = *reinterpret_cast<const uint2*>(planeCb + coff), b2 = *reinterpret_cast<const uint2*>(planeCr + coff);
+                            cbw[0] = a2.x; cbw[1] = a2.y; crw[0] = b2.x; crw[1] = b2.y;
+                        } else if (NCS == 4) {
+                            cbw[0] = *reinterpret_cast<const uint32_t*>(planeCb + coff);
+                            crw[0] = *reinterpret_cast<const uint32_t*>(planeCr + coff);
+                        } else if (NCS == 2) {
+                            cbw[0] = *reinterpret_cast<const uint16_t*>(planeCb + coff);
+                            crw[0] = *reinterpret_cast<const uint16_t*>(planeCr + coff);
+                        } else {
+                            cbw[0] = planeCb[coff];
+                            crw[0] = planeCr[coff];
+                        }
+#pragma unroll
+                        for (int k = 0; k < NCS; k++)
+                            chroma_terms((int)__byte_perm(cbw[k >> 2], 0, 0x4440 + (k & 3)), (int)__byte_perm(crw[k >> 2], 0, 0x4440 + (k & 3)),
+                                         rr[k], gg[k], bb[k]);
+                    }
+                    const uint8_t* yp = planeY + rp * (uint32_t)(RP * PYt) + PXW * xg;
+                    uint8_t* o = ob + (rp * (uint32_t)RP * rowb + xg * (uint32_t)(PXW * 4));
+#pragma unroll
+                    for (int r = 0; r < RP; r++) {
+#pragma unroll
+                        for (int g = 0; g < PXW / 4; g++) {
+                            const uint32_t yw = *reinterpret_cast<const uint32_t*>(yp + r * PYt + 4 * g);
+                            uint32_t p[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const uint32_t yv = __byte_perm(yw, 0, 0x4440 + j);
+                                if (NC == 1) {
+                                    p[j] = yv * 0x010101u | 0xff000000u;
+                                } else {
+                                    const int ci = (4 * g + j) / H;
+                                    p[j] = ycc_pixel((int)yv, rr[ci], gg[ci], bb[ci]);
+                                }
+                            }
+                            __stcs(reinterpret_cast<uint4*>(o + (uint32_t)r * rowb) + g, make_uint4(p[0], p[1], p[2], p[3]));
+                        }
                     }
                 }
             } else
