@@ -20,7 +20,19 @@
 #include "zpx_internal.h"
 #include "zpx_kernels.h"
 
+// resident threads per SM the fused kernel is compiled for (register cap = 65536 / that).  Measured on one B200
+// (tools/k2_variants.sh, K2 time, 512 / 640 / 768): 4:2:0 1.72 / 1.72 / 1.87 ms, 4:4:4 1.54 / 1.63 / 1.59, 4:2:2 4.19 /
+// 4.34 / 4.78, gray 0.600 / 0.573 / 0.868 -- colour stays at 512 (126 registers, no spills), gray takes 640 (102).
+#ifndef ZPX_K2_THREADS_PER_SM
+#define ZPX_K2_THREADS_PER_SM 512
+#endif
+#ifndef ZPX_K2_THREADS_PER_SM_GRAY
+#define ZPX_K2_THREADS_PER_SM_GRAY 640
+#endif
+
 namespace zpx {
+
+__host__ __device__ constexpr int k2_threads_per_sm(int nc) { return nc == 1 ? ZPX_K2_THREADS_PER_SM_GRAY : ZPX_K2_THREADS_PER_SM; }
 
 // ---------------------------------------------------------------------------
 // mbarrier / bulk-copy (TMA unit, non-tensor form) helpers
@@ -85,7 +97,7 @@ struct K2Cfg {
 // NTMAX bounds the registers (512 threads per SM); the launch uses as many threads as the group's largest tile has
 // blocks (K2Params::nt, a multiple of 32), so that phase 1 leaves no thread without a block.
 template <int H, int V, int NC, int NS, int NTMAX>
-__global__ void __launch_bounds__(NTMAX, 512 / NTMAX) k2_fused(const K2Params P) {
+__global__ void __launch_bounds__(NTMAX, k2_threads_per_sm(NC) / NTMAX) k2_fused(const K2Params P) {
     const int NT = (int)blockDim.x;
     using Cfg = K2Cfg<H, V, NC>;
     constexpr int BPM = Cfg::BPM;
@@ -548,8 +560,8 @@ static cudaError_t launch_fused_ns(const K2Params& P, int sms, cudaStream_t s) {
 template <int H, int V, int NC>
 static cudaError_t launch_fused_t(const K2Params& P, int sms, cudaStream_t s) {
     using Cfg = K2Cfg<H, V, NC>;
-    constexpr int NT = (NC == 3 && H == 2 && V == 2) ? 256 : 128;  // == k2_fused_threads(H, V, NC)
-    if ((512 / NT) * (Cfg::smem_bytes(P.tmax, 3) + 1024) <= 227 * 1024) return launch_fused_ns<H, V, NC, 3, NT>(P, sms, s);
+    constexpr int NT = (NC == 3 && H == 2 && V == 2) ? ZPX_K2_420_THREADS : 128;  // == k2_fused_threads(H, V, NC)
+    if ((k2_threads_per_sm(NC) / NT) * (Cfg::smem_bytes(P.tmax, 3) + 1024) <= 227 * 1024) return launch_fused_ns<H, V, NC, 3, NT>(P, sms, s);
     return launch_fused_ns<H, V, NC, 2, NT>(P, sms, s);
 }
 

@@ -67,7 +67,10 @@ cudaError_t k3l_launch_refine_apply(const K1Params& P, const uint32_t* list, int
 // Threads per CTA of the fused kernel (= blocks a tile can hold) for a sampling; 512 / threads CTAs are resident
 // per SM.  Measured on B200: 4:2:0 is 1 % faster with 256-thread CTAs (tiles of 40 MCUs fill 240 of them), every
 // other sampling 4-9 % faster with 128 (4:2:2 3.69 -> 3.84 TB/s, gray + 4:4:4 512x512 3.30 -> 3.62 TB/s).
-static inline int k2_fused_threads(int h, int v, int nc) { return (nc == 3 && h == 2 && v == 2) ? 256 : 128; }
+#ifndef ZPX_K2_420_THREADS
+#define ZPX_K2_420_THREADS 256
+#endif
+static inline int k2_fused_threads(int h, int v, int nc) { return (nc == 3 && h == 2 && v == 2) ? ZPX_K2_420_THREADS : 128; }
 
 struct K2Params {
     const int16_t* coef;
