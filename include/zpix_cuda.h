@@ -205,8 +205,9 @@ int32_t zpx_batch_decode(zpx_batch *b, void *stream);
  * (= 4*width).  status receives the final per-image status (may be NULL). */
 int32_t zpx_batch_fetch_rgba(zpx_batch *b, uint8_t *const *out, const size_t *out_stride, int32_t *status);
 /* Copy the native variant's .pixels buffer (exact layout of the Image jpeg.load
- * returns: MCU-padded Gray / planar YCbCr, or 4*W*H RGBA / CMYK).  Images that took the fused kernel have planes
- * only if the batch was opened with ZPX_OPT_NATIVE_PLANES != 0 (else their status becomes ZPX_E_UNSUPPORTED_STREAM). */
+ * returns: MCU-padded Gray / planar YCbCr, or 4*W*H RGBA / CMYK).  Works after any decode: images that took the fused
+ * kernel without ZPX_OPT_NATIVE_PLANES get their planes reconstructed now, from the coefficients still resident on the
+ * device (one more IDCT pass; open the batch with ZPX_OPT_NATIVE_PLANES = 1 or 2 to have the fused kernel write them). */
 int32_t zpx_batch_fetch_native(zpx_batch *b, uint8_t *const *out, int32_t *status);
 /* Final per-image status after decode (header errors, device-detected entropy errors). */
 int32_t zpx_batch_status(zpx_batch *b, int32_t *status);
@@ -284,7 +285,8 @@ int32_t zpx_partition(const uint64_t *weights, int32_t n, int32_t n_devices, int
                                     28 MB of compressed input per chunk; < 0 = off) */
 #define ZPX_OPT_PIPELINE_RAMP 6  /* 1 (default): the pipeline's first two chunks are 1/4 and 1/2 of the chunk size */
 #define ZPX_OPT_PIPELINE_WORKERS 7 /* host threads (each with its own device buffers) of that pipeline: 1..8, default 3 */
-#define ZPX_OPT_NATIVE_PLANES 9 /* 0 (default): native planes exist only for images on the unfused kernels;
+#define ZPX_OPT_NATIVE_PLANES 9 /* 0 (default): the decode writes native planes only for images on the unfused kernels
+                                   (zpx_batch_fetch_native makes the others on demand);
                                    1: the fused kernel writes them too, beside the RGBA (zpx_batch_fetch_native works
                                    for every image); 2: planes only, no RGBA.  Read when a batch is opened. */
 #define ZPX_OPT_PROGRESSIVE_MODE 10 /* 0 (default): progressive frames whose scan script is an ordinary successive

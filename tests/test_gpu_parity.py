@@ -193,6 +193,15 @@ def test_synthetic_shapes(jpeg, ctx):
     _assert_same(jpeg, ctx, datas, names)
 
 
+def test_wide_gray_rows_cut_into_several_tiles(jpeg, ctx):
+    """gray images wider than one tile of the fused kernel (128 blocks): the tiles of a row start at block columns
+    that are not multiples of eight (the coefficient rows' swizzle key is the ABSOLUTE column) -- found by the
+    planar-layout test of round 2: 1100 px = 138 blocks = 2 tiles of 69"""
+    datas = [S.encode(62000 + i, w, h, mode="L", restart_rows=rr) for i, (w, h, rr) in
+             enumerate([(1100, 33, 0), (1100, 40, 1), (2056, 24, 0), (3000, 17, 1), (1032, 64, 0), (4099, 9, 0)])]
+    _assert_same(jpeg, ctx, datas)
+
+
 def test_cfg2_sample(jpeg, ctx):
     """BASELINE.json configs[1] at reduced count: 1920x1080 4:2:0, DRI = one MCU row."""
     datas = S.make_batch(2, 16, 1920, 1080, subsampling="4:2:0", restart_rows=1)
@@ -540,6 +549,37 @@ def test_native_variant_matches_reference_planes(jpeg, fixtures_dir):
             assert np.array_equal(m.cb.reshape(-1, m.c_stride), ref.cb)
             assert np.array_equal(m.cr.reshape(-1, m.c_stride), ref.cr)
         assert np.array_equal(img.rgbaPixels().reshape(ref.height, ref.width, 4), ref.rgbaPixels())
+
+
+def test_native_planes_on_demand_after_a_fused_decode(jpeg, ctx, fixtures_dir):
+    """zpx_batch_fetch_native after a plain decode (ZPX_OPT_NATIVE_PLANES = 0): the RGBA came from the fused kernel, the
+    planes of those images are reconstructed when asked for, from the resident coefficients: Image.pixels byte for byte
+    (whole planes, MCU padding and the reference's never-reconstructed blocks included); a second fetch reuses them."""
+    from tools.multiscan import recode
+    names = ["video-001.q50.420.jpeg", "video-001.q50.422.jpeg", "video-001.q50.444.jpeg", "video-001.q50.411.jpeg",
+             "video-005.gray.jpeg", "video-001.221212.jpeg", "video-001.cmyk.jpeg", "video-001.rgb.jpeg",
+             "video-001.q50.420.progressive.jpeg", "video-005.gray.q50.progressive.jpeg", "video-001.restart2.jpeg"]
+    datas = [_read(fixtures_dir, n) for n in names]
+    datas.append(recode(S.encode(60010, 97, 75, subsampling="4:2:0"), [[0], [1], [2]], 0))
+    datas += S.make_batch(2, 2, 1920, 1080, subsampling="4:2:0", restart_rows=1)
+    refs = [O.decode(d) for d in datas]
+    with jpeg.Batch(ctx, datas) as b:
+        b.upload()
+        b.decode()
+        launches = ctx.kernel_launches
+        for attempt in range(2):
+            nat, st = b.fetch_native()
+            assert st == [0] * len(datas)
+            for i, (got, ref) in enumerate(zip(nat, refs)):
+                assert got.size == ref.pixels.size and np.array_equal(got, ref.pixels), (i, attempt)
+            if attempt == 0:
+                assert ctx.kernel_launches > launches  # the planes were made now ...
+                launches = ctx.kernel_launches
+            else:
+                assert ctx.kernel_launches == launches + 1  # ... and only the CMYK interleave runs again
+        outs, st = b.fetch_rgba()
+        for o, ref in zip(outs, refs):
+            assert np.array_equal(o.reshape(-1), ref.rgbaPixels().reshape(-1))
 
 
 def test_native_cmyk_variant(jpeg, fixtures_dir):

@@ -121,6 +121,7 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr};
     DevBuf blob, ublob, coef, out, planes, desc, status, subs, scratch;
+    DevBuf planes_late, late_list;  // native planes of fused images, made on demand (zpx_batch_fetch_native)
     HostBuf stage, hdesc, hstatus, hflag;
 };
 
@@ -173,6 +174,12 @@ struct DevicePlan {
     std::vector<uint32_t> inject_flags;         // test hook (zpx_batch_set_coefficients): per image, copied over img_flags
     zpx_timing timing;
     bool uploaded = false, decoded = false;
+    // fused images whose planes nobody asked for at open time (ZPX_OPT_NATIVE_PLANES = 0): laid out in a buffer of their
+    // own, reconstructed by the unfused IDCT kernel the first time zpx_batch_fetch_native wants them
+    std::vector<uint32_t> late;
+    size_t late_plane_bytes = 0;
+    int late_max_blocks = 0;
+    bool late_done = false;
     int native = 0;  // ZPX_OPT_NATIVE_PLANES at the time the plan was built
 };
 
@@ -393,11 +400,13 @@ void build_plan(zpx_batch* b, int di) {
         pl.out_off.push_back(pl.out_bytes);
         pl.out_bytes += align_up((size_t)4 * p.width * p.height, 256);
         // native planes (generic path): exact makeImg layout: Y, Cb, Cr contiguous, then black
-        pl.plane_off0.push_back(pl.plane_bytes);
-        if (!im.fused || pl.native != 0) {
+        {
+            const bool late = im.fused && pl.native == 0;  // planes on demand, in dc.planes_late
+            size_t& total = late ? pl.late_plane_bytes : pl.plane_bytes;
+            pl.plane_off0.push_back(total);
             zpx_image_info info;
             zpx_fill_info(p, &info);
-            size_t base = pl.plane_bytes;
+            size_t base = total;
             if (p.ncomp == 1) {
                 im.plane_off[0] = base;
                 im.plane_stride[0] = 8 * p.mxx;
@@ -421,7 +430,11 @@ void build_plan(zpx_batch* b, int di) {
                     base += (size_t)im.plane_stride[3] * im.plane_rows[3];
                 }
             }
-            pl.plane_bytes = align_up(base, 256);
+            total = align_up(base, 256);
+            if (late) {
+                pl.late.push_back((uint32_t)k);
+                pl.late_max_blocks = std::max<int>(pl.late_max_blocks, (int)nblocks);
+            }
         }
         if (!im.fused) {
             pl.generic.push_back((uint32_t)k);
@@ -937,6 +950,7 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
     pl.timing.entropy_launches = k1_launches;
     pl.timing.idct_launches = k2_launches;
     pl.decoded = true;
+    pl.late_done = false;
     return ZPX_OK;
 }
 
@@ -1152,6 +1166,8 @@ void zpx_ctx_destroy(zpx_ctx* c) {
         d.status.release();
         d.subs.release();
         d.scratch.release();
+        d.planes_late.release();
+        d.late_list.release();
         d.hflag.release();
         d.stage.release();
         d.hdesc.release();
@@ -1494,6 +1510,28 @@ int32_t zpx_batch_fetch_native(zpx_batch* b, uint8_t* const* out, int32_t* statu
         DeviceCtx& dc = ctx->devs[di];
         CU(ctx, cudaSetDevice(dc.dev));
         CU(ctx, after_decode(dc));
+        // planes of fused images that were decoded without ZPX_OPT_NATIVE_PLANES: the coefficients are still resident,
+        // the unfused IDCT kernel writes the planes now (makeImg's layout, zeros where the reference reconstructs nothing)
+        bool want_late = false;
+        for (uint32_t k : pl.late) want_late = want_late || (out[pl.images[k]] && b->status[pl.images[k]] == 0);
+        if (want_late && !pl.late_done) {
+            CU(ctx, dc.planes_late.ensure(pl.late_plane_bytes + 256));
+            CU(ctx, dc.late_list.ensure(pl.late.size() * sizeof(uint32_t)));
+            CU(ctx, cudaMemsetAsync(dc.planes_late.p, 0, pl.late_plane_bytes, dc.stream));
+            CU(ctx, cudaMemcpyAsync(dc.late_list.p, pl.late.data(), pl.late.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, dc.stream));
+            K2GParams kg{};
+            kg.coef = (const int16_t*)dc.coef.p;
+            kg.planes = (uint8_t*)dc.planes_late.p;
+            kg.imgs = (const ZpxImageDev*)((const uint8_t*)dc.desc.p + pl.off_imgs);
+            kg.quant = (const ZpxQuantDev*)((const uint8_t*)dc.desc.p + pl.off_quant);
+            const int total = (int)pl.late.size();
+            for (int i0 = 0; i0 < total; i0 += 32768) {
+                kg.list = (const uint32_t*)dc.late_list.p + i0;
+                CU(ctx, k2g_launch_planes(kg, std::min(32768, total - i0), pl.late_max_blocks, dc.stream));
+                ctx->launches++;
+            }
+            pl.late_done = true;
+        }
         CU(ctx, cudaEventRecord(dc.ev[6], dc.stream));
         size_t k = 0;
         while (k < pl.images.size()) {
@@ -1503,12 +1541,9 @@ int32_t zpx_batch_fetch_native(zpx_batch* b, uint8_t* const* out, int32_t* statu
             if (!out[i] || b->status[i] != 0) { k++; continue; }
             zpx_image_info info;
             zpx_fill_info(p, &info);
+            const bool late = im.fused && pl.native == 0;
             if (p.variant == ZPX_VARIANT_RGBA) {
                 CU(ctx, cudaMemcpyAsync(out[i], (const uint8_t*)dc.out.p + im.out_off, info.native_len, cudaMemcpyDeviceToHost, dc.stream));
-                k++;
-            } else if (im.fused && pl.native == 0) {
-                // the fused kernel keeps its planes in shared memory unless ZPX_OPT_NATIVE_PLANES asked for them
-                b->status[i] = ZPX_E_UNSUPPORTED_STREAM;
                 k++;
             } else if (p.variant == ZPX_VARIANT_CMYK) {
                 // Image{.CMYK}: applyBlack's interleave, built from the planes on demand (4-component frames
@@ -1531,14 +1566,14 @@ int32_t zpx_batch_fetch_native(zpx_batch* b, uint8_t* const* out, int32_t* statu
                     const ZpxImageDev& imj = pl.imgs[k2];
                     if (!out[j] || b->status[j] != 0) break;
                     if (pj.variant != ZPX_VARIANT_GRAY && pj.variant != ZPX_VARIANT_YCBCR) break;
-                    if (imj.fused && pl.native == 0) break;
+                    if ((imj.fused && pl.native == 0) != late) break;
                     if (imj.plane_off[0] != im.plane_off[0] + run || out[j] != out[i] + run) break;
                     zpx_image_info ij;
                     zpx_fill_info(pj, &ij);
                     run += ij.native_len;
                     k2++;
                 }
-                CU(ctx, cudaMemcpyAsync(out[i], (const uint8_t*)dc.planes.p + im.plane_off[0], run, cudaMemcpyDeviceToHost, dc.stream));
+                CU(ctx, cudaMemcpyAsync(out[i], (const uint8_t*)(late ? dc.planes_late.p : dc.planes.p) + im.plane_off[0], run, cudaMemcpyDeviceToHost, dc.stream));
                 k = k2;
             }
         }
@@ -1706,7 +1741,11 @@ int32_t zpx_batch_set_coefficients(zpx_batch* b, int32_t i, const int16_t* block
     }
     CU(ctx, cudaSetDevice(dc.dev));
     CU(ctx, cudaStreamSynchronize(dc.stream));
-    CU(ctx, cudaMemcpy((uint8_t*)dc.coef.p + im.coef_base * 128, sw.data(), nb * 128, cudaMemcpyHostToDevice));
+    // (on the context's stream and waited for: a plain cudaMemcpy from pageable memory returns once the bytes are
+    // staged, and nothing orders its DMA before kernels on the non-blocking streams the decode uses -- seen as a rare
+    // stale-coefficient mismatch in the block tests)
+    CU(ctx, cudaMemcpyAsync((uint8_t*)dc.coef.p + im.coef_base * 128, sw.data(), nb * 128, cudaMemcpyHostToDevice, dc.stream));
+    CU(ctx, cudaStreamSynchronize(dc.stream));
     if (pl.inject_flags.size() != pl.imgs.size()) pl.inject_flags.assign(pl.imgs.size(), 0);
     pl.inject_flags[b->slot_of[i]] = wide ? 1u : 0u;
     return ZPX_OK;

@@ -165,7 +165,7 @@ struct ZpxWarpDev {
 };
 
 // K2 tile: a run of MCUs inside one MCU row of one image.
-struct ZpxTileDev {
+struct alignas(16) ZpxTileDev {  // (one 128-bit load)
     uint32_t img;
     uint16_t my;
     uint16_t n;      // MCUs in tile

@@ -144,12 +144,18 @@ __global__ void __launch_bounds__(NTMAX, k2_threads_per_sm(NC) / NTMAX) k2_fused
     __shared__ TileCtx ctx[NS];
     __shared__ __align__(16) uint32_t qsm[NS][3 * 32];  // per row four words q[2j] | q[2j+1] << 24 (dp2a operands)
 
-    // issue the bulk copy of one tile into a stage and publish its context (thread 0);
-    // threads < 32*NC stage the image's quantisers when the image changes
+    // issue the bulk copy of one tile into a stage, publish its context and stage the image's quantisers when the
+    // image changes.  One warp does all of it: the image descriptor, its flags and the quantisers are dependent
+    // global loads (about a thousand cycles before the copy can be issued), and the warp that waits for them reaches
+    // the barrier after phase 1 that much later, with every other warp waiting there (ncu: 16 % of the warp samples
+    // sit at that barrier).  A tile's threads are ordered luma, Cb, Cr, so the LAST warp holds chroma blocks (sparse
+    // IDCT), is only partly filled, or has no block at all (4:4:4 tiles of 96 blocks in a 128-thread CTA): it has the
+    // slack.  Measured (K2 time, same box): 4:4:4 -7 %, 4:2:2 -3.8 %; 4:2:0 +4 % and gray +2 %, which keep warp 0.
     int pf_img = -1;  // image whose quantisers were staged last (uniform)
+    const int ftid = (NC == 3 && !(H == 2 && V == 2)) ? NT - 32 : 0;  // first thread of the fetching warp
     auto fetch = [&](const ZpxTileDev tn, int stg) {
         const ZpxImageDev* __restrict__ imn = &P.imgs[tn.img];
-        if (tid == 0) {
+        if (tid == ftid) {
             const uint32_t bytes = (uint32_t)tn.n * BPM * 128;
             const bool planar = NC == 3 && imn->layout == ZPX_LAYOUT_PLANAR;
             uint8_t* const sdst = stage0 + (size_t)stg * stage_bytes;
@@ -199,26 +205,43 @@ __global__ void __launch_bounds__(NTMAX, k2_threads_per_sm(NC) / NTMAX) k2_fused
             }
             ctx[stg] = c;
         }
-        if (tid < 32 * NC) {
+        if (tid >= ftid && tid < ftid + 32) {
             // (every stage keeps its own copy: a later tile of another image must not disturb it)
-            const int c = tid >> 5, k = tid & 31;
+            const int k = tid & 31;
             if ((int)tn.img != pf_img) {
-                const int* q = P.quant[imn->qidx[c]].q;
-                qsm[stg][c * 32 + k] = (uint32_t)q[2 * k] | (uint32_t)q[2 * k + 1] << 24;
+                const int* qp[NC];
+#pragma unroll
+                for (int c = 0; c < NC; c++) qp[c] = P.quant[imn->qidx[c]].q;
+                int2 qv[NC];
+#pragma unroll
+                for (int c = 0; c < NC; c++) qv[c] = __ldg(reinterpret_cast<const int2*>(qp[c]) + k);  // all loads in flight together
+#pragma unroll
+                for (int c = 0; c < NC; c++) qsm[stg][c * 32 + k] = (uint32_t)qv[c].x | (uint32_t)qv[c].y << 24;
             } else {
                 const int prev = stg == 0 ? NS - 1 : stg - 1;
-                qsm[stg][c * 32 + k] = qsm[prev][c * 32 + k];
+#pragma unroll
+                for (int c = 0; c < NC; c++) qsm[stg][c * 32 + k] = qsm[prev][c * 32 + k];
             }
         }
         pf_img = (int)tn.img;
     };
+    auto load_tile = [&](int i) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.tiles) + i);
+        ZpxTileDev t;
+        t.img = v.x;
+        t.my = (uint16_t)(v.y & 0xffffu);
+        t.n = (uint16_t)(v.y >> 16);
+        t.mx0 = v.z;
+        t.pad = v.w;
+        return t;
+    };
     // prologue: the first NS-1 tiles of this CTA
     for (int i = 0; i < NS - 1; i++) {
-        if (tile + i * (int)gridDim.x < P.ntiles) fetch(P.tiles[tile + i * (int)gridDim.x], i);
+        if (tile + i * (int)gridDim.x < P.ntiles) fetch(load_tile(tile + i * (int)gridDim.x), i);
         __syncthreads();  // the copy of qsm[prev] above must see the previous stage's values
     }
     // descriptor of the tile to prefetch next, loaded one iteration early (its latency is hidden)
-    ZpxTileDev tn_pf = P.tiles[min(tile + (NS - 1) * (int)gridDim.x, P.ntiles - 1)];
+    ZpxTileDev tn_pf = load_tile(min(tile + (NS - 1) * (int)gridDim.x, P.ntiles - 1));
 
     uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
     int stage = 0;
@@ -228,7 +251,7 @@ __global__ void __launch_bounds__(NTMAX, k2_threads_per_sm(NC) / NTMAX) k2_fused
             const int ahead = tile + (NS - 1) * (int)gridDim.x;
             const int stg = stage == 0 ? NS - 1 : stage - 1;
             if (ahead < P.ntiles) fetch(tn_pf, stg);
-            tn_pf = P.tiles[min(ahead + (int)gridDim.x, P.ntiles - 1)];
+            tn_pf = load_tile(min(ahead + (int)gridDim.x, P.ntiles - 1));
         }
 
         mbar_wait(&bars[stage], (phase_bits >> stage) & 1u);
@@ -249,7 +272,7 @@ __global__ void __launch_bounds__(NTMAX, k2_threads_per_sm(NC) / NTMAX) k2_fused
                 const int wt = (int)t.wt;
                 const int r = i / wt, col = i - r * wt;
                 slot = i;
-                bxa = col;
+                bxa = (int)t.mx0 + col;  // (absolute: a wide gray row is cut into tiles that need not start at a multiple of 8)
                 pitch = wt * 8 + 16;
                 dst = planeY + (r * 8) * pitch + col * 8;
                 q = qs_t;
@@ -742,6 +765,14 @@ __global__ void __launch_bounds__(256) k2_test_colour(const int mode, const uint
 cudaError_t k2_launch_test_colour(int mode, const uint8_t* samples, size_t n, uint8_t* rgba, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     k2_test_colour<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mode, samples, n, reinterpret_cast<uint32_t*>(rgba));
+    return cudaGetLastError();
+}
+
+// the IDCT half alone: native planes of the listed images (zpx_batch_fetch_native after a fused decode)
+cudaError_t k2g_launch_planes(const K2GParams& P, int n_list, int max_blocks, cudaStream_t s) {
+    if (n_list <= 0) return cudaSuccess;
+    dim3 g1((max_blocks + 127) / 128, n_list);
+    k2g_idct_planes<<<g1, 128, 0, s>>>(P);
     return cudaGetLastError();
 }
 

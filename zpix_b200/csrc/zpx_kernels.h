@@ -99,6 +99,7 @@ struct K2GParams {
     const uint32_t* list;  // image indices taking this path
 };
 cudaError_t k2g_launch(const K2GParams& P, int n_list, int max_blocks, size_t max_pixels, cudaStream_t s);
+cudaError_t k2g_launch_planes(const K2GParams& P, int n_list, int max_blocks, cudaStream_t s);  // planes only
 // Image{.CMYK} pixels (applyBlack's result) of one 4-component image into dst (4*W*H bytes, device)
 cudaError_t k2g_launch_cmyk_native(const K2GParams& P, uint32_t img, size_t pixels, uint8_t* dst, cudaStream_t s);
 
