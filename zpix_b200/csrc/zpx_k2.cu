@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(NTMAX, k2_threads_per_sm(NC) / NTMAX) k2_fused
     // IDCT), is only partly filled, or has no block at all (4:4:4 tiles of 96 blocks in a 128-thread CTA): it has the
     // slack.  Measured (K2 time, same box): 4:4:4 -7 %, 4:2:2 -3.8 %; 4:2:0 +4 % and gray +2 %, which keep warp 0.
     int pf_img = -1;  // image whose quantisers were staged last (uniform)
-    const int ftid = (NC == 3 && !(H == 2 && V == 2)) ? NT - 32 : 0;  // first thread of the fetching warp
+    constexpr bool FETCH_LAST = NC == 3 && !(H == 2 && V == 2);
+    const int ftid = FETCH_LAST ? NT - 32 : 0;  // first thread of the fetching warp
     auto fetch = [&](const ZpxTileDev tn, int stg) {
         const ZpxImageDev* __restrict__ imn = &P.imgs[tn.img];
         if (tid == ftid) {
@@ -205,22 +206,33 @@ __global__ void __launch_bounds__(NTMAX, k2_threads_per_sm(NC) / NTMAX) k2_fused
             }
             ctx[stg] = c;
         }
-        if (tid >= ftid && tid < ftid + 32) {
-            // (every stage keeps its own copy: a later tile of another image must not disturb it)
-            const int k = tid & 31;
+        if (FETCH_LAST) {
+            if (tid >= ftid) {
+                // (every stage keeps its own copy: a later tile of another image must not disturb it)
+                const int k = tid & 31;
+                if ((int)tn.img != pf_img) {
+                    const int* qp[NC];
+#pragma unroll
+                    for (int c = 0; c < NC; c++) qp[c] = P.quant[imn->qidx[c]].q;
+                    int2 qv[NC];
+#pragma unroll
+                    for (int c = 0; c < NC; c++) qv[c] = __ldg(reinterpret_cast<const int2*>(qp[c]) + k);  // all loads in flight together
+#pragma unroll
+                    for (int c = 0; c < NC; c++) qsm[stg][c * 32 + k] = (uint32_t)qv[c].x | (uint32_t)qv[c].y << 24;
+                } else {
+                    const int prev = stg == 0 ? NS - 1 : stg - 1;
+#pragma unroll
+                    for (int c = 0; c < NC; c++) qsm[stg][c * 32 + k] = qsm[prev][c * 32 + k];
+                }
+            }
+        } else if (tid < 32 * NC) {  // one warp per component
+            const int c = tid >> 5, k = tid & 31;
             if ((int)tn.img != pf_img) {
-                const int* qp[NC];
-#pragma unroll
-                for (int c = 0; c < NC; c++) qp[c] = P.quant[imn->qidx[c]].q;
-                int2 qv[NC];
-#pragma unroll
-                for (int c = 0; c < NC; c++) qv[c] = __ldg(reinterpret_cast<const int2*>(qp[c]) + k);  // all loads in flight together
-#pragma unroll
-                for (int c = 0; c < NC; c++) qsm[stg][c * 32 + k] = (uint32_t)qv[c].x | (uint32_t)qv[c].y << 24;
+                const int* q = P.quant[imn->qidx[c]].q;
+                qsm[stg][c * 32 + k] = (uint32_t)q[2 * k] | (uint32_t)q[2 * k + 1] << 24;
             } else {
                 const int prev = stg == 0 ? NS - 1 : stg - 1;
-#pragma unroll
-                for (int c = 0; c < NC; c++) qsm[stg][c * 32 + k] = qsm[prev][c * 32 + k];
+                qsm[stg][c * 32 + k] = qsm[prev][c * 32 + k];
             }
         }
         pf_img = (int)tn.img;
