@@ -470,7 +470,7 @@ void build_plan(zpx_batch* b, int di) {
                     t.my = (uint16_t)my;
                     t.n = (uint16_t)(nr * p.mxx);
                     t.mx0 = 0;
-                    t.pad = (uint32_t)nr | (uint32_t)p.mxx << 16;
+                    t.pad = (uint32_t)nr | (uint32_t)p.mxx << 16 | (im.qidx[0] < 255 ? (uint32_t)(im.qidx[0] + 1) << 8 : 0u);
                     g.tiles.push_back(t);
                 }
             } else
@@ -481,7 +481,11 @@ void build_plan(zpx_batch* b, int di) {
                     t.my = (uint16_t)my;
                     t.n = (uint16_t)std::min(tn, p.mxx - mx0);
                     t.mx0 = (uint32_t)mx0;
-                    t.pad = 0;
+                    // colour tiles: the components' quantiser indices, so that the kernel's loads of the tables do not
+                    // wait for the image descriptor first (gray tiles: rows | width << 16, above; gray has one table)
+                    t.pad = nc == 3 && im.qidx[0] < 1023 && im.qidx[1] < 1023 && im.qidx[2] < 1023
+                                ? (uint32_t)(im.qidx[0] + 1) | (uint32_t)(im.qidx[1] + 1) << 10 | (uint32_t)(im.qidx[2] + 1) << 20 | 1u << 31
+                                : nc == 1 && im.qidx[0] < 255 ? (uint32_t)(im.qidx[0] + 1) << 8 : 0u;
                     g.tiles.push_back(t);
                 }
             g.bytes += nblocks * 128 + (uint64_t)4 * p.width * p.height;

@@ -23,6 +23,9 @@
 // resident threads per SM the fused kernel is compiled for (register cap = 65536 / that).  Measured on one B200
 // (tools/k2_variants.sh, K2 time, 512 / 640 / 768): 4:2:0 1.72 / 1.72 / 1.87 ms, 4:4:4 1.54 / 1.63 / 1.59, 4:2:2 4.19 /
 // 4.34 / 4.78, gray 0.600 / 0.573 / 0.868 -- colour stays at 512 (126 registers, no spills), gray takes 640 (102).
+#ifndef ZPX_K2_TILE_QIDX
+#define ZPX_K2_TILE_QIDX 0
+#endif
 #ifndef ZPX_K2_THREADS_PER_SM
 #define ZPX_K2_THREADS_PER_SM 512
 #endif
@@ -154,6 +157,14 @@ __global__ void __launch_bounds__(NTMAX, k2_threads_per_sm(NC) / NTMAX) k2_fused
     int pf_img = -1;  // image whose quantisers were staged last (uniform)
     constexpr bool FETCH_LAST = NC == 3 && !(H == 2 && V == 2);
     const int ftid = FETCH_LAST ? NT - 32 : 0;  // first thread of the fetching warp
+    // quantiser table of component c: colour tiles carry the indices (pad: bit 31, three 10-bit fields holding
+    // index + 1), so the table loads do not depend on the image descriptor's
+    auto qindex = [&](const ZpxTileDev& tn, const ZpxImageDev* imn, int c) -> int {
+        // (colour: measured -1 % for 4:2:0 and 4:4:4, +1 % for 4:2:2 -- off unless ZPX_K2_TILE_QIDX; gray: +4 %)
+        if (ZPX_K2_TILE_QIDX && NC == 3 && (tn.pad >> 31)) return (int)((tn.pad >> (10 * c)) & 1023u) - 1;
+        if (NC == 1 && ((tn.pad >> 8) & 0xffu)) return (int)((tn.pad >> 8) & 0xffu) - 1;  // gray: rows | index + 1 << 8 | width << 16
+        return imn->qidx[c];
+    };
     auto fetch = [&](const ZpxTileDev tn, int stg) {
         const ZpxImageDev* __restrict__ imn = &P.imgs[tn.img];
         if (tid == ftid) {
@@ -188,10 +199,11 @@ __global__ void __launch_bounds__(NTMAX, k2_threads_per_sm(NC) / NTMAX) k2_fused
             c.width = imn->width;
             c.height = imn->height;
             c.out_off = imn->out_off;
-            c.nr = tn.pad & 0xffu ? tn.pad & 0xffu : 1u;
-            c.wt = tn.pad >> 16 ? tn.pad >> 16 : tn.n;
+            c.nr = (NC == 1 && (tn.pad & 0xffu)) ? tn.pad & 0xffu : 1u;
+            c.wt = (NC == 1 && (tn.pad >> 16)) ? tn.pad >> 16 : tn.n;
             // (progressive scans do not track the coefficient range: their frames always take the exact rows)
-            c.wide = (P.img_flags[imn->status_slot] & 1u) | (imn->progressive ? 1u : 0u);
+            // (the flags are indexed by the image's slot on the device, which is its index in the image table)
+            c.wide = (P.img_flags[tn.img] & 1u) | (imn->progressive ? 1u : 0u);
             c.poff[0] = imn->plane_off[0];
             c.poff[1] = imn->plane_off[1];
             c.poff[2] = imn->plane_off[2];
@@ -213,7 +225,7 @@ __global__ void __launch_bounds__(NTMAX, k2_threads_per_sm(NC) / NTMAX) k2_fused
                 if ((int)tn.img != pf_img) {
                     const int* qp[NC];
 #pragma unroll
-                    for (int c = 0; c < NC; c++) qp[c] = P.quant[imn->qidx[c]].q;
+                    for (int c = 0; c < NC; c++) qp[c] = P.quant[qindex(tn, imn, c)].q;
                     int2 qv[NC];
 #pragma unroll
                     for (int c = 0; c < NC; c++) qv[c] = __ldg(reinterpret_cast<const int2*>(qp[c]) + k);  // all loads in flight together
@@ -228,7 +240,7 @@ __global__ void __launch_bounds__(NTMAX, k2_threads_per_sm(NC) / NTMAX) k2_fused
         } else if (tid < 32 * NC) {  // one warp per component
             const int c = tid >> 5, k = tid & 31;
             if ((int)tn.img != pf_img) {
-                const int* q = P.quant[imn->qidx[c]].q;
+                const int* q = P.quant[qindex(tn, imn, c)].q;
                 qsm[stg][c * 32 + k] = (uint32_t)q[2 * k] | (uint32_t)q[2 * k + 1] << 24;
             } else {
                 const int prev = stg == 0 ? NS - 1 : stg - 1;
