@@ -21,7 +21,7 @@ ap.add_argument("--seeds", type=int, default=20)
 ap.add_argument("--first", type=int, default=0)
 ap.add_argument("--out", default="gpurun_out/fuzz")
 ap.add_argument("--mode", type=int, default=0)
-ap.add_argument("--native", type=int, default=0, help="1: also compare the native variant (planes / interleave) byte for byte")
+ap.add_argument("--native", type=int, default=0, help="1: also compare the native variant (planes / interleave) byte for byte; 2: the same with ZPX_OPT_FORCE_GENERIC")
 ap.add_argument("--structural", type=int, default=0, help="N more files per base with marker-level damage")
 ap.add_argument("--synth", type=int, default=0, help="1: synthetic base files (other shapes, DRI, CMYK, YCbCrK) instead of the fixtures")
 ap.add_argument("--prog-only", type=int, default=0, help="1: progressive base files only")
@@ -51,7 +51,14 @@ def bases():
         kw2 = [dict(subsampling="4:2:0"), dict(subsampling="4:4:4"), dict(mode="L"), dict(mode="CMYK"),
                dict(subsampling="4:2:0", restart_rows=8), dict(subsampling="4:2:2", restart_rows=3),
                dict(subsampling="4:2:0", quality=97), dict(subsampling="4:2:0", progressive=True)]
-        return [S.encode(71000 + i, 640, 480, **k) for i, k in enumerate(kw2)]
+        out = [S.encode(71000 + i, 640, 480, **k) for i, k in enumerate(kw2)]
+        # gray rows cut into several fused-kernel tiles, progressive gray / 4:2:2, multi-scan frames of several tiles per row
+        from tools.multiscan import recode
+        out += [S.encode(71100, 1100, 40, mode="L"), S.encode(71101, 1100, 40, mode="L", progressive=True),
+                S.encode(71102, 1363, 48, subsampling="4:2:2", progressive=True),
+                recode(S.encode(71104, 1363, 48, subsampling="4:2:2"), [[0], [1], [2]], 0),
+                recode(S.encode(71106, 1920, 32, subsampling="4:2:0"), [[1], [0, 2]], 0)]
+        return out
     kw = [dict(subsampling="4:2:0"), dict(subsampling="4:2:0", restart_rows=1), dict(subsampling="4:2:0", restart_blocks=3),
           dict(subsampling="4:2:2"), dict(subsampling="4:2:2", restart_blocks=5), dict(subsampling="4:4:4"),
           dict(subsampling="4:4:4", restart_rows=1), dict(mode="L"), dict(mode="L", restart_blocks=4), dict(mode="CMYK"),
@@ -111,8 +118,8 @@ def structural_damage(data, rng, count):
 ctx = jpeg.Context([0])
 ctx.set_option(1, a.mode)
 ctx.set_option(10, a.prog_mode)
-if a.native:
-    ctx.set_option(2, 1)  # planes only exist on the unfused path
+if a.native == 2:
+    ctx.set_option(2, 1)  # 2: everything on the unfused kernels (1: the fused kernel's images get their planes on demand)
 bad = total = 0
 for seed in range(a.first, a.first + a.seeds):
     rng = np.random.default_rng(900000 + seed)
