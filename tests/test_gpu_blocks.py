@@ -125,6 +125,21 @@ def _random_blocks(rng, n, kind):
         if kind == "lo4_mixed":
             hit = np.nonzero(rng.random(n) < 0.02)[0]
             b[hit, rng.choice(np.array([4, 32, 39, 60, 63, 12, 33]), len(hit))] = rng.choice(np.array([-1, 1, 300]), len(hit))
+    elif kind == "r7":        # only coefficient row 7 zero (the gray kernel's variant), a few blocks with a value there
+        b[:, :56] = rng.integers(-1023, 1024, (n, 56))
+        hit = np.nonzero(rng.random(n) < 0.01)[0]
+        b[hit, rng.choice(np.array([56, 60, 63]), len(hit))] = rng.choice(np.array([-1, 1, 300]), len(hit))
+    elif kind in ("r6", "r6_mixed"):
+        # coefficient rows 6 and 7 zero (warps of such blocks skip those rows in the fused kernel); "r6_mixed": a few blocks
+        # with a value in row 6 or 7, and a third of the blocks with nothing outside the 4x4 corner
+        b[:, :48] = rng.choice(np.array([-4096, -1023, -60, -1, 0, 1, 60, 1023, 4095]), (n, 48), p=[.03, .07, .15, .1, .3, .1, .15, .07, .03])
+        if kind == "r6_mixed":
+            hit = np.nonzero(rng.random(n) < 0.02)[0]
+            b[hit, rng.choice(np.array([48, 55, 56, 63, 59]), len(hit))] = rng.choice(np.array([-1, 1, 300]), len(hit))
+            lo = np.nonzero(rng.random(n) < 0.33)[0]
+            keep = np.zeros(64, bool)
+            keep[[8 * r + c for r in range(4) for c in range(4)]] = True
+            b[np.ix_(lo, np.nonzero(~keep)[0])] = 0
     return b.astype(np.int16)
 
 
@@ -167,7 +182,7 @@ def _run(jpeg, ctx, width, height, comp_hv, quant_zz, mode, blocks, generic, wan
 
 @settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(seed=st.integers(0, 2**31 - 1), name=st.sampled_from(sorted(SAMPLINGS)),
-       kind=st.sampled_from(["sparse", "dense", "edge", "wide", "dc_rows", "lo4", "lo4_mixed"]), q16=st.booleans(), dims=st.sampled_from([(64, 48), (150, 103), (257, 33), (33, 130)]))
+       kind=st.sampled_from(["sparse", "dense", "edge", "wide", "dc_rows", "lo4", "lo4_mixed", "r6", "r6_mixed", "r7"]), q16=st.booleans(), dims=st.sampled_from([(64, 48), (150, 103), (257, 33), (33, 130)]))
 def test_blocks_match_reconstruct_block(jpeg, ctx, seed, name, kind, q16, dims):
     """random blocks x random quantisers, every sampling, fused and unfused kernels, planes and RGBA"""
     rng = np.random.default_rng(seed)
@@ -217,11 +232,13 @@ def test_exact_row_variant_equals_fast_variant_in_range(jpeg, ctx):
 
 @pytest.mark.parametrize("name", ["gray", "444", "422", "420", "440", "411", "410"])
 def test_sparse_block_idct_equals_the_general_one(jpeg, ctx, name):
-    """the fused kernel's sparse-block IDCT (warps whose 32 blocks have nothing outside the top-left 4x4 corner) against
+    """the fused kernel's sparse-block IDCTs (warps whose 32 blocks have zero coefficient rows 6 and 7 -- 4:2:0 --, a
+    zero row 7 -- gray --, or nothing outside the top-left 4x4 corner -- the other samplings) against
     the oracle's reconstructBlock and against the same kernel with the variant switched off (ZPX_OPT_K2_DENSE)"""
     rng = np.random.default_rng(5 + len(name))
     mode, comp_hv = SAMPLINGS[name]
-    for kind, (width, height) in (("lo4", (640, 64)), ("lo4_mixed", (1280, 48)), ("lo4_mixed", (333, 77))):
+    for kind, (width, height) in (("lo4", (640, 64)), ("lo4_mixed", (1280, 48)), ("lo4_mixed", (333, 77)), ("r6", (640, 64)),
+                                  ("r6_mixed", (1280, 48)), ("r6_mixed", (333, 77)), ("r7", (1280, 48))):
         mxx, myy = _geometry(width, height, comp_hv)
         n = mxx * myy * sum(h * v for h, v in comp_hv)
         blocks = _random_blocks(rng, n, kind)

@@ -18,7 +18,7 @@ def main():
     ap.add_argument("--names", nargs="*", default=None)
     ap.add_argument("--like-test", type=float, default=0, help="seconds to spend replaying the edge-tile test with fresh seeds")
     ap.add_argument("--shuffle", type=int, default=0, help="non-zero: run the cases in a random order (context reuse across shapes)")
-    ap.add_argument("--kinds", nargs="*", default=["sparse", "dense", "lo4_mixed"])
+    ap.add_argument("--kinds", nargs="*", default=["sparse", "dense", "lo4_mixed", "r6_mixed"])
     a = ap.parse_args()
     import test_gpu_blocks as T
     from zpix_b200 import jpeg

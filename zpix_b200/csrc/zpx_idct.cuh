@@ -176,25 +176,36 @@ __device__ __forceinline__ void dequant_idct_block_q8(LoadRow ld, const uint32_t
     }
 }
 
-// Same values as dequant_idct_block_q8 for a block whose coefficients outside the top-left 4x4 corner are all zero
-// (rows 4..7 and columns 4..7 of the natural-order block): the zero inputs are constants, so the multiplications
-// by them, the row pass of rows 4..7 (every output of an all-zero row is (0 + 128) >> 8 = 0) and the column terms
-// they feed fold away at compile time; every surviving operation is the one the general code performs, on the same
-// operands (wrapping 32-bit), hence bit-identical.  The caller takes this variant only when EVERY block of the warp
-// qualifies (a warp vote), which chroma blocks of photographs usually do.
-template <typename LoadRow>
-__device__ __forceinline__ void dequant_idct_block_q8_lo4(LoadRow ld, const uint32_t* __restrict__ qp, uint32_t (&px)[16]) {
+// Same values as dequant_idct_block_q8 for a block whose coefficient rows NR..7 are all zero (and, with LOCOLS, whose
+// columns 4..7 are zero too: nothing outside the top-left 4x4 corner when NR == 4): the zero inputs are constants, so
+// the multiplications by them, the row pass of the zero rows (every output of an all-zero row is (0 + 128) >> 8 = 0)
+// and the column terms they feed fold away at compile time; every surviving operation is the one the general code
+// performs, on the same operands (wrapping 32-bit), hence bit-identical.  The caller takes a variant only when EVERY
+// block of the warp qualifies (a warp vote): <4, true> for chroma blocks of photographs, <6, false> for luma blocks
+// whose two highest-frequency rows quantise to zero.  (The reference has a data-dependent shortcut of its own at the
+// same place: rows whose AC are all zero, idct.zig:84-97.)
+template <int NR, bool LOCOLS, typename LoadRow>
+__device__ __forceinline__ void dequant_idct_block_q8_sparse(LoadRow ld, const uint32_t* __restrict__ qp, uint32_t (&px)[16]) {
     int b[64];
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
+    for (int r = 0; r < NR; r++) {
         const uint4 c = ld(r);
-        const uint2 q = *reinterpret_cast<const uint2*>(qp + r * 4);
-        const int s0 = dp2a_lo_su(c.x, q.x) << 11, s1 = dp2a_hi_su(c.x, q.x);
-        const int s2 = dp2a_lo_su(c.y, q.y), s3 = dp2a_hi_su(c.y, q.y);
-        idct_row(s0, s1, s2, s3, 0, 0, 0, 0, &b[r * 8]);
+        if (LOCOLS) {
+            const uint2 q = *reinterpret_cast<const uint2*>(qp + r * 4);
+            const int s0 = dp2a_lo_su(c.x, q.x) << 11, s1 = dp2a_hi_su(c.x, q.x);
+            const int s2 = dp2a_lo_su(c.y, q.y), s3 = dp2a_hi_su(c.y, q.y);
+            idct_row(s0, s1, s2, s3, 0, 0, 0, 0, &b[r * 8]);
+        } else {
+            const uint4 q = *reinterpret_cast<const uint4*>(qp + r * 4);
+            const int s0 = dp2a_lo_su(c.x, q.x) << 11, s1 = dp2a_hi_su(c.x, q.x);
+            const int s2 = dp2a_lo_su(c.y, q.y), s3 = dp2a_hi_su(c.y, q.y);
+            const int s4 = dp2a_lo_su(c.z, q.z) << 11, s5 = dp2a_hi_su(c.z, q.z);
+            const int s6 = dp2a_lo_su(c.w, q.w), s7 = dp2a_hi_su(c.w, q.w);
+            idct_row(s0, s1, s2, s3, s4, s5, s6, s7, &b[r * 8]);
+        }
     }
 #pragma unroll
-    for (int k = 32; k < 64; k++) b[k] = 0;
+    for (int k = NR * 8; k < 64; k++) b[k] = 0;
 #pragma unroll
     for (int x = 0; x < 8; x++) idct_col(&b[x]);
 #pragma unroll

@@ -26,6 +26,15 @@
 #ifndef ZPX_K2_TILE_QIDX
 #define ZPX_K2_TILE_QIDX 0
 #endif
+#ifndef ZPX_K2_420_ROWS6
+#define ZPX_K2_420_ROWS6 1
+#endif
+#ifndef ZPX_K2_422_ROWS6
+#define ZPX_K2_422_ROWS6 0
+#endif
+#ifndef ZPX_K2_GRAY_ROWS7
+#define ZPX_K2_GRAY_ROWS7 1
+#endif
 #ifndef ZPX_K2_THREADS_PER_SM
 #define ZPX_K2_THREADS_PER_SM 512
 #endif
@@ -334,17 +343,34 @@ __global__ void __launch_bounds__(NTMAX, k2_threads_per_sm(NC) / NTMAX) k2_fused
                 uint4 c[8];
 #pragma unroll
                 for (int r = 0; r < 8; r++) c[r] = blk[r ^ key];
-                // Sparse blocks: when all 32 blocks of the warp have nothing outside their top-left 4x4 corner (chroma
-                // blocks mostly: a tile's threads are ordered luma, Cb, Cr), the IDCT with those zeros folded in
-                // (zpx_idct.cuh: the same operations on the same operands, minus the ones on constants)
-                uint32_t hi = 0;
+                // Sparse blocks, decided per warp by a vote.  ONE variant beside the general code per instantiation (a
+                // third unrolled IDCT body was measured 2.5 - 11 % slower on every sampling: instruction cache), chosen
+                // by measurement (K2 time on one B200, tools/k2_variants.sh):
+                //   4:2:0: coefficient rows 6 and 7 zero in all 32 blocks of the warp -- luma blocks whose highest
+                //          frequencies quantise to zero, and chroma -- take the IDCT without those rows (-2.1 % against
+                //          the 4x4 variant, which only chroma warps take);
+                //   gray:  row 7 zero (its luma keeps more high frequencies; the 4x4 variant never applies): -1.7 %;
+                //   other samplings: nothing outside the top-left 4x4 corner (chroma blocks: a tile's threads are
+                //          ordered luma, Cb, Cr) -> the 4x4 IDCT (4:2:2 with the rows-6-7 variant instead: +4 %)
+                // (zpx_idct.cuh: the same operations on the same operands, minus the ones on constant zeros)
+                constexpr bool ROWS6 = NC == 3 && ((ZPX_K2_420_ROWS6 && H == 2 && V == 2) || (ZPX_K2_422_ROWS6 && H == 2 && V == 1));
+                constexpr bool ROWS7 = ZPX_K2_GRAY_ROWS7 && NC == 1;  // gray: only row 7 (its luma keeps more high frequencies)
+                uint32_t hi = c[7].x | c[7].y | c[7].z | c[7].w;
+                if (!ROWS7) hi |= c[6].x | c[6].y | c[6].z | c[6].w;
+                if (!ROWS6 && !ROWS7) {
+                    hi |= c[4].x | c[4].y | c[4].z | c[4].w | c[5].x | c[5].y | c[5].z | c[5].w;
 #pragma unroll
-                for (int r = 0; r < 4; r++) hi |= c[r].z | c[r].w | c[r + 4].x | c[r + 4].y | c[r + 4].z | c[r + 4].w;
+                    for (int r = 0; r < 4; r++) hi |= c[r].z | c[r].w;
+                }
                 uint32_t px[16];
                 if (P.dense_only || __any_sync(0xffffffffu, valid && hi != 0))
                     dequant_idct_block_q8([&](int r) { return c[r]; }, q, px);
+                else if (ROWS7)
+                    dequant_idct_block_q8_sparse<7, false>([&](int r) { return c[r]; }, q, px);
+                else if (ROWS6)
+                    dequant_idct_block_q8_sparse<6, false>([&](int r) { return c[r]; }, q, px);
                 else
-                    dequant_idct_block_q8_lo4([&](int r) { return c[r]; }, q, px);
+                    dequant_idct_block_q8_sparse<4, true>([&](int r) { return c[r]; }, q, px);
                 if (valid) {
 #pragma unroll
                     for (int r = 0; r < 8; r++)
