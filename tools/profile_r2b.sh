@@ -4,6 +4,8 @@
 # tools/ncu_summary.py and tools/launch_list_summary.py.
 set -u
 O=gpurun_out
+python bench.py > $O/r2b_bench_n1.json 2> $O/r2b_bench_n1.err          # the full line (value, e2e, parity, other_configs ...)
+python bench.py --impl reference > $O/r2b_bench_ref_n1.json 2> /dev/null  # the reference arm on the same box
 B="python bench.py --steps 2 --warmup 3 --skip-extras"
 $B > $O/r2b_bench_plain.json 2> $O/r2b_bench_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/r2b_launches_bench.csv $B > $O/r2b_bench_under_ncu.json 2> $O/r2b_bench_under_ncu.err
