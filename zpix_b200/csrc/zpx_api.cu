@@ -122,6 +122,7 @@ struct DeviceCtx {
     cudaEvent_t ev[8] = {nullptr};
     DevBuf blob, ublob, coef, out, planes, desc, status, subs, scratch;
     DevBuf planes_late, late_list;  // native planes of fused images, made on demand (zpx_batch_fetch_native)
+    DevBuf carry;                   // End-Of-Band runs handed from scan to scan (rescue_eob_carry)
     HostBuf stage, hdesc, hstatus, hflag;
 };
 
@@ -820,6 +821,8 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
     k1.coef = (uint4*)dc.coef.p;
     k1.status = (unsigned long long*)dc.status.p;
     k1.img_flags = img_flags;
+    k1.eob_in = nullptr;
+    k1.eob_out = nullptr;
     if (!pl.segs.empty()) {
         CU(ctx, k0_launch_unstuff(k1.blob, (uint8_t*)dc.ublob.p, (const ZpxSegDev*)(desc + pl.off_segs), (int)pl.segs.size(), st));
         k1_launches++;
@@ -982,6 +985,99 @@ int collect_timing(zpx_batch* b, int di) {
 cudaError_t after_decode(DeviceCtx& dc) { return cudaStreamWaitEvent(dc.stream, dc.ev[3], 0); }
 
 // combine header status, host-side pending errors and the device error records
+// Progressive frames in which a scan ended inside an End-Of-Band run (corrupt streams only).  The reference keeps the
+// run in the decoder (decoder.zig:144, reset only at a restart marker :1451), so the next scan starts by skipping
+// blocks; the batch decode runs the scans of a frame level by level, side by side, each from a run of zero, and flags
+// such a frame instead.  Here the flagged frames of one device are decoded again the reference's way: coefficients
+// zeroed, scans launched ONE BY ONE in file order on the general kernel (k3_progressive), the run handed from a scan's
+// last interval to the next scan's first through two words per image (read / written alternately), then reconstructed
+// by the unfused kernels.  Slow (a launch per scan) and rare.
+int rescue_eob_carry(zpx_batch* b, size_t di, const std::vector<uint32_t>& slots) {
+    zpx_ctx* ctx = b->ctx;
+    DeviceCtx& dc = ctx->devs[di];
+    DevicePlan& pl = b->plans[di];
+    cudaStream_t st = dc.stream;
+    uint8_t* desc = (uint8_t*)dc.desc.p;
+    const size_t nimg = pl.imgs.size();
+    std::vector<char> flagged(nimg, 0);
+    for (uint32_t k : slots) flagged[k] = 1;
+    std::vector<std::vector<uint32_t>> per_scan;  // [scan ordinal] -> intervals of the flagged frames
+    for (uint32_t i = 0; i < (uint32_t)pl.ivs.size(); i++) {
+        const ZpxScanDev& sc = pl.scans[pl.ivs[i].scan];
+        if (!flagged[sc.img]) continue;
+        if (per_scan.size() <= (size_t)sc.scan_index) per_scan.resize((size_t)sc.scan_index + 1);
+        per_scan[(size_t)sc.scan_index].push_back(i);
+    }
+    size_t max_list = slots.size();
+    for (const auto& l : per_scan) max_list = std::max(max_list, l.size());
+    CU(ctx, dc.carry.ensure(2 * nimg * sizeof(uint32_t)));
+    CU(ctx, dc.late_list.ensure(max_list * sizeof(uint32_t)));
+    CU(ctx, cudaMemsetAsync(dc.carry.p, 0, 2 * nimg * sizeof(uint32_t), st));
+    int max_blocks = 0;
+    size_t max_pixels = 0;
+    std::vector<uint32_t> late, eager;
+    for (uint32_t k : slots) {
+        const ZpxImageDev& im = pl.imgs[k];
+        const ZpxParsed& p = b->parsed[pl.images[k]];
+        const size_t nb = (size_t)p.mxx * p.myy * im.bpm;
+        CU(ctx, cudaMemsetAsync((uint8_t*)dc.coef.p + im.coef_base * 128, 0, nb * 128, st));
+        CU(ctx, cudaMemsetAsync((unsigned long long*)dc.status.p + k, 0xff, sizeof(unsigned long long), st));
+        max_blocks = std::max(max_blocks, (int)nb);
+        max_pixels = std::max(max_pixels, (size_t)p.width * p.height);
+        (im.fused && pl.native == 0 ? late : eager).push_back(k);
+    }
+    K1Params k1;
+    memset(&k1, 0, sizeof(k1));
+    k1.blob = (const uint8_t*)dc.blob.p;
+    k1.ublob = (const uint8_t*)dc.ublob.p;
+    k1.ivs = (const ZpxIntervalDev*)(desc + pl.off_ivs);
+    k1.scans = (const ZpxScanDev*)(desc + pl.off_scans);
+    k1.imgs = (const ZpxImageDev*)(desc + pl.off_imgs);
+    k1.huff = (const ZpxHuffDev*)(desc + pl.off_huff);
+    k1.coef = (uint4*)dc.coef.p;
+    k1.status = (unsigned long long*)dc.status.p;
+    k1.img_flags = (uint32_t*)((uint8_t*)dc.status.p + align_up(nimg * sizeof(unsigned long long), 256));
+    uint32_t* cw = (uint32_t*)dc.carry.p;
+    for (size_t s = 0; s < per_scan.size(); s++) {
+        if (per_scan[s].empty()) continue;
+        k1.eob_in = cw + (s & 1) * nimg;
+        k1.eob_out = cw + ((s + 1) & 1) * nimg;
+        CU(ctx, cudaMemcpyAsync(dc.late_list.p, per_scan[s].data(), per_scan[s].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU(ctx, k3_launch_progressive(k1, (const uint32_t*)dc.late_list.p, (int)per_scan[s].size(), st));
+        ctx->launches++;
+    }
+    // reconstruction (dequantise + IDCT -> planes -> colour) of those frames
+    K2GParams kg{};
+    kg.coef = (const int16_t*)dc.coef.p;
+    kg.out = (uint8_t*)dc.out.p;
+    kg.imgs = k1.imgs;
+    kg.quant = (const ZpxQuantDev*)(desc + pl.off_quant);
+    kg.list = (const uint32_t*)dc.late_list.p;
+    for (int pass = 0; pass < 2; pass++) {
+        const std::vector<uint32_t>& l = pass == 0 ? eager : late;
+        if (l.empty()) continue;
+        if (pass == 1) {
+            // frames that took the fused kernel have no planes of their own: the on-demand plane buffer serves as
+            // scratch (zpx_batch_fetch_native makes every frame's planes again, from the coefficients written above)
+            CU(ctx, dc.planes_late.ensure(pl.late_plane_bytes + 256));
+            for (uint32_t k : l) {
+                zpx_image_info info;
+                zpx_fill_info(b->parsed[pl.images[k]], &info);
+                CU(ctx, cudaMemsetAsync((uint8_t*)dc.planes_late.p + pl.imgs[k].plane_off[0], 0, info.native_len, st));
+            }
+            pl.late_done = false;
+        }
+        kg.planes = (uint8_t*)(pass == 0 ? dc.planes.p : dc.planes_late.p);
+        CU(ctx, cudaMemcpyAsync(dc.late_list.p, l.data(), l.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if (pl.native == 2) CU(ctx, k2g_launch_planes(kg, (int)l.size(), max_blocks, st));
+        else CU(ctx, k2g_launch(kg, (int)l.size(), max_blocks, max_pixels, st));
+        ctx->launches += pl.native == 2 ? 1 : 2;
+    }
+    CU(ctx, cudaMemcpyAsync(dc.hstatus.p, dc.status.p, nimg * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return ZPX_OK;
+}
+
 int finalize_status(zpx_batch* b) {
     if (b->status_ready) return ZPX_OK;
     zpx_ctx* ctx = b->ctx;
@@ -997,6 +1093,18 @@ int finalize_status(zpx_batch* b) {
         CU(ctx, cudaStreamSynchronize(dc.stream));
         const unsigned long long* hs = (const unsigned long long*)dc.hstatus.p;
         int failed = 0;
+        // first: progressive frames that were flagged because a scan ended inside an End-Of-Band run are decoded again,
+        // scan by scan with the run carried (the device statuses in hs are read again afterwards)
+        {
+            std::vector<uint32_t> carry;
+            for (size_t k = 0; k < pl.images.size(); k++)
+                if (hs[k] != ZPX_STATUS_NONE && (int)(hs[k] & 0xff) == ZPX_E_UNSUPPORTED_STREAM && b->parsed[pl.images[k]].progressive)
+                    carry.push_back((uint32_t)k);
+            if (!carry.empty() && !getenv("ZPX_NO_EOB_RESCUE")) {
+                int e = rescue_eob_carry(b, di, carry);
+                if (e) return e;
+            }
+        }
         for (size_t k = 0; k < pl.images.size(); k++) {
             const int bi = pl.images[k];
             const ZpxParsed& p = b->parsed[bi];
@@ -1172,6 +1280,7 @@ void zpx_ctx_destroy(zpx_ctx* c) {
         d.scratch.release();
         d.planes_late.release();
         d.late_list.release();
+        d.carry.release();
         d.hflag.release();
         d.stage.release();
         d.hdesc.release();

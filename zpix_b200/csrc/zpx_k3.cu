@@ -204,6 +204,9 @@ __global__ void __launch_bounds__(K3_NT, 5) k3_progressive(const K1Params P, con
     // lane 0 only:
     int dc0 = 0, dc1 = 0, dc2 = 0, dc3 = 0;
     uint32_t eob_run = 0;
+    // (serial re-decode: the reference keeps the run across scans, decoder.zig:144 -- the scan's first interval starts
+    // with what the previous scan left; a restart marker resets it, :1451)
+    if (P.eob_in != nullptr && iv.ordinal == 0) eob_run = P.eob_in[im->status_slot];
     // refinement batch
     uint32_t bj0 = 0, bn = 0, bk = 0;   // batch = blocks [bj0, bj0+bn), bk done
     short pre[2 * K3_BATCH];             // prefetched coefficients of the next batch: zig-zag lane, lane+32
@@ -612,8 +615,12 @@ __global__ void __launch_bounds__(K3_NT, 5) k3_progressive(const K1Params P, con
     // The reference keeps its End-Of-Band run across scans (decoder.zig:144, reset only at RSTn :1451); here
     // every scan starts from zero (scans of one level run side by side), so a run that is still open when a
     // scan ends (corrupt streams only) would make the next scan differ: refuse the image instead.
-    if (!err && lane == 0 && (iv.flags & 2u) && eob_run != 0)
-        report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + iv.n_blocks, ZPX_E_UNSUPPORTED_STREAM);
+    // (the host then decodes the image again with its scans one after the other and the run handed on: zpx_api.cu)
+    if (!err && lane == 0 && (iv.flags & 2u)) {
+        if (P.eob_out != nullptr) P.eob_out[im->status_slot] = eob_run;
+        else if (eob_run != 0)
+            report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + iv.n_blocks, ZPX_E_UNSUPPORTED_STREAM);
+    }
 }
 
 cudaError_t k3_launch_progressive(const K1Params& P, const uint32_t* list, int n_list, cudaStream_t s) {

@@ -22,6 +22,8 @@ struct K1Params {
     const ZpxHuffDev* huff;
     uint4* coef;                  // 8 x uint4 per block
     unsigned long long* status;   // per image: smallest error key, ZPX_STATUS_NONE if none
+    const uint32_t* eob_in;       // NULL, or (k3_progressive, the serial re-decode of zpx_api.cu: scans launched one by one in
+    uint32_t* eob_out;            // file order) per image: the End-Of-Band run the previous scan left open / this one leaves
     uint32_t* img_flags;          // per image (status slot), zeroed before the decode: bit 0 = some coefficient of a
                                   // sequential scan lies outside [-4096, 4095] (the fused IDCT then takes the
                                   // reference's all-AC-zero row literally, zpx_idct.cuh)
