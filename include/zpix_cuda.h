@@ -191,10 +191,10 @@ int32_t zpx_batch_info(const zpx_batch *b, int32_t i, zpx_image_info *out);
 int32_t zpx_batch_upload(zpx_batch *b);
 /* Run the unstuffing + entropy + IDCT/colour kernels; results stay in device memory.
  * stream: a cudaStream_t to launch on (single-device contexts only), or NULL for the context's own streams.
- * With NULL the call returns after completion.  With a stream it returns once the work is enqueued -- with one
- * exception: batches that take the self-synchronising entropy decoder (no or few restart markers) and hold a
- * segment longer than 32 sub-sequences read one 4-byte convergence flag back per sweep (usually once), i.e. the
- * call then waits for the synchronisation passes, never for the kernels that write coefficients or pixels.
+ * With NULL the call returns after completion.  With a stream it returns once the work is enqueued, nothing is read
+ * back (the self-synchronising entropy decoder enqueues a fixed number of synchronisation rounds, each gated on a
+ * device flag; a stream that needs more -- adversarial data -- is found and decoded again by zpx_batch_status or
+ * the fetch calls, so consumers of zpx_batch_device_rgba call zpx_batch_status first).
  * Ordering contract: work the caller enqueues on `stream` after this call sees the results.  The library's own
  * reads (zpx_batch_status, zpx_batch_fetch_*, zpx_batch_fetch_coefficients) run on the context's stream, which
  * the library orders after the decode's last kernel itself: they may be called right away, without synchronising
@@ -296,6 +296,8 @@ int32_t zpx_partition(const uint64_t *weights, int32_t n, int32_t n_devices, int
                                     * (zpx_k3.cu); 1: always one warp per scan */
 #define ZPX_OPT_K2_DENSE 11 /* 1: the fused kernel never takes its sparse-block IDCT (warps whose 32 blocks have no
                              * coefficient outside the top-left 4x4 corner); results are identical either way */
+#define ZPX_OPT_GATED_SWEEPS 12 /* 0..8 (-1: test hook), default 2: synchronisation rounds of the self-synchronising entropy decoder that
+                                 * a decode on the caller's stream enqueues ahead of time (see zpx_batch_decode) */
 #define ZPX_OPT_TEST_WIDE 8  /* test hook: 1 = frames filled by zpx_batch_set_coefficients take the kernels' exact
                                 all-AC-zero-row IDCT variant whatever their coefficients */
 int32_t zpx_ctx_set_option(zpx_ctx *ctx, int32_t option, int64_t value);

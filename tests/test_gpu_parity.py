@@ -907,6 +907,39 @@ def test_results_read_after_a_decode_on_the_callers_stream(jpeg, fixtures_dir):
     c.close()
 
 
+def test_self_synchronising_decoder_on_the_callers_stream(jpeg, fixtures_dir):
+    """streams without restart markers decoded on a caller's stream: the synchronisation rounds are enqueued blind (gated
+    on device flags, nothing read back).  Default sub-sequences converge within them; 32-byte sub-sequences need more
+    rounds than were enqueued would be noticed by the status call and repaired by decoding again with the host loop
+    (forced here through the option's test value).  Same
+    pixels as the oracle either way, also when the device pointer is taken after zpx_batch_status alone."""
+    import torch
+    datas = S.make_batch(3, 6, 512, 512, first=5000, mode="YCbCr", subsampling="4:4:4") + S.make_batch(3, 4, 512, 512, mode="L")
+    datas += [_read(fixtures_dir, "iceberg.jpg"), S.encode(63000, 1920, 1080, subsampling="4:2:0")]
+    want = [O.decode(d).rgbaPixels() for d in datas]
+    stream = torch.cuda.Stream()
+    for mode, sub, rounds in ((2, 0, 2), (2, 32, 2), (2, 32, 0), (2, 0, -1), (0, 0, 2)):
+        c = jpeg.Context([0])
+        c.set_option(1, mode)
+        c.set_option(3, sub)
+        c.set_option(12, rounds)  # ZPX_OPT_GATED_SWEEPS; -1 = test hook: the rounds count as not converged
+        with jpeg.Batch(c, datas) as b:
+            b.upload()
+            for _ in range(2):
+                launches = c.kernel_launches
+                b.decode(stream.cuda_stream)
+                enq = c.kernel_launches - launches
+                assert b.status() == [0] * len(datas)
+                if rounds == -1:
+                    assert c.kernel_launches - launches > enq  # the status call decoded again
+                ptr = b.device_rgba_ptr(len(datas) - 2)
+                assert ptr
+                outs, st = b.fetch_rgba()
+                for o, w in zip(outs, want):
+                    assert np.array_equal(o, w), (mode, sub)
+        c.close()
+
+
 def test_native_batch_one_call(jpeg, fixtures_dir):
     """zpx_decode_batch_native: the whole batch comes back as the Image variants jpeg.load returns -- planes of the
     fused kernel (MCU padding included) for the ordinary files, unfused kernels for the rest -- through the chunk

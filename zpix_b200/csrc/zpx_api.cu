@@ -181,6 +181,7 @@ struct DevicePlan {
     size_t late_plane_bytes = 0;
     int late_max_blocks = 0;
     bool late_done = false;
+    const int* conv_flag = nullptr;  // device flag: set if the sweeps enqueued on a caller's stream did not converge
     int native = 0;  // ZPX_OPT_NATIVE_PLANES at the time the plan was built
 };
 
@@ -192,7 +193,7 @@ struct zpx_ctx {
     std::string last_cuda_str;
     std::atomic<uint64_t> launches{0};
     int64_t opt_entropy_mode = 0, opt_force_generic = 0, opt_subseq = 0, opt_pipeline_chunk = 0;
-    int64_t opt_pipeline_ramp = 1, opt_pipeline_workers = 3, opt_test_wide = 0, opt_native = 0, opt_progressive_mode = 0, opt_k2_dense = 0;
+    int64_t opt_pipeline_ramp = 1, opt_pipeline_workers = 3, opt_test_wide = 0, opt_native = 0, opt_progressive_mode = 0, opt_k2_dense = 0, opt_gated_sweeps = 2;
     bool busy = false;
     const zpx_batch* resident = nullptr;  // the batch whose data currently occupies the device buffers
     std::vector<zpx_ctx*> shadows;  // further sets of device buffers/streams for the chunk pipeline of zpx_decode_batch_rgba
@@ -788,7 +789,7 @@ void build_plan(zpx_batch* b, int di) {
     for (const FusedGroup& g : pl.groups) pl.timing.idct_fused_bytes += g.bytes;
 }
 
-int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
+int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream, bool host_sweeps = false) {
     zpx_ctx* ctx = b->ctx;
     DeviceCtx& dc = ctx->devs[di];
     DevicePlan& pl = b->plans[di];
@@ -853,14 +854,42 @@ int decode_on_device(zpx_batch* b, int di, cudaStream_t user_stream) {
         ks.s_out = (unsigned long long*)(sb + S * 24);
         ks.s_n = (int*)(sb + S * 32);
         ks.s_bad = (int*)(sb + S * 36);
-        ks.changed = (int*)(sb + S * 40);
+        ks.changed = (int*)(sb + S * 40);  // (256 bytes: up to 64 flags)
+        ks.gate = nullptr;
         int* hflag = (int*)dc.hflag.p;
+        pl.conv_flag = nullptr;
         // sweep 0 decodes every sub-sequence from its guess and settles each warp; later sweeps carry
         // end states across warp boundaries until nothing changes (exact fixed point)
         CU(ctx, k1s_launch_sync(ks, 0, st));
         k1_launches++;
         bool multi = false;
         for (size_t k = 0; k < pl.n_sub_iv; k++) multi = multi || pl.ivs[k].nsub > 32;
+        if (multi && user_stream != nullptr && !host_sweeps) {
+            // On the caller's stream nothing is read back: the boundary pass and ZPX_OPT_GATED_SWEEPS further rounds of
+            // (sweep, boundary pass) are enqueued now, each launch gated on the flag the pass before it wrote -- a
+            // round with nothing to do costs two empty launches.  Streams that need more rounds than that (tiny
+            // sub-sequences, adversarial data) leave the last flag set: the status call sees it and decodes the
+            // device's share again with the host loop below (finalize_status).
+            const int ZPX_GATED_SWEEPS = std::max(0, (int)ctx->opt_gated_sweeps);  // (ZPX_OPT_GATED_SWEEPS, default 2)
+            int* F = ks.changed;
+            CU(ctx, cudaMemsetAsync(F, 0, (2 * ZPX_GATED_SWEEPS + 1) * sizeof(int), st));
+            ks.changed = F;
+            CU(ctx, k1s_launch_fix(ks, st));
+            k1_launches++;
+            for (int r = 1; r <= ZPX_GATED_SWEEPS; r++) {
+                ks.gate = F + 2 * r - 2;
+                ks.changed = F + 2 * r - 1;
+                CU(ctx, k1s_launch_sync(ks, r, st));
+                ks.gate = F + 2 * r - 1;
+                ks.changed = F + 2 * r;
+                CU(ctx, k1s_launch_fix(ks, st));
+                k1_launches += 2;
+            }
+            ks.gate = nullptr;
+            pl.conv_flag = F + 2 * ZPX_GATED_SWEEPS;
+            if (ctx->opt_gated_sweeps < 0) CU(ctx, cudaMemsetAsync(F, 1, 1, st));  // test hook: exercise the repair path
+            multi = false;
+        }
         for (int sweep = 1; multi; sweep++) {
             // warp boundaries first (cheap); a full sweep only if one of them moved
             CU(ctx, cudaMemsetAsync(ks.changed, 0, sizeof(int), st));
@@ -1088,6 +1117,18 @@ int finalize_status(zpx_batch* b) {
         CU(ctx, cudaSetDevice(dc.dev));
         CU(ctx, dc.hstatus.ensure(pl.imgs.size() * sizeof(unsigned long long)));
         CU(ctx, after_decode(dc));
+        if (pl.conv_flag != nullptr) {
+            // a decode on the caller's stream whose synchronisation sweeps were enqueued blind: did they converge?
+            int* hflag = (int*)dc.hflag.p;
+            CU(ctx, cudaMemcpyAsync(hflag, pl.conv_flag, sizeof(int), cudaMemcpyDeviceToHost, dc.stream));
+            CU(ctx, cudaStreamSynchronize(dc.stream));
+            if (*hflag != 0) {
+                int e = decode_on_device(b, (int)di, nullptr, true);  // (rare: more sweeps were needed; the host loop does them)
+                if (e) return e;
+                CU(ctx, after_decode(dc));
+            }
+            pl.conv_flag = nullptr;
+        }
         CU(ctx, cudaMemcpyAsync(dc.hstatus.p, dc.status.p, pl.imgs.size() * sizeof(unsigned long long),
                                 cudaMemcpyDeviceToHost, dc.stream));
         CU(ctx, cudaStreamSynchronize(dc.stream));
@@ -1308,6 +1349,10 @@ int32_t zpx_ctx_set_option(zpx_ctx* c, int32_t option, int64_t value) {
         case ZPX_OPT_TEST_WIDE: c->opt_test_wide = value; return ZPX_OK;
         case ZPX_OPT_PROGRESSIVE_MODE: c->opt_progressive_mode = value; return ZPX_OK;
         case ZPX_OPT_K2_DENSE: c->opt_k2_dense = value; return ZPX_OK;
+        case ZPX_OPT_GATED_SWEEPS:
+            if (value < -1 || value > 8) return ZPX_E_INVALID_ARG;  // (-1: test hook, the rounds count as not converged)
+            c->opt_gated_sweeps = value;
+            return ZPX_OK;
         case ZPX_OPT_NATIVE_PLANES:
             if (value < 0 || value > 2) return ZPX_E_INVALID_ARG;
             c->opt_native = value;
@@ -1938,6 +1983,7 @@ static int32_t decode_batch_pipelined(zpx_ctx* ctx, const uint8_t* const* bufs, 
         sh->opt_native = ctx->opt_native;
         sh->opt_progressive_mode = ctx->opt_progressive_mode;
         sh->opt_k2_dense = ctx->opt_k2_dense;
+        sh->opt_gated_sweeps = ctx->opt_gated_sweeps;
     }
     // chunk list: the first two chunks are a quarter and a half of the regular size, so that the first
     // device->host copy starts early (the pipeline is bound by that copy; its fill time is pure loss)

@@ -230,6 +230,7 @@ struct K1SyncSmem {
 };
 
 __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int sweep) {
+    if (P.gate != nullptr && *P.gate == 0) return;  // (enqueued ahead of time: the previous pass changed nothing)
     extern __shared__ __align__(16) uint8_t k1s_smem[];
     K1SyncSmem& S = *reinterpret_cast<K1SyncSmem*>(k1s_smem);
     const CkStore ck{S.ck + threadIdx.x, S.cn + threadIdx.x, S.cdc + threadIdx.x};
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(K1S_NT) k1s_sync(const K1SParams P, const int 
 // up to 128 different scans here: tables are read in HBM.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(K1S_NT) k1s_fix(const K1SParams P) {
+    if (P.gate != nullptr && *P.gate == 0) return;
     __shared__ uint32_t s_ring[K1_RW * K1S_NT];
     const int g = blockIdx.x * K1S_NT + threadIdx.x;
     const bool valid = g < P.n_warps;

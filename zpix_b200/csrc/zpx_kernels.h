@@ -45,6 +45,7 @@ struct K1SParams {
     int* s_bad;                 //                   1: that decode skipped an invalid code (the write pass then probes
                                 //                   the symbol after the lane's last block, see k1s_write)
     int* changed;               // device flag: an end state crossing a warp boundary changed in this sweep
+    const int* gate;            // NULL, or: the launch has nothing to do unless this flag (the previous pass's `changed`) is set
 };
 cudaError_t k1s_launch_sync(const K1SParams& P, int sweep, cudaStream_t s);
 cudaError_t k1s_launch_fix(const K1SParams& P, cudaStream_t s);
