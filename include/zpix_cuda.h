@@ -210,7 +210,7 @@ int32_t zpx_batch_fetch_rgba(zpx_batch *b, uint8_t *const *out, const size_t *ou
  * device (one more IDCT pass; open the batch with ZPX_OPT_NATIVE_PLANES = 1 or 2 to have the fused kernel write them). */
 int32_t zpx_batch_fetch_native(zpx_batch *b, uint8_t *const *out, int32_t *status);
 /* Final per-image status after decode (header errors, device-detected entropy errors).  Waits for the decode.  Rare
- * corrupt progressive frames (a scan that ends inside an End-Of-Band run) are decoded a second time here, scan by
+ * corrupt frames (a scan that ends inside an End-Of-Band run) are decoded a second time here, scan by
  * scan, before their status is known: consumers of zpx_batch_device_rgba call this first.  (The fetch calls do.) */
 int32_t zpx_batch_status(zpx_batch *b, int32_t *status);
 /* Device pointer of image i's RGBA (GPU-resident hand-off, no D2H); NULL on error. */

@@ -133,17 +133,13 @@ for seed in range(a.first, a.first + a.seeds):
         b.decode()
         outs, st = b.fetch_rgba()
         nats = b.fetch_native()[0] if a.native else None
-        progs = [bool(b.info(i).progressive) for i in range(len(datas))]
     for i, d in enumerate(datas):
         total += 1
-        prog = progs[i]  # (sequential frames with a run across a scan boundary: still refused)
         try:
             img = O.decode(d)
             want, err = img.rgbaPixels(), "ok"
-            if img.eob_carry and not prog:
-                want, err = None, "UnsupportedStream"
         except O.OracleError as e:
-            want, err = None, ("UnsupportedStream" if O.last_eob_carry() and not prog else e.name)
+            want, err = None, e.name
         ovf = O.last_coef_overflow()
         got = jpeg.lib.zpx_error_name(st[i]).decode() if st[i] else "ok"
         if err == "ReferencePanics" or (st[i] == 104 and ovf):

@@ -1014,11 +1014,12 @@ int collect_timing(zpx_batch* b, int di) {
 cudaError_t after_decode(DeviceCtx& dc) { return cudaStreamWaitEvent(dc.stream, dc.ev[3], 0); }
 
 // combine header status, host-side pending errors and the device error records
-// Progressive frames in which a scan ended inside an End-Of-Band run (corrupt streams only).  The reference keeps the
+// Frames in which a scan ended inside an End-Of-Band run (corrupt streams only; in sequential frames the symbol itself is
+// already out of place).  The reference keeps the
 // run in the decoder (decoder.zig:144, reset only at a restart marker :1451), so the next scan starts by skipping
 // blocks; the batch decode runs the scans of a frame level by level, side by side, each from a run of zero, and flags
 // such a frame instead.  Here the flagged frames of one device are decoded again the reference's way: coefficients
-// zeroed, scans launched ONE BY ONE in file order on the general kernel (k3_progressive), the run handed from a scan's
+// zeroed, scans launched ONE BY ONE in file order (k3_progressive; k1_lane_per_interval for sequential frames), the run handed from a scan's
 // last interval to the next scan's first through two words per image (read / written alternately), then reconstructed
 // by the unfused kernels.  Slow (a launch per scan) and rare.
 int rescue_eob_carry(zpx_batch* b, size_t di, const std::vector<uint32_t>& slots) {
@@ -1030,13 +1031,28 @@ int rescue_eob_carry(zpx_batch* b, size_t di, const std::vector<uint32_t>& slots
     const size_t nimg = pl.imgs.size();
     std::vector<char> flagged(nimg, 0);
     for (uint32_t k : slots) flagged[k] = 1;
-    std::vector<std::vector<uint32_t>> per_scan;  // [scan ordinal] -> intervals of the flagged frames
+    std::vector<std::vector<uint32_t>> per_scan;  // [scan ordinal] -> intervals of the flagged progressive frames
+    // sequential frames (several scans, End-Of-Band-run symbols in their tables: k1_lane_per_interval): per scan the
+    // contiguous range of its intervals, one launch each
+    struct Range { uint32_t first, last, count; };
+    std::vector<std::map<uint32_t, Range>> seq_scan;  // [scan ordinal][image slot]
     for (uint32_t i = 0; i < (uint32_t)pl.ivs.size(); i++) {
         const ZpxScanDev& sc = pl.scans[pl.ivs[i].scan];
         if (!flagged[sc.img]) continue;
-        if (per_scan.size() <= (size_t)sc.scan_index) per_scan.resize((size_t)sc.scan_index + 1);
-        per_scan[(size_t)sc.scan_index].push_back(i);
+        const size_t so = (size_t)sc.scan_index;
+        if (pl.imgs[sc.img].progressive) {
+            if (per_scan.size() <= so) per_scan.resize(so + 1);
+            per_scan[so].push_back(i);
+        } else {
+            if (seq_scan.size() <= so) seq_scan.resize(so + 1);
+            auto it = seq_scan[so].find(sc.img);
+            if (it == seq_scan[so].end()) seq_scan[so][sc.img] = Range{i, i, 1};
+            else { it->second.first = std::min(it->second.first, i); it->second.last = std::max(it->second.last, i); it->second.count++; }
+        }
     }
+    for (const auto& m : seq_scan)
+        for (const auto& kv : m)
+            if (kv.second.last - kv.second.first + 1 != kv.second.count) return ZPX_OK;  // (not contiguous: leave the frames refused)
     size_t max_list = slots.size();
     for (const auto& l : per_scan) max_list = std::max(max_list, l.size());
     CU(ctx, dc.carry.ensure(2 * nimg * sizeof(uint32_t)));
@@ -1067,13 +1083,23 @@ int rescue_eob_carry(zpx_batch* b, size_t di, const std::vector<uint32_t>& slots
     k1.status = (unsigned long long*)dc.status.p;
     k1.img_flags = (uint32_t*)((uint8_t*)dc.status.p + align_up(nimg * sizeof(unsigned long long), 256));
     uint32_t* cw = (uint32_t*)dc.carry.p;
-    for (size_t s = 0; s < per_scan.size(); s++) {
-        if (per_scan[s].empty()) continue;
+    for (size_t s = 0; s < std::max(per_scan.size(), seq_scan.size()); s++) {
         k1.eob_in = cw + (s & 1) * nimg;
         k1.eob_out = cw + ((s + 1) & 1) * nimg;
-        CU(ctx, cudaMemcpyAsync(dc.late_list.p, per_scan[s].data(), per_scan[s].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        CU(ctx, k3_launch_progressive(k1, (const uint32_t*)dc.late_list.p, (int)per_scan[s].size(), st));
-        ctx->launches++;
+        if (s < per_scan.size() && !per_scan[s].empty()) {
+            CU(ctx, cudaMemcpyAsync(dc.late_list.p, per_scan[s].data(), per_scan[s].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            CU(ctx, k3_launch_progressive(k1, (const uint32_t*)dc.late_list.p, (int)per_scan[s].size(), st));
+            ctx->launches++;
+        }
+        if (s < seq_scan.size()) {
+            for (const auto& kv : seq_scan[s]) {
+                K1Params kl = k1;
+                kl.ivs = k1.ivs + kv.second.first;
+                kl.n_iv = (int)kv.second.count;
+                CU(ctx, k1_launch_lane_per_interval(kl, dc.sm_count, st));
+                ctx->launches++;
+            }
+        }
     }
     // reconstruction (dequantise + IDCT -> planes -> colour) of those frames
     K2GParams kg{};
@@ -1139,8 +1165,7 @@ int finalize_status(zpx_batch* b) {
         {
             std::vector<uint32_t> carry;
             for (size_t k = 0; k < pl.images.size(); k++)
-                if (hs[k] != ZPX_STATUS_NONE && (int)(hs[k] & 0xff) == ZPX_E_UNSUPPORTED_STREAM && b->parsed[pl.images[k]].progressive)
-                    carry.push_back((uint32_t)k);
+                if (hs[k] != ZPX_STATUS_NONE && (int)(hs[k] & 0xff) == ZPX_E_UNSUPPORTED_STREAM) carry.push_back((uint32_t)k);
             if (!carry.empty() && !getenv("ZPX_NO_EOB_RESCUE")) {
                 int e = rescue_eob_carry(b, di, carry);
                 if (e) return e;

@@ -146,6 +146,9 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
 
     int dc0 = st.dc0, dc1 = st.dc1, dc2 = st.dc2, dc3 = st.dc3;
     uint32_t eob_run = 0;
+    // (serial re-decode, zpx_api.cu rescue_eob_carry: the scan's first interval starts with the End-Of-Band run the scan
+    // before it left open, decoder.zig:144)
+    if (!SUB && P.eob_in != nullptr && iv.ordinal == 0 && st.count != 0) eob_run = P.eob_in[im->status_slot] & 0xffffu;
     int wide = 0;  // >= 13: some coefficient of the lane lies outside [-4096, 4095]
     const uint32_t total = st.count;
     uint32_t left = total;  // blocks still to decode (including the current one)
@@ -342,8 +345,13 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     // every scan starts from zero, so a run that is still open when a scan ends (corrupt streams only) would
     // make the next scan differ: refuse the image instead.
     if (wide >= 13) atomicOr(&P.img_flags[im->status_slot], 1u);  // a coefficient outside [-4096, 4095]
-    if (!SUB && st.count != 0 && (iv.flags & 2u) && eob_run != 0)
-        report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + iv.n_blocks, ZPX_E_UNSUPPORTED_STREAM);
+    if (!SUB && st.count != 0 && (iv.flags & 2u)) {
+        if (P.eob_out != nullptr) {
+            if (left == 0) P.eob_out[im->status_slot] = eob_run;  // (a lane that stopped at an error hands nothing on)
+        } else if (eob_run != 0) {
+            report(P.status, im->status_slot, sc->scan_index, (uint64_t)iv.first_block + iv.n_blocks, ZPX_E_UNSUPPORTED_STREAM);
+        }
+    }
 }
 
 // Dynamic shared memory of the write kernels
