@@ -106,10 +106,11 @@ extern "C" {
 #define ZPX_E_INVALID_ARG 102
 #define ZPX_E_BAD_STATE 103     /* calls made in the wrong order for this batch */
 #define ZPX_E_COEF_RANGE 104    /* a coefficient does not fit int16 (non-conforming 8-bit stream) */
-#define ZPX_E_UNSUPPORTED_STREAM 105 /* stream shape this build does not decode on the GPU: an End-Of-Band run
-                                        in a self-synchronising sequential scan, or one left open across a scan
-                                        boundary (the reference's eob_run survives scans, decoder.zig:144/:1451);
-                                        both only occur in corrupt files */
+#define ZPX_E_UNSUPPORTED_STREAM 105 /* reserved.  The kernels use it internally to flag a frame in which a scan ends
+                                        inside an End-Of-Band run (the reference's eob_run survives scans,
+                                        decoder.zig:144/:1451; corrupt files only); the status / fetch calls decode
+                                        such frames again, scan by scan with the run carried, and report what the
+                                        reference reports */
 #define ZPX_E_MALFORMED_TABLE 106    /* DHT on which the reference itself panics (over-subscribed code) */
 
 /* ---- image variants jpeg.load returns (src/image/image.zig:24-33) ------- */
