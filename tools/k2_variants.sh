@@ -18,6 +18,6 @@ for v in $2; do
     cp $d/zpix_b200/libzpixcuda.so $so
     echo "built $so"
   else
-    echo "== $v"; ZPX_LIB_PATH=$PWD/$so python tools/k2_time.py
+    echo "== $v"; ZPX_LIB_PATH=$PWD/$so python ${ZPX_PROBE:-tools/k2_time.py}
   fi
 done
