@@ -20,6 +20,10 @@
 #include "zpx_internal.h"
 #include "zpx_kernels.h"
 
+#ifndef ZPX_WINDOW_LOP3
+#define ZPX_WINDOW_LOP3 1
+#endif
+
 namespace zpx {
 
 constexpr int K1_MAXSLOTS = 256;  // lanes with a stream ("slots") per CTA, at most
@@ -157,8 +161,15 @@ struct Window {
     __device__ __forceinline__ void advance(const RingReader<RS>& rd, uint32_t from, uint32_t tot) {
         const uint32_t t = (from & 31u) + tot;
         const uint32_t m = (uint32_t)((int)(t << 26) >> 31);
+#if ZPX_WINDOW_LOP3
+        // one three-input logic instruction per word: (next & m) | (this & ~m)  (the compiler builds it from a compare, a
+        // select and a two-input LOP3, all three on the position's dependency chain)
+        asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(w0) : "r"(w0), "r"(w1), "r"(m));
+        asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(w1) : "r"(w1), "r"(w2), "r"(m));
+#else
         w0 = (w1 & m) | (w0 & ~m);
         w1 = (w2 & m) | (w1 & ~m);
+#endif
         a2 += m & (uint32_t)RS;
         if (a2 == rd.ring + K1_RW * RS) a2 = rd.ring;
         w2 = lds_u32(a2);
