@@ -27,6 +27,9 @@
 
 #include "zpx_k1_common.cuh"
 
+#ifndef ZPX_K1_ONE_SELECT
+#define ZPX_K1_ONE_SELECT 1
+#endif
 #ifndef ZPX_K1_VOTE_EVERY
 #define ZPX_K1_VOTE_EVERY 2
 #endif
@@ -210,7 +213,14 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
                 else e0 = __ldg(gac + (hi >> (32 - ZPX_LUT_BITS)));
                 const bool act = k <= 63;
                 const bool rare = act && (int)e0 <= 0;
+#if ZPX_K1_ONE_SELECT
+                // (one select on the chain between the table look-up and the entry's fields: "block open" is known early)
+                uint32_t e;
+                asm("{ .reg .pred q, p; setp.ne.s32 q, %2, 0; setp.gt.and.s32 p, %1, 0, q; selp.b32 %0, %1, %3, p; }"
+                    : "=r"(e) : "r"(e0), "r"((int)act), "r"(K1_NULL_E));
+#else
                 const uint32_t e = (act && (int)e0 > 0) ? e0 : K1_NULL_E;
+#endif
                 {
                     const int len = fe_len(e), s32 = fe_s32(e);
                     int tot = fe_tot(e);
