@@ -36,6 +36,11 @@
 
 namespace zpx {
 
+// The run a scan's first interval starts with in the serial re-decode (never in the batch decode).  Out of line on
+// purpose: inlined, the load shared a scoreboard with the ring's prefetch load and every block's first test of eob_run
+// waited for that prefetch (long-scoreboard stalls 0.20 -> 0.51 per issue, ncu) although the load itself never ran.
+static __device__ __noinline__ uint32_t k1_carry_in(const uint32_t* p) { return *p & 0xffffu; }
+
 // slow-path wrapper shared by the DC and AC steps: returns the entry fields, sets err / eob_run / wide
 template <bool SMEM>
 __device__ __forceinline__ uint32_t k1_rare(const K1Params& P, uint32_t hi, bool isdc, uint32_t e, const uint4& bi, uint32_t tb,
@@ -155,7 +160,7 @@ __device__ __forceinline__ void k1_lane_loop(const K1Params& P, const ZpxInterva
     uint32_t eob_run = 0;
     // (serial re-decode, zpx_api.cu rescue_eob_carry: the scan's first interval starts with the End-Of-Band run the scan
     // before it left open, decoder.zig:144)
-    if (!SUB && P.eob_in != nullptr && iv.ordinal == 0 && st.count != 0) eob_run = P.eob_in[im->status_slot] & 0xffffu;
+    if (!SUB && P.eob_in != nullptr && iv.ordinal == 0 && st.count != 0) eob_run = k1_carry_in(P.eob_in + im->status_slot);
     int wide = 0;  // >= 13: some coefficient of the lane lies outside [-4096, 4095]
     const uint32_t total = st.count;
     uint32_t left = total;  // blocks still to decode (including the current one)

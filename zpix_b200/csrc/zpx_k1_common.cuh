@@ -21,7 +21,7 @@
 #include "zpx_kernels.h"
 
 #ifndef ZPX_WINDOW_LOP3
-#define ZPX_WINDOW_LOP3 1
+#define ZPX_WINDOW_LOP3 2
 #endif
 
 namespace zpx {
@@ -160,6 +160,16 @@ struct Window {
     // (then the registers move up and w2 is the next ring word; otherwise w2 is simply read again)
     __device__ __forceinline__ void advance(const RingReader<RS>& rd, uint32_t from, uint32_t tot) {
         const uint32_t t = (from & 31u) + tot;
+#if ZPX_WINDOW_LOP3 == 2
+        // predicate form: compare + selects (one dependent operation less than shift, shift, LOP3)
+        const bool cross = t >= 32u;
+        w0 = cross ? w1 : w0;
+        w1 = cross ? w2 : w1;
+        a2 += cross ? (uint32_t)RS : 0u;
+        if (a2 == rd.ring + K1_RW * RS) a2 = rd.ring;
+        w2 = lds_u32(a2);
+        return;
+#endif
         const uint32_t m = (uint32_t)((int)(t << 26) >> 31);
 #if ZPX_WINDOW_LOP3
         // one three-input logic instruction per word: (next & m) | (this & ~m)  (the compiler builds it from a compare, a
