@@ -130,6 +130,9 @@ __device__ __forceinline__ int extend32(uint32_t hi, int len, int size) {
 
 }  // namespace
 
+// (see k1_carry_in, zpx_k1.cu: an inlined load here would share a scoreboard with the stream loads)
+static __device__ __noinline__ uint32_t k3_carry_in(const uint32_t* p) { return *p; }
+
 __global__ void __launch_bounds__(K3_NT, 5) k3_progressive(const K1Params P, const uint32_t* __restrict__ list, const int n_list) {
     __shared__ __align__(16) WarpSm s_w[K3_WARPS];
     __shared__ uint8_t s_unzig[64];
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(K3_NT, 5) k3_progressive(const K1Params P, con
     uint32_t eob_run = 0;
     // (serial re-decode: the reference keeps the run across scans, decoder.zig:144 -- the scan's first interval starts
     // with what the previous scan left; a restart marker resets it, :1451)
-    if (P.eob_in != nullptr && iv.ordinal == 0) eob_run = P.eob_in[im->status_slot];
+    if (P.eob_in != nullptr && iv.ordinal == 0) eob_run = k3_carry_in(P.eob_in + im->status_slot);  // (out of line: zpx_k1.cu)
     // refinement batch
     uint32_t bj0 = 0, bn = 0, bk = 0;   // batch = blocks [bj0, bj0+bn), bk done
     short pre[2 * K3_BATCH];             // prefetched coefficients of the next batch: zig-zag lane, lane+32
