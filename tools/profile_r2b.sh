@@ -12,6 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
 Q="python tools/quick_bench.py --n 1024 --distinct 64 --iters 1"
 $Q > $O/r2b_qb_cfg2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"k2_fused" -c 1 -o $O/r2b_cfg2_k2 -f $Q > $O/r2b_ncu_cfg2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k1_lane" -c 1 -o $O/r2b_cfg2_k1 -f $Q > $O/r2b_ncu_cfg2_k1.log 2>&1
 Q4="python tools/quick_bench.py --n 128 --distinct 16 --w 3840 --h 2160 --sub 4:2:2 --iters 1"
 $Q4 > $O/r2b_qb_cfg4.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"k2_fused" -c 1 -o $O/r2b_cfg4_k2 -f $Q4 > $O/r2b_ncu_cfg4.log 2>&1
