@@ -38,7 +38,8 @@ namespace zpx {
 
 // The run a scan's first interval starts with in the serial re-decode (never in the batch decode).  Out of line on
 // purpose: inlined, the load shared a scoreboard with the ring's prefetch load and every block's first test of eob_run
-// waited for that prefetch (long-scoreboard stalls 0.20 -> 0.51 per issue, ncu) although the load itself never ran.
+// waited for that prefetch (long-scoreboard stalls 0.20 -> 0.51 per issue, ncu; 0.31 with this) although the load itself
+// never ran.
 static __device__ __noinline__ uint32_t k1_carry_in(const uint32_t* p) { return *p & 0xffffu; }
 
 // slow-path wrapper shared by the DC and AC steps: returns the entry fields, sets err / eob_run / wide
