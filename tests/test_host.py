@@ -234,6 +234,16 @@ def test_unstuffing_plan_covers_every_interval(zlib, fixtures_dir):
         assert rep.pieces_ok == 1
 
 
+def test_unstuffing_kernel_index_logic_model():
+    """device side of k0_unstuff, without a GPU: tools/k0_model.py restates the kernel's index logic lane by lane
+    (linear output buffer, leftover move, shared head / tail vectors, boundary steps, zero padding of an interval's
+    last piece) and compares it with a plain FF 00 -> FF replacement on random pieces of random alignment"""
+    from tools import k0_model
+
+    for seed in range(300):
+        k0_model.test(seed)
+
+
 def test_progressive_scan_script_classification(zlib, fixtures_dir):
     """Which progressive frames may take the lane-per-scan kernels (they apply correction bits as blind adds and keep
     the non-zero history in bit maps): every reference fixture (libjpeg's scripts) does; a frame whose script repeats a

@@ -10,14 +10,20 @@
 // Work unit: one warp per piece (ZpxSegDev: about 16 KB of raw bytes of one interval, cut by the host where no
 // FF 00 pair is split; the host also knows how many pairs precede the piece, i.e. where its output starts).
 // A round moves 512 raw bytes: coalesced 16-byte loads into shared memory, then 4 steps in which lane l looks
-// at word 32 k + l (conflict-free; stuffed bytes found with byte-parallel arithmetic), ballots + popc give its
-// output position, and the kept bytes go to a 1 KB output ring from which complete 16-byte vectors are stored to
-// HBM; head and tail bytes that share a vector with the neighbouring piece are stored one by one.  Reads and
-// writes every entropy-coded byte once.
+// at word 32 k + l and the word before it (conflict-free; the previous round's last word sits in the word in front
+// of the staging area).  A byte is dropped iff (byte | ~predecessor) == 0 -- one exact zero-byte test per word,
+// byte-parallel.  Three steps out of four have nothing to drop (a warp vote) and store their four bytes per lane
+// straight; otherwise ballots + popc give each lane its output position.  The kept bytes go to a LINEAR buffer:
+// complete 16-byte vectors are stored to HBM after every round and the < 16 bytes left over move to its start, so a
+// step's byte stores share one address register and there is no ring mask.  Whether a step lies entirely inside the
+// piece is decided per round for interior rounds and per 128-byte step otherwise (a 6 KB interval has two boundary
+// steps, not eight).  Head and tail bytes that share a vector with the neighbouring piece are stored one by one.
+// Reads and writes every entropy-coded byte once.  (The first form of this kernel -- 1 KB output ring, two
+// zero-byte tests per word, per-round boundary handling -- took 0.32 ms on cfg2, this one 0.24 ms; 0.14 ms is the
+// traffic at the measured HBM peak.)  tools/k0_model.py is a lane-by-lane Python model of the index logic, checked
+// against a plain unstuffing on random pieces (tests/test_host.py).
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
-
 #include <type_traits>
 
 #include "zpx_internal.h"
@@ -28,124 +34,6 @@ namespace zpx {
 constexpr int K0_WARPS = 4;
 
 __global__ void __launch_bounds__(K0_WARPS * 32) k0_unstuff(const uint8_t* __restrict__ blob, uint8_t* __restrict__ ublob,
-                                                            const ZpxSegDev* __restrict__ segs, const int n_segs) {
-    __shared__ __align__(16) uint8_t s_in[K0_WARPS][512];
-    __shared__ __align__(16) uint8_t s_out[K0_WARPS][1024];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gid = blockIdx.x * K0_WARPS + warp;
-    if (gid >= n_segs) return;  // whole warps
-    const ZpxSegDev sg = segs[gid];
-    uint8_t* in = s_in[warp];
-    uint8_t* out = s_out[warp];
-    const uint64_t a0 = sg.src & ~(uint64_t)15;
-    const uint32_t m = (uint32_t)(sg.dst & 15u);
-    uint8_t* gbase = ublob + (sg.dst - m);   // 16-byte aligned; ring position p <-> gbase + p
-    uint32_t wpos = m, flushed = 0;          // bytes produced / bytes stored (flushed is a multiple of 16)
-    int rel0 = -(int)(sg.src - a0);          // (offset of the round's first byte) - src
-    const uint32_t lt = (1u << lane) - 1u;
-
-    auto flush_full = [&]() {
-        const uint32_t nvec = (wpos - flushed) >> 4;
-        for (uint32_t v0 = 0; v0 < nvec; v0 += 32) {
-            const uint32_t v = v0 + lane;
-            if (v < nvec) {
-                const uint32_t off = flushed + 16u * v;
-                if (off == 0 && m != 0) {
-                    // the first vector is shared with the piece before this one: only bytes m..15 are ours
-                    for (uint32_t b = m; b < 16; b++) gbase[b] = out[b];
-                } else {
-                    *reinterpret_cast<uint4*>(gbase + off) = *reinterpret_cast<const uint4*>(out + (off & 1023u));
-                }
-            }
-        }
-        flushed += nvec << 4;
-    };
-
-    uint32_t prev_lastw = 0;  // last raw word of the previous round
-    for (uint64_t base = a0; base < sg.src + sg.len; base += 512, rel0 += 512) {
-        const uint64_t my = base + 16u * (uint32_t)lane;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (my < sg.src + sg.len) v = __ldg(reinterpret_cast<const uint4*>(blob + my));
-        reinterpret_cast<uint4*>(in)[lane] = v;
-        __syncwarp();
-        // a round whose 512 bytes all belong to the piece, the first one not being the piece's first byte
-        const bool interior = rel0 >= 1 && rel0 + 512 <= (int)sg.len;
-        // four steps of 128 bytes; lane l looks at word 32 k + l (conflict-free) and the word before it
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int w = 32 * k + lane;
-            const uint32_t x = reinterpret_cast<const uint32_t*>(in)[w];
-            const uint32_t pw = (k > 0 || lane > 0) ? reinterpret_cast<const uint32_t*>(in)[w > 0 ? w - 1 : 0] : prev_lastw;
-            const uint32_t ny = ~__funnelshift_l(pw, x, 8);  // byte i = ~(the byte before byte i of x)
-            // 0x80 in every byte of x that is 0x00 and whose predecessor is 0xFF: the 0x00 of an FF 00 pair
-            // (exact per byte: no carries between bytes)
-            const uint32_t drop = ~((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) | (((ny & 0x7f7f7f7fu) + 0x7f7f7f7fu) | ny) | 0x7f7f7f7fu);
-            if (interior && !__any_sync(0xffffffffu, drop != 0)) {
-                // nothing to remove in these 128 bytes (three steps out of four)
-                const uint32_t o = wpos + 4u * (uint32_t)lane;
-                out[o & 1023u] = (uint8_t)x;
-                out[(o + 1) & 1023u] = (uint8_t)(x >> 8);
-                out[(o + 2) & 1023u] = (uint8_t)(x >> 16);
-                out[(o + 3) & 1023u] = (uint8_t)(x >> 24);
-                wpos += 128u;
-            } else if (interior) {
-                // some words of these 128 bytes lose one or two bytes
-                const int ngone = __popc(drop);
-                const uint32_t b1 = __ballot_sync(0xffffffffu, ngone >= 1), b2 = __ballot_sync(0xffffffffu, ngone >= 2);
-                uint32_t o = wpos + 4u * (uint32_t)lane - (uint32_t)(__popc(b1 & lt) + __popc(b2 & lt));
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (!(drop & (0x80u << (8 * i)))) out[(o++) & 1023u] = (uint8_t)(x >> (8 * i));
-                wpos += 128u - (uint32_t)(__popc(b1) + __popc(b2));
-            } else {
-                // first / last round of the piece: bytes outside [0, len) are not kept either; the piece's first
-                // byte is never a stuffed 0x00 (its predecessor is not part of the piece)
-                const int rel = rel0 + 4 * w;
-                uint32_t gone = drop;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (rel + i == 0) gone &= ~(0x80u << (8 * i));
-                    if (rel + i < 0 || rel + i >= (int)sg.len) gone |= 0x80u << (8 * i);
-                }
-                const int ngone = __popc(gone);
-                // kept bytes before this lane's word = 4 * lane - bytes gone in the lanes below
-                const uint32_t b1 = __ballot_sync(0xffffffffu, ngone >= 1), b2 = __ballot_sync(0xffffffffu, ngone >= 2);
-                const uint32_t b3 = __ballot_sync(0xffffffffu, ngone >= 3), b4 = __ballot_sync(0xffffffffu, ngone >= 4);
-                uint32_t o = wpos + 4u * (uint32_t)lane - (uint32_t)(__popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt) + __popc(b4 & lt));
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (!(gone & (0x80u << (8 * i)))) out[(o++) & 1023u] = (uint8_t)(x >> (8 * i));
-                wpos += 128u - (uint32_t)(__popc(b1) + __popc(b2) + __popc(b3) + __popc(b4));
-            }
-        }
-        prev_lastw = reinterpret_cast<const uint32_t*>(in)[127];
-        __syncwarp();
-        flush_full();
-        __syncwarp();
-    }
-    if (sg.flags & 1u) {
-        // last piece of its interval: zeros up to the next 16-byte boundary (K1 reads whole 16-byte chunks)
-        const uint32_t padn = (16u - (wpos & 15u)) & 15u;
-        if ((uint32_t)lane < padn) out[(wpos + lane) & 1023u] = 0;
-        wpos += padn;
-        __syncwarp();
-        flush_full();
-    }
-    // bytes of the last, incomplete vector (the piece after this one owns the rest of it)
-    const uint32_t rest = wpos - flushed;
-    if ((uint32_t)lane < rest && !(flushed == 0 && (uint32_t)lane < m)) gbase[flushed + lane] = out[(flushed + lane) & 1023u];
-}
-
-// Second form of the same pass (the default; the first stays behind ZPX_K0_V1=1 for A/B runs).  Same work unit,
-// same round of 512 raw bytes in four steps of one word per lane; what changed is the bookkeeping around it:
-//  * the kept bytes go to a LINEAR buffer (the < 16 bytes that do not fill a vector move to its start after every
-//    round), so a step's four byte stores share one address register and there is no ring mask;
-//  * a byte is dropped iff (byte | ~predecessor) == 0: one exact zero-byte test per word instead of two;
-//  * the word before a lane's word always comes from shared memory (the previous round's last word sits in the
-//    word in front of the staging area), no select;
-//  * "interior" is decided per 128-byte step, not per round: a piece of one 6 KB interval has 2 boundary steps
-//    instead of 8.
-__global__ void __launch_bounds__(K0_WARPS * 32) k0_unstuff2(const uint8_t* __restrict__ blob, uint8_t* __restrict__ ublob,
                                                              const ZpxSegDev* __restrict__ segs, const int n_segs) {
     __shared__ __align__(16) uint8_t s_in[K0_WARPS][16 + 512];
     __shared__ __align__(16) uint8_t s_out[K0_WARPS][16 + 512 + 16];
@@ -265,10 +153,7 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_unstuff2(const uint8_t* __re
 
 cudaError_t k0_launch_unstuff(const uint8_t* blob, uint8_t* ublob, const ZpxSegDev* segs, int n_segs, cudaStream_t s) {
     if (n_segs <= 0) return cudaSuccess;
-    static const bool v1 = [] { const char* e = getenv("ZPX_K0_V1"); return e && e[0] == '1'; }();
-    const int grid = (n_segs + K0_WARPS - 1) / K0_WARPS;
-    if (v1) k0_unstuff<<<grid, K0_WARPS * 32, 0, s>>>(blob, ublob, segs, n_segs);
-    else k0_unstuff2<<<grid, K0_WARPS * 32, 0, s>>>(blob, ublob, segs, n_segs);
+    k0_unstuff<<<(n_segs + K0_WARPS - 1) / K0_WARPS, K0_WARPS * 32, 0, s>>>(blob, ublob, segs, n_segs);
     return cudaGetLastError();
 }
 
