@@ -31,7 +31,14 @@
 
 namespace zpx {
 
-constexpr int K0_WARPS = 4;
+#ifndef ZPX_K0_PREFETCH
+#define ZPX_K0_PREFETCH 1
+#endif
+#ifndef ZPX_K0_WARPS
+#define ZPX_K0_WARPS 4
+#endif
+
+constexpr int K0_WARPS = ZPX_K0_WARPS;
 
 __global__ void __launch_bounds__(K0_WARPS * 32) k0_unstuff(const uint8_t* __restrict__ blob, uint8_t* __restrict__ ublob,
                                                              const ZpxSegDev* __restrict__ segs, const int n_segs) {
@@ -105,9 +112,17 @@ __global__ void __launch_bounds__(K0_WARPS * 32) k0_unstuff(const uint8_t* __res
         // (else: a step after the piece's last byte)
     };
 
+    // the next round's 16 bytes are loaded while this round is worked on (one round of latency hidden per warp)
+    uint4 vn = make_uint4(0u, 0u, 0u, 0u);
+    if (ZPX_K0_PREFETCH && -(int)(sg.src - a0) + 16 * lane < len) vn = __ldg(reinterpret_cast<const uint4*>(gin));
     for (int rel0 = -(int)(sg.src - a0); rel0 < max(len, 1); rel0 += 512, gin += 512) {
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (rel0 + 16 * lane < len) v = __ldg(reinterpret_cast<const uint4*>(gin));
+        uint4 v = vn;
+        if (ZPX_K0_PREFETCH) {
+            vn = make_uint4(0u, 0u, 0u, 0u);
+            if (rel0 + 512 + 16 * lane < len) vn = __ldg(reinterpret_cast<const uint4*>(gin + 512));
+        } else if (rel0 + 16 * lane < len) {
+            v = __ldg(reinterpret_cast<const uint4*>(gin));
+        }
         reinterpret_cast<uint4*>(in)[lane] = v;
         if (lane == 31) reinterpret_cast<uint32_t*>(in)[-1] = carry;
         carry = v.w;
