@@ -242,6 +242,8 @@ def test_unstuffing_kernel_index_logic_model():
 
     for seed in range(300):
         k0_model.test(seed)
+    for seed in range(4):  # intervals of 6 - 40 KB cut at the product's piece size
+        k0_model.test(seed, big=True)
 
 
 def test_progressive_scan_script_classification(zlib, fixtures_dir):

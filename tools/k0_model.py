@@ -104,13 +104,14 @@ def make_interval(rng, n):
         else: b.append(rng.randrange(0, 255))
     return bytes(b)
 
-def test(seed):
+def test(seed, big=False):
     rng = random.Random(seed)
     pre = rng.randrange(0, 40)
-    ivs = [make_interval(rng, rng.choice([1, 2, 5, 15, 16, 17, 100, 127, 128, 129, 500, 511, 512, 513, 640, 1024, 3000])) for _ in range(rng.randrange(1, 5))]
+    sizes = [1, 2, 5, 15, 16, 17, 100, 127, 128, 129, 500, 511, 512, 513, 640, 1024, 3000] if not big else [6400, 16383, 16385, 40000]
+    ivs = [make_interval(rng, rng.choice(sizes)) for _ in range(rng.randrange(1, 5))]
     blob = bytearray(rng.randbytes(pre))
     pieces, dstpos, exp = [], 0, bytearray()
-    seg = rng.choice([64, 200, 512, 1000, 4000])
+    seg = rng.choice([64, 200, 512, 1000, 4000]) if not big else 16384  # (ZPX_SEG_BYTES)
     for iv in ivs:
         src0 = len(blob); blob += iv; blob += rng.randbytes(rng.randrange(0, 7))
         ustart = dstpos
@@ -140,4 +141,5 @@ def test(seed):
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     for s in range(n): test(s)
+    for s in range(max(1, n // 50)): test(s, big=True)
     print("ok", n)
